@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s of the GNGF hot path (forward + loss + backward + Adam) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+One "step" = one pass of the hot path over one batch of synthetic coordinates:
+GeneralNeuralGaugeFields.forward (models.py:394-484) -> the reference's loss assembly (utils.py:78-174,
+functions.py:243-245) -> backward -> Adam (functions.py:96-127).  The default workload is BASELINE.json
+configs[1] ("cfg2": the shape of strawberry.jpeg with grid-search ID 4061: P = 57 404 pixels per batch, L = 4
+levels n = [8,12,20,32], T = 256 slots, K = 4, F = 2, HPD 2-32-64-128-256, decoder 8-64-64-3) on synthetic data
+(pixel-lattice coordinates in a seeded random order, uniform random targets, random-init weights).
+
+JSON line (rank 0): see README/DESIGN.md.  `value` is device time with inputs resident in HBM (CUDA events per
+step, L2 flushed between steps); `e2e` is the same step driven through the module API with HOST (pinned)
+inputs copied in and the loss read back every step; `roofline` describes the dominant kernel of the step;
+`cpu_baseline` is the oracle port (numpy restatement of the reference) timed on this box's host cores.
+`--impl reference` times that CPU port alone (the reference is PyTorch-on-CPU code that cannot travel to the
+GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: strawberry.jpeg + param ID 4061 (README.md:15-18, params.py:26-51)
+    "cfg2": dict(P=57404, L=4, n_min=8, n_max=32, T=256, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
+                 lattice_hw=(508, 339), topk_only=False, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
+                 lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6)),
+}
+
+
+def make_inputs(w, seed, rank=0):
+    """Synthetic batch of the workload's shape: coordinates are pixel-lattice points (row, col)/(max(h,w)-1) as in
+    main.py:42-51, drawn without replacement in a seeded random order; targets uniform in [0,1)."""
+    h, wd = w["lattice_hw"]
+    rng = np.random.default_rng(seed + 7919 * rank)
+    flat = rng.permutation(h * wd)[: w["P"]]
+    x = np.stack([flat // wd, flat % wd], 1).astype(np.float32) / np.float32(max(h, wd) - 1)
+    y = rng.random((w["P"], 3), dtype=np.float32)
+    return x, y
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy restatement of the reference), forward + loss + backward + Adam
+# ------------------------------------------------------------------------------------------------------------
+def cpu_port_step_factory(w, sample_P, seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gngf_oracle as O
+    rng = np.random.default_rng(seed)
+    n_ls = O.level_resolutions(w["n_min"], w["n_max"], w["L"])
+    widths = [2, *w["hpd"], w["T"]]
+    mw = [w["L"] * w["F"], *w["mlp"], 3]
+
+    def lin(i, o):
+        b = 1 / np.sqrt(i)
+        return rng.uniform(-b, b, (o, i)).astype(np.float32), rng.uniform(-b, b, o).astype(np.float32)
+
+    hp = [lin(widths[i], widths[i + 1]) for i in range(len(widths) - 1)]
+    ml = [lin(mw[i], mw[i + 1]) for i in range(len(mw) - 1)]
+    params = {"hpd_w": [a for a, _ in hp], "hpd_b": [b for _, b in hp],
+              "tables": [rng.uniform(-1e-4, 1e-4, (w["T"], w["F"])).astype(np.float32) for _ in range(w["L"])],
+              "mlp_w": [a for a, _ in ml], "mlp_b": [b for _, b in ml]}
+    cfg = {"n_ls": n_ls, "table_size": w["T"], "topk_k": w["K"], "mix_mode": True, "use_hash": False,
+           "leaky": False, "topk_only": w["topk_only"]}
+    lcfg = {k: w[k] for k in ("gamma", "epsilon", "l_mse", "l_js_kl")}
+    ws = dict(w, P=sample_P)
+    x, y = make_inputs(ws, seed)
+    adam = {}
+
+    def step():
+        fwd = O.gngf_forward(params, x, cfg)
+        total, _, _, _ = O.total_loss(fwd["rgb"], y, fwd["pbar"], w["gamma"], w["epsilon"], w["l_mse"], w["l_js_kl"], 0.0)
+        grads = O.gngf_backward(params, x, y, cfg, fwd, lcfg)
+        for key in ("hpd_w", "hpd_b", "tables", "mlp_w", "mlp_b"):           # Adam, functions.py:96-127
+            for i, (p, g) in enumerate(zip(params[key], grads[key])):
+                m, v, t = adam.get((key, i), (np.zeros_like(p), np.zeros_like(p), 0))
+                t += 1
+                m = 0.9 * m + 0.1 * g
+                v = 0.99 * v + 0.01 * g * g
+                p -= 1e-3 * (m / (1 - 0.9 ** t)) / (np.sqrt(v / (1 - 0.99 ** t)) + 1e-15)
+                adam[(key, i)] = (m, v, t)
+        return float(total)
+
+    return step
+
+
+def time_cpu_port(w, sample_P, seed, steps, warmup):
+    step = cpu_port_step_factory(w, sample_P, seed)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        n = os.cpu_count() or 1
+    return int(n)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class CallProfiler:
+    """Times every C-ABI call with CUDA events on the launching stream (installed as _lib.PROFILER)."""
+
+    def __init__(self, torch):
+        self.torch, self.events = torch, []
+
+    def record(self, name, fn, args):
+        a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        self.events.append((name, args, a, b))
+        return rc
+
+    def summary(self):
+        self.torch.cuda.synchronize()
+        agg = {}
+        for name, args, a, b in self.events:
+            key = (name, cost_key(name, args))
+            t, n = agg.get(key, (0.0, 0))
+            agg[key] = (t + a.elapsed_time(b), n + 1)
+        return agg
+
+
+def cost_key(name, args):
+    """Shape signature of a call -> used to attach algorithmic bytes / FLOPs."""
+    if name == "gngf_linear_fwd":
+        return tuple(int(v) for v in args[3:6])
+    if name == "gngf_linear_bwd":
+        return tuple(int(v) for v in args[3:6]) + (args[7] is not None,)
+    return ()
+
+
+def algorithmic_cost(name, key, w, lat):
+    """(bound, amount per launch, unit): ALGORITHMIC bytes (hbm) or FLOPs (tensor) of one launch."""
+    P, L, F, K, T = w["P"], w["L"], w["F"], w["K"], w["T"]
+    U, S = lat.num_nodes, lat.num_level_nodes
+    if name == "gngf_linear_fwd":
+        M, N, Kd = key
+        return "tensor", 2.0 * M * N * Kd
+    if name == "gngf_linear_bwd":
+        M, N, Kd, has_dx = key
+        return "tensor", 2.0 * M * N * Kd * (2 if has_dx else 1)
+    table = {
+        # per point: x (8) + per level 4 node-feature gathers (4*F*4) + enc row (F*4) + 4 multiplicity atomics (4*4)
+        "gngf_encode_fwd": P * (8 + L * (4 * F * 4 + F * 4 + 16)),
+        # per point: x (8) + per level d enc (F*4) + 4 vector reductions (4*F*4)
+        "gngf_encode_bwd": P * (8 + L * (F * 4 + 4 * F * 4)),
+        # API output idx_topk (P,L,4,K) int64 written, (K int32 read per row)
+        "gngf_lattice_gather_rows_i64": P * L * 4 * K * (8 + 4) + P * 8,
+        "gngf_lattice_gather_rows": P * L * 4 * K * (4 + 4) + P * 8,
+        "gngf_node_features_fwd": S * (K * (8 + F * 4) + F * 4),
+        "gngf_node_features_bwd": S * (F * 4 + K * (8 + 2 * F * 4 + 4)),
+        "gngf_softmax_topk_fwd": U * (2 * T * 4 + K * 8),
+        "gngf_hpd_dlogits": U * (2 * T * 4 + K * 12) + L * T * 4,
+        "gngf_lattice_colsum": S * 4 + U * T * 4 + L * T * 4,
+        "gngf_sigmoid_bwd": P * 3 * 4 * 3,
+        "gngf_hpd_first_layer_fwd": U * w["hpd"][0] * 4,
+        "gngf_hpd_first_layer_bwd": U * w["hpd"][0] * 4,
+    }
+    return "hbm", float(table.get(name, 0))
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from collision_handling_in_instantngp_b200 import _lib, dp, launch_count
+    from collision_handling_in_instantngp_b200.loss import total_loss
+    from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(65535)
+
+    net = GeneralNeuralGaugeFields(input_dim=2, hash_table_size=w["T"], num_levels=w["L"], n_min=w["n_min"],
+                                   n_max=w["n_max"], MLP_hidden_layers_widths=w["mlp"],
+                                   HPD_hidden_layers_widths=w["hpd"], HPD_out_features=w["T"], feature_dim=w["F"],
+                                   topk_k=w["K"], should_keep_topk_only=w["topk_only"])
+    h, wd = w["lattice_hw"]
+    m = max(h, wd) - 1
+    net.set_coord_bounds((0.0, 0.0), ((h - 1) / m, (wd - 1) / m))
+    opt = torch.optim.Adam(                                                     # functions.py:96-127
+        [{"params": net.encoding.parameters(), "lr": w["lr"]["encoding"], "weight_decay": w["wd"]["encoding"]},
+         {"params": net.HPD.parameters(), "lr": w["lr"]["hpd"], "weight_decay": w["wd"]["hpd"]},
+         {"params": net.mlp.parameters(), "lr": w["lr"]["mlp"], "weight_decay": w["wd"]["mlp"]}],
+        betas=(0.9, 0.99), eps=1e-15, capturable=True, fused=True)
+    reducer = dp.GradientAllReducer([p for g in opt.param_groups for p in g["params"]]) if world > 1 else None
+
+    x_np, y_np = make_inputs(w, 65535, rank)
+    x_host, y_host = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(y_np).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+    rows = 4 * w["P"] * world
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        rgb, probs, idx, _ = net(x, 1.0)
+        colsum = dp.all_reduce_colsum(probs.colsum) if world > 1 else probs.colsum
+        loss, _, _ = total_loss(rgb, y, colsum, rows, w["gamma"], w["epsilon"], w["l_mse"], w["l_js_kl"])
+        loss.backward()
+        if reducer is not None:
+            reducer()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
+
+    # ---- warm-up, then the device-timed region: inputs resident in HBM, CUDA events around every step ----
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    barrier()
+    n0 = launch_count()
+    step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    launches_per_step = launch_count() - n0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(x_dev, y_dev)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    dev_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    # ---- end-to-end: host (pinned) inputs copied in, loss read back, every step ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        loss = step(xd, yd)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+
+    # ---- per-kernel device times (separate pass, same steps) -> dominant kernel + roofline ----
+    prof = CallProfiler(torch)
+    _lib.PROFILER = prof
+    for _ in range(args.steps):
+        flush.zero_()
+        step(x_dev, y_dev)
+    _lib.PROFILER = None
+    agg = prof.summary()
+    lat = net.last_state.lat
+    per_name = {}
+    for (name, key), (t, n) in agg.items():
+        bound, amount = algorithmic_cost(name, key, w, lat)
+        e = per_name.setdefault(name, dict(ms=0.0, n=0, amount=0.0, bound=bound))
+        e["ms"] += t; e["n"] += n; e["amount"] += amount * n
+    total_kernel_ms = sum(e["ms"] for e in per_name.values())
+    top = max(per_name.items(), key=lambda kv: kv[1]["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tc_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "measured" if peaks else "fallback"
+    tname, te = top
+    per_launch_s = te["ms"] / te["n"] / 1e3
+    per_launch_amount = te["amount"] / te["n"]
+    if te["bound"] == "hbm":
+        achieved, peak, unit = per_launch_amount / per_launch_s / 1e9, hbm_peak, "GB/s"
+    else:
+        achieved, peak, unit = per_launch_amount / per_launch_s / 1e12, tc_peak, "TFLOP/s"
+    roofline = {"bound": te["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "traffic": None, "kernel": tname, "launches_per_step": te["n"] / args.steps,
+                "share_of_step_kernel_time": te["ms"] / total_kernel_ms, "peak_source": peak_src,
+                "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 5) for k, v in
+                                        sorted(per_name.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_P = args.cpu_sample
+        sec = time_cpu_port(w, sample_P, 65535, steps=3, warmup=1)
+        cpu_base = {"value": sample_P / sec, "unit": "samples/s", "cores": cpu_threads(), "kind": "port",
+                    "sample": f"{sample_P} of the workload's {w['P']} coordinates per step, 3 steps after 1 warm-up, "
+                              "oracle/gngf_oracle.py (numpy fp32) forward+loss+backward+Adam"}
+    if rank == 0:
+        total = w["P"] * world
+        line = {
+            "metric": "train samples/sec (fwd+bwd GNGF hash encode+MLP)", "value": total / (dev_ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "points_per_gpu_step": w["P"], "levels": w["L"],
+                       "table_size": w["T"], "topk_k": w["K"], "feature_dim": w["F"], "hpd": [2, *w["hpd"], w["T"]],
+                       "decoder": [w["L"] * w["F"], *w["mlp"], 3], "step": "forward+loss+backward+Adam",
+                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"dp{world}",
+                       "lattice_nodes": lat.num_nodes, "level_nodes": lat.num_level_nodes},
+            "e2e": {"value": total / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+                    "path": "module API, eager, pinned host inputs copied in and loss read back every step"},
+            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clocks, "roofline": roofline,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="points per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        sample_P = args.cpu_sample
+        sec = time_cpu_port(w, sample_P, 65535, steps=args.steps, warmup=args.warmup)
+        val = sample_P / sec
+        cores = cpu_threads()
+        sample = (f"{sample_P} of the workload's {w['P']} coordinates per step; oracle/gngf_oracle.py (numpy fp32 port of "
+                  "the reference's PyTorch-CPU path) forward+loss+backward+Adam")
+        print(json.dumps({
+            "impl": "reference", "metric": "train samples/sec (fwd+bwd GNGF hash encode+MLP)", "value": val,
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "points_per_step_sample": sample_P, "levels": w["L"],
+                       "table_size": w["T"], "topk_k": w["K"], "feature_dim": w["F"],
+                       "step": "forward+loss+backward+Adam"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }), flush=True)
+        return
+    run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

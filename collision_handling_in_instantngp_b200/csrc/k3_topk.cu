@@ -1,0 +1,261 @@
+// K3: softmax + nan_to_num + top-k, one warp per row (models.py:85, 111, DifferentiableTopk 5-42), and
+// K5b: the fused softmax / top-k / column-sum backward that turns per-node adjoints into dlogits.
+//
+// Selection order is (value descending, index ascending) -- torch.topk leaves ties unspecified; the oracle
+// defines them the same way.  Every candidate is a 64-bit key (ordered value bits << 32 | ~index), so one
+// unsigned max-reduction picks the winner and "strictly below the previous winner" removes chosen entries
+// without any marking: K rounds, each a strided scan + 5 shuffle steps.
+#include "common.cuh"
+
+namespace gngf {
+
+constexpr int TOPK_WARPS = 4;
+constexpr int SMEM_ROW_MAX = 8192;  // floats cached per warp
+
+__device__ __forceinline__ uint32_t ordered_bits(float v) {
+  v = v + 0.0f;  // -0 -> +0
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ uint64_t make_key(float v, uint32_t idx) {
+  return (static_cast<uint64_t>(ordered_bits(v)) << 32) | static_cast<uint64_t>(~idx);
+}
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, k, o);
+    k = other > k ? other : k;
+  }
+  return k;
+}
+
+// K rounds of selection over `vals` (T entries, lane-strided); lane 0 writes the winners.
+template <typename IdxT>
+__device__ __forceinline__ void select_topk(const float* vals, int64_t T, int K, int lane, float* topv, IdxT* topi) {
+  uint64_t prev = ~0ull;
+  for (int k = 0; k < K; ++k) {
+    uint64_t best = 0ull;
+    for (int64_t t = lane; t < T; t += 32) {
+      const uint64_t key = make_key(vals[t], static_cast<uint32_t>(t));
+      if (key < prev && key > best) best = key;
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) {
+      topi[k] = static_cast<IdxT>(~static_cast<uint32_t>(best));
+      topv[k] = from_ordered_bits(static_cast<uint32_t>(best >> 32));
+    }
+    prev = best;
+  }
+}
+
+// logits (R,T) -> probs (R,T) [optional, may alias], topv/topi (R,K), row_max/row_sum (R) [optional]
+__global__ void __launch_bounds__(TOPK_WARPS * 32)
+    softmax_topk_kernel(const float* logits, int64_t R, int64_t T, int K, float* probs, float* __restrict__ topv,
+                        int32_t* __restrict__ topi, float* __restrict__ row_max, float* __restrict__ row_sum,
+                        int cache_row) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * TOPK_WARPS + warp;
+  if (r >= R) return;
+  const float* z = logits + r * T;
+  float* cache = cache_row ? smem + static_cast<int64_t>(warp) * T : nullptr;
+  float* pout = probs ? probs + r * T : nullptr;
+
+  float m = -INFINITY;
+  for (int64_t t = lane; t < T; t += 32) {
+    const float v = z[t];
+    if (cache) cache[t] = v;
+    m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  float s = 0.0f;
+  for (int64_t t = lane; t < T; t += 32) {
+    const float e = expf((cache ? cache[t] : z[t]) - m);
+    if (cache) cache[t] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  // p = e / sum, NaN -> 0 (nan_to_num; +-inf cannot occur in a softmax output)
+  if (cache || pout) {
+    for (int64_t t = lane; t < T; t += 32) {
+      float p = (cache ? cache[t] : expf(z[t] - m)) / s;
+      if (p != p) p = 0.0f;
+      if (cache) cache[t] = p;
+      if (pout) pout[t] = p;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (row_max) row_max[r] = m;
+    if (row_sum) row_sum[r] = s;
+  }
+  if (cache) {
+    select_topk<int32_t>(cache, T, K, lane, topv + r * K, topi + r * K);
+  } else if (pout) {
+    select_topk<int32_t>(pout, T, K, lane, topv + r * K, topi + r * K);
+  } else {
+    // large row, nothing materialised: recompute p on every scan
+    uint64_t prev = ~0ull;
+    for (int k = 0; k < K; ++k) {
+      uint64_t best = 0ull;
+      for (int64_t t = lane; t < T; t += 32) {
+        float p = expf(z[t] - m) / s;
+        if (p != p) p = 0.0f;
+        const uint64_t key = make_key(p, static_cast<uint32_t>(t));
+        if (key < prev && key > best) best = key;
+      }
+      best = warp_max_u64(best);
+      if (lane == 0) {
+        topi[r * K + k] = static_cast<int32_t>(~static_cast<uint32_t>(best));
+        topv[r * K + k] = from_ordered_bits(static_cast<uint32_t>(best >> 32));
+      }
+      prev = best;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TOPK_WARPS * 32)
+    topk_kernel(const float* __restrict__ values, int64_t R, int64_t T, int K, float* __restrict__ topv,
+                int64_t* __restrict__ topi) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * TOPK_WARPS + warp;
+  if (r >= R) return;
+  select_topk<int64_t>(values + r * T, T, K, lane, topv + r * K, topi + r * K);
+}
+
+__global__ void __launch_bounds__(256) topk_scatter_kernel(const float* __restrict__ gv,
+                                                           const int64_t* __restrict__ topi, int64_t R, int64_t T,
+                                                           int K, float* __restrict__ gin) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= R * K) return;
+  const int64_t r = i / K;
+  const int64_t t = topi[i];
+  if (t >= 0 && t < T) gin[r * T + t] = gv[i];
+}
+
+// K5b.  One warp per lattice node u:
+//   G[t]      = sum_l c_l * gcol[l,t] + gdense[u,t] + sum_k g_k [t == utopi[u,k]],   c_l = cnt[s(l,u)],
+//   g_k       = dtv[u,k] + sum_l c_l * gcol_k[l,k]
+//   dlogit[t] = p[t] * (G[t] - <G,p>)
+__global__ void __launch_bounds__(TOPK_WARPS * 32)
+    hpd_dlogits_kernel(const __grid_constant__ gngf_lattice lat, const float* __restrict__ uprobs, int64_t T, int K,
+                       const int32_t* __restrict__ utopi, const float* __restrict__ dtv,
+                       const int32_t* __restrict__ cnt, const float* __restrict__ gcol,
+                       const float* __restrict__ gcol_k, const float* __restrict__ gdense,
+                       float* __restrict__ dlogits) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  const int64_t u = static_cast<int64_t>(blockIdx.x) * TOPK_WARPS + warp;
+  if (u >= U) return;
+  const int L = lat.num_levels;
+  const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
+  // cl[l] = multiplicity of this node on level l (0 when the node is outside that level's box)
+  __shared__ float cl_s[TOPK_WARPS][GNGF_MAX_LEVELS];
+  float* cl = cl_s[warp];
+  if (lane < L) {
+    float c = 0.0f;
+    if (cnt) {
+      const int i = cx - lat.lox[lane], j = cy - lat.loy[lane];
+      if (i >= 0 && i < lat.lwx[lane] && j >= 0 && j < lat.lwy[lane])
+        c = static_cast<float>(cnt[lat.loff[lane] + static_cast<int64_t>(i) * lat.lwy[lane] + j]);
+    }
+    cl[lane] = c;
+  }
+  __syncwarp();
+  const float* p = uprobs + u * T;
+  float* out = dlogits + u * T;
+
+  // <G,p>: sparse (top-k) part, lanes stride K ...
+  float dot = 0.0f;
+  for (int k = lane; k < K; k += 32) {
+    float g = dtv[u * K + k];
+    if (gcol_k)
+      for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
+    dot = fmaf(g, p[utopi[u * K + k]], dot);
+  }
+  // ... plus the dense column-sum part
+  const float* gd = gdense ? gdense + u * T : nullptr;
+  if (gcol || gd) {
+    for (int64_t t = lane; t < T; t += 32) {
+      float g = gd ? gd[t] : 0.0f;
+      if (gcol)
+        for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
+      dot = fmaf(g, p[t], dot);
+    }
+  }
+  dot = warp_sum(dot);
+  for (int64_t t = lane; t < T; t += 32) {
+    float g = gd ? gd[t] : 0.0f;
+    if (gcol)
+      for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
+    out[t] = p[t] * (g - dot);
+  }
+  __syncwarp();
+  for (int k = lane; k < K; k += 32) {
+    float g = dtv[u * K + k];
+    if (gcol_k)
+      for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
+    const int t = utopi[u * K + k];
+    out[t] = fmaf(p[t], g, out[t]);
+  }
+}
+
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_softmax_topk_fwd(const float* logits, int64_t R, int64_t T, int32_t K, float* probs, float* topv,
+                          int32_t* topi, float* row_max, float* row_sum, void* stream) {
+  if (R < 0 || T <= 0 || K <= 0 || K > T || K > GNGF_MAX_TOPK || T >= (1ll << 31)) return GNGF_ERR_INVALID_ARGUMENT;
+  if (R == 0) return GNGF_OK;
+  const int cache = T <= gngf::SMEM_ROW_MAX;
+  const size_t smem = cache ? sizeof(float) * T * gngf::TOPK_WARPS : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gngf::softmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return gngf::check_launch();
+  }
+  gngf::softmax_topk_kernel<<<static_cast<unsigned>(gngf::ceil_div(R, gngf::TOPK_WARPS)), gngf::TOPK_WARPS * 32, smem,
+                              gngf::as_stream(stream)>>>(logits, R, T, K, probs, topv, topi, row_max, row_sum, cache);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_topk_fwd(const float* values, int64_t R, int64_t T, int32_t K, float* topv, int64_t* topi, void* stream) {
+  if (R < 0 || T <= 0 || K <= 0 || K > T || T >= (1ll << 31)) return GNGF_ERR_INVALID_ARGUMENT;
+  if (R == 0) return GNGF_OK;
+  gngf::topk_kernel<<<static_cast<unsigned>(gngf::ceil_div(R, gngf::TOPK_WARPS)), gngf::TOPK_WARPS * 32, 0,
+                      gngf::as_stream(stream)>>>(values, R, T, K, topv, topi);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_topk_bwd(const float* grad_values, const int64_t* topi, int64_t R, int64_t T, int32_t K, float* grad_in,
+                  void* stream) {
+  if (R < 0 || T <= 0 || K <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (R == 0) return GNGF_OK;
+  cudaStream_t st = gngf::as_stream(stream);
+  if (cudaMemsetAsync(grad_in, 0, sizeof(float) * R * T, st) != cudaSuccess) return gngf::check_launch();
+  gngf::topk_scatter_kernel<<<static_cast<unsigned>(gngf::ceil_div(R * K, 256)), 256, 0, st>>>(grad_values, topi, R, T,
+                                                                                               K, grad_in);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_hpd_dlogits(gngf_lattice lat, const float* uprobs, int64_t T, int32_t K, const int32_t* utopi,
+                     const float* dtv, const int32_t* cnt, const float* gcol, const float* gcol_k,
+                     const float* gdense, float* dlogits, void* stream) {
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  if (U <= 0 || T <= 0 || K <= 0 || K > T) return GNGF_ERR_INVALID_ARGUMENT;
+  if ((gcol || gcol_k) && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::hpd_dlogits_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::TOPK_WARPS)), gngf::TOPK_WARPS * 32, 0,
+                             gngf::as_stream(stream)>>>(lat, uprobs, T, K, utopi, dtv, cnt, gcol, gcol_k, gdense,
+                                                        dlogits);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// K4: the feature lookup of MultiResHashEncoding.forward (models.py:194-222) and _bilinear_interpolate
+// (models.py:621-655), restructured around the lattice:
+//
+//   node pass   nfeat[s,:] = mix_k(table_l[utopi[u,k],:], utopv[u,:])     once per level node s = (l, cx, cy)
+//   point pass  enc[p, l*F+f] = sum_v w_bil[p,l,v] * nfeat[s(p,l,v), f]   4 gathers per (point, level)
+//
+// Every (point, level, corner) row of the reference that lands on the same node has the same top-k slots and
+// probabilities, so mixing K table rows per *row* (the reference) and per *node* (here) is the same
+// arithmetic done once.  The point pass is an HBM/L2-bound gather: one thread per (point, level), the
+// (P, L*F) output row written as contiguous float2.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gngf {
+
+__device__ __forceinline__ float mix_weight_norm(const float* tv, int K, int mode, float& mx) {
+  // returns the normaliser; mx = max (softmax mode)
+  mx = 0.0f;
+  if (mode == GNGF_MIX_SOFTMAX) {
+    mx = tv[0];
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, tv[k]);
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s += expf(tv[k] - mx);
+    return s;
+  }
+  if (mode == GNGF_MIX_WEIGHTED_AVG) {
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s += tv[k];
+    return s;
+  }
+  return 1.0f;
+}
+__device__ __forceinline__ float mix_weight(float tv, int mode, float mx, float norm) {
+  if (mode == GNGF_MIX_SOFTMAX) return expf(tv - mx) / norm;
+  if (mode == GNGF_MIX_WEIGHTED_AVG) return tv / norm;
+  return tv;
+}
+
+// grid (ceil(max level box / 256), L); thread per level node
+__global__ void __launch_bounds__(256)
+    node_features_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ gngf_tables tables,
+                             int64_t T, int F, int K, int mode, const float* __restrict__ utopv,
+                             const int32_t* __restrict__ utopi, float* __restrict__ nfeat) {
+  const int l = blockIdx.y;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int wy = lat.lwy[l];
+  if (i >= static_cast<int64_t>(lat.lwx[l]) * wy) return;
+  const int cx = lat.lox[l] + static_cast<int>(i / wy), cy = lat.loy[l] + static_cast<int>(i % wy);
+  const int64_t u = global_node(lat, cx, cy);
+  const float* tv = utopv + u * K;
+  const int32_t* ti = utopi + u * K;
+  const float* table = tables.ptr[l];
+  float mx;
+  const float norm = mix_weight_norm(tv, K, mode, mx);
+  float acc[GNGF_MAX_FEATURES];
+#pragma unroll
+  for (int f = 0; f < GNGF_MAX_FEATURES; ++f) acc[f] = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    // weighted-average mode follows the reference's op order: (sum_k g*p) / (sum_k p)
+    const float w = (mode == GNGF_MIX_WEIGHTED_AVG) ? tv[k] : mix_weight(tv[k], mode, mx, norm);
+    const float* row = table + static_cast<int64_t>(ti[k]) * F;
+#pragma unroll
+    for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+      if (f < F) acc[f] = fmaf(row[f], w, acc[f]);
+  }
+  float* out = nfeat + (lat.loff[l] + i) * F;
+#pragma unroll
+  for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+    if (f < F) out[f] = (mode == GNGF_MIX_WEIGHTED_AVG) ? acc[f] / norm : acc[f];
+}
+
+// thread per (point, level)
+template <int F>
+__global__ void __launch_bounds__(256)
+    encode_fwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
+                      const float* __restrict__ nfeat, float* __restrict__ enc, int32_t* __restrict__ cnt,
+                      int32_t* __restrict__ err_flag) {
+  const int L = lat.num_levels;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= P * L) return;
+  const int64_t p = i / L;
+  const int l = static_cast<int>(i - p * L);
+  const float2 xy = x[p];
+  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+  bool outside = false;
+  int64_t s[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) s[v] = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
+  float acc[F];
+  if constexpr (F == 2) {
+    float2 nf[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) nf[v] = __ldg(reinterpret_cast<const float2*>(nfeat) + s[v]);
+    acc[0] = 0.0f;
+    acc[1] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      acc[0] = fmaf(nf[v].x, c.w[v], acc[0]);
+      acc[1] = fmaf(nf[v].y, c.w[v], acc[1]);
+    }
+    reinterpret_cast<float2*>(enc)[i] = make_float2(acc[0], acc[1]);
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(nfeat + s[v] * F + f), c.w[v], acc[f]);
+#pragma unroll
+    for (int f = 0; f < F; ++f) enc[i * F + f] = acc[f];
+  }
+  if (cnt) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) atomicAdd(cnt + s[v], 1);
+  }
+  if (outside && err_flag) *err_flag = 1;
+}
+
+// hash-function mode: enc straight from table_l[hash(corner)], optional idx output (P,L,4) int64
+template <int F>
+__global__ void __launch_bounds__(256)
+    encode_hash_fwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
+                           const __grid_constant__ gngf_tables tables, int64_t T, float* __restrict__ enc,
+                           int64_t* __restrict__ idx_out) {
+  const int L = lat.num_levels;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= P * L) return;
+  const int64_t p = i / L;
+  const int l = static_cast<int>(i - p * L);
+  const float2 xy = x[p];
+  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+  const float* table = tables.ptr[l];
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint32_t gx = static_cast<uint32_t>(c.cx + (v & 1)), gy = static_cast<uint32_t>(c.cy + (v >> 1));
+    int64_t h = static_cast<int64_t>(static_cast<int32_t>(gx ^ (gy * 2654435761u))) % T;
+    if (h < 0) h += T;
+    if (idx_out) idx_out[i * 4 + v] = h;
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(table + h * F + f), c.w[v], acc[f]);
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f) enc[i * F + f] = acc[f];
+}
+
+// out[l, n] += sum over level nodes s of level l: cnt[s] * uvals[u(s), n]
+// grid (ceil(N/128), node chunks, L), block 128: thread = one column n
+__global__ void __launch_bounds__(128)
+    lattice_colsum_kernel(const __grid_constant__ gngf_lattice lat, const int32_t* __restrict__ cnt,
+                          const float* __restrict__ uvals, int64_t N, int64_t nodes_per_block,
+                          float* __restrict__ out) {
+  const int l = blockIdx.z;
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int wy = lat.lwy[l];
+  const int64_t box = static_cast<int64_t>(lat.lwx[l]) * wy;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * nodes_per_block;
+  const int64_t i1 = min(box, i0 + nodes_per_block);
+  if (i0 >= box || n >= N) return;
+  float acc = 0.0f;
+  for (int64_t i = i0; i < i1; ++i) {
+    const int c = cnt[lat.loff[l] + i];
+    if (c == 0) continue;
+    const int64_t u = global_node(lat, lat.lox[l] + static_cast<int>(i / wy), lat.loy[l] + static_cast<int>(i % wy));
+    acc = fmaf(static_cast<float>(c), uvals[u * N + n], acc);
+  }
+  atomicAdd(out + l * N + n, acc);
+}
+
+// out (P,L,4,N) = uvals[u(p,l,v), :]; thread per output element
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+    gather_rows_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
+                       const Tin* __restrict__ uvals, int64_t N, Tout* __restrict__ out) {
+  const int L = lat.num_levels;
+  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (e >= P * L * 4 * N) return;
+  const int64_t row = e / N;
+  const int64_t k = e - row * N;
+  const int v = static_cast<int>(row & 3);
+  const int64_t pl = row >> 2;
+  const int64_t p = pl / L;
+  const int l = static_cast<int>(pl - p * L);
+  const float2 xy = x[p];
+  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+  const int64_t u = global_node(lat, c.cx + (v & 1), c.cy + (v >> 1));
+  out[e] = static_cast<Tout>(uvals[u * N + k]);
+}
+
+// adjoint of gather_rows (f32): dvals[u(p,l,v), k] += dout[p,l,v,k]
+__global__ void __launch_bounds__(256)
+    scatter_rows_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
+                        const float* __restrict__ dout, int64_t N, float* __restrict__ dvals) {
+  const int L = lat.num_levels;
+  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (e >= P * L * 4 * N) return;
+  const int64_t row = e / N;
+  const int64_t k = e - row * N;
+  const int v = static_cast<int>(row & 3);
+  const int64_t pl = row >> 2;
+  const int64_t p = pl / L;
+  const int l = static_cast<int>(pl - p * L);
+  const float2 xy = x[p];
+  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+  const int64_t u = global_node(lat, c.cx + (v & 1), c.cy + (v >> 1));
+  const float g = dout[e];
+  if (g != 0.0f) atomicAdd(dvals + u * N + k, g);
+}
+
+static int valid_lat(const gngf_lattice& lat) {
+  return lat.num_levels > 0 && lat.num_levels <= GNGF_MAX_LEVELS && lat.wx > 0 && lat.wy > 0;
+}
+static int64_t max_level_box(const gngf_lattice& lat) {
+  int64_t m = 0;
+  for (int l = 0; l < lat.num_levels; ++l) m = std::max<int64_t>(m, static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l]);
+  return m;
+}
+
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_node_features_fwd(gngf_lattice lat, gngf_tables tables, int64_t T, int32_t F, int32_t K, int32_t mix_mode,
+                           const float* utopv, const int32_t* utopi, float* nfeat, void* stream) {
+  if (!gngf::valid_lat(lat) || F <= 0 || F > GNGF_MAX_FEATURES || K <= 0 || K > GNGF_MAX_TOPK || T <= 0)
+    return GNGF_ERR_INVALID_ARGUMENT;
+  dim3 grid(static_cast<unsigned>(gngf::ceil_div(gngf::max_level_box(lat), 256)), lat.num_levels);
+  gngf::node_features_fwd_kernel<<<grid, 256, 0, gngf::as_stream(stream)>>>(lat, tables, T, F, K, mix_mode, utopv,
+                                                                            utopi, nfeat);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_encode_fwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, const float* nfeat, float* enc,
+                    int32_t* cnt, int32_t* err_flag, void* stream) {
+  if (!gngf::valid_lat(lat) || P < 0 || F <= 0 || F > GNGF_MAX_FEATURES) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
+  cudaStream_t st = gngf::as_stream(stream);
+  const float2* x2 = reinterpret_cast<const float2*>(x);
+  switch (F) {
+    case 1: gngf::encode_fwd_kernel<1><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
+    case 2: gngf::encode_fwd_kernel<2><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
+    case 4: gngf::encode_fwd_kernel<4><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
+    case 8: gngf::encode_fwd_kernel<8><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
+    default: return GNGF_ERR_UNSUPPORTED;
+  }
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_encode_hash_fwd(const float* x, int64_t P, gngf_lattice lat, gngf_tables tables, int64_t T, int32_t F,
+                         float* enc, int64_t* idx_out, void* stream) {
+  if (!gngf::valid_lat(lat) || P < 0 || T <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
+  cudaStream_t st = gngf::as_stream(stream);
+  const float2* x2 = reinterpret_cast<const float2*>(x);
+  switch (F) {
+    case 1: gngf::encode_hash_fwd_kernel<1><<<blocks, 256, 0, st>>>(x2, P, lat, tables, T, enc, idx_out); break;
+    case 2: gngf::encode_hash_fwd_kernel<2><<<blocks, 256, 0, st>>>(x2, P, lat, tables, T, enc, idx_out); break;
+    case 4: gngf::encode_hash_fwd_kernel<4><<<blocks, 256, 0, st>>>(x2, P, lat, tables, T, enc, idx_out); break;
+    case 8: gngf::encode_hash_fwd_kernel<8><<<blocks, 256, 0, st>>>(x2, P, lat, tables, T, enc, idx_out); break;
+    default: return GNGF_ERR_UNSUPPORTED;
+  }
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_lattice_colsum(gngf_lattice lat, const int32_t* cnt, const float* uvals, int64_t N, float* out, void* stream) {
+  if (!gngf::valid_lat(lat) || N <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  const int64_t box = gngf::max_level_box(lat);
+  const int64_t nodes_per_block = std::max<int64_t>(32, gngf::ceil_div(box, 64));
+  dim3 grid(static_cast<unsigned>(gngf::ceil_div(N, 128)), static_cast<unsigned>(gngf::ceil_div(box, nodes_per_block)),
+            lat.num_levels);
+  gngf::lattice_colsum_kernel<<<grid, 128, 0, gngf::as_stream(stream)>>>(lat, cnt, uvals, N, nodes_per_block, out);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_lattice_gather_rows(const float* x, int64_t P, gngf_lattice lat, const float* uvals, int64_t N, float* out,
+                             void* stream) {
+  if (!gngf::valid_lat(lat) || P < 0 || N <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const int64_t n = P * lat.num_levels * 4 * N;
+  gngf::gather_rows_kernel<float, float><<<static_cast<unsigned>(gngf::ceil_div(n, 256)), 256, 0,
+                                           gngf::as_stream(stream)>>>(reinterpret_cast<const float2*>(x), P, lat, uvals,
+                                                                      N, out);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_lattice_gather_rows_i64(const float* x, int64_t P, gngf_lattice lat, const int32_t* uvals, int64_t N,
+                                 int64_t* out, void* stream) {
+  if (!gngf::valid_lat(lat) || P < 0 || N <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const int64_t n = P * lat.num_levels * 4 * N;
+  gngf::gather_rows_kernel<int32_t, int64_t><<<static_cast<unsigned>(gngf::ceil_div(n, 256)), 256, 0,
+                                               gngf::as_stream(stream)>>>(reinterpret_cast<const float2*>(x), P, lat,
+                                                                          uvals, N, out);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_lattice_scatter_rows(const float* x, int64_t P, gngf_lattice lat, const float* dout, int64_t N, float* dvals,
+                              void* stream) {
+  if (!gngf::valid_lat(lat) || P < 0 || N <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const int64_t n = P * lat.num_levels * 4 * N;
+  gngf::scatter_rows_kernel<<<static_cast<unsigned>(gngf::ceil_div(n, 256)), 256, 0, gngf::as_stream(stream)>>>(
+      reinterpret_cast<const float2*>(x), P, lat, dout, N, dvals);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// K5a: backward of the feature lookup, again split along the lattice:
+//
+//   point pass  dnf[s(p,l,v), f] += denc[p, l*F+f] * w_bil[p,l,v]      one vector reduction per corner
+//   node pass   table_grad_l[utopi[u,k], f] += dnf[s,f] * w_k           K vector reductions per level node
+//               dtv[u,k] += d mix / d topv (closed form of the autograd of models.py:212-217)
+//
+// The reference scatter-adds K*F values per (point, level, corner) row into the tables
+// (embedding_dense_backward, 16 launches) and materialises (rows, T) zero tensors for the top-k adjoint
+// (models.py:27-35).  Because mix and gather are linear in the incoming gradient and identical for every row
+// that shares a node, summing the F-vector per level node first cuts the atomics by 2K and leaves the
+// data-dependent scatter to a pass over S level nodes instead of 4*L*P rows.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gngf {
+
+template <int F>
+__global__ void __launch_bounds__(256)
+    encode_bwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
+                      const float* __restrict__ denc, float* __restrict__ dnf) {
+  const int L = lat.num_levels;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= P * L) return;
+  const int64_t p = i / L;
+  const int l = static_cast<int>(i - p * L);
+  const float2 xy = x[p];
+  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+  bool outside = false;
+  float d[F];
+  if constexpr (F == 2) {
+    const float2 t = reinterpret_cast<const float2*>(denc)[i];
+    d[0] = t.x;
+    d[1] = t.y;
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) d[f] = denc[i * F + f];
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int64_t s = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
+    const float w = c.w[v];
+    if (w == 0.0f) continue;  // x == 1.0 rows: the far corners carry exactly zero weight
+    if constexpr (F % 2 == 0) {
+#pragma unroll
+      for (int f = 0; f < F; f += 2) red_add_v2(dnf + s * F + f, d[f] * w, d[f + 1] * w);
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) atomicAdd(dnf + s * F + f, d[f] * w);
+    }
+  }
+}
+
+// grid (ceil(max level box / 256), L); thread per level node
+__global__ void __launch_bounds__(256)
+    node_features_bwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ gngf_tables tables,
+                             const __grid_constant__ gngf_tables tgrads, int64_t T, int F, int K, int mode,
+                             const float* __restrict__ utopv, const int32_t* __restrict__ utopi,
+                             const float* __restrict__ dnf, float* __restrict__ dtv) {
+  const int l = blockIdx.y;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int wy = lat.lwy[l];
+  if (i >= static_cast<int64_t>(lat.lwx[l]) * wy) return;
+  float d[GNGF_MAX_FEATURES];
+  bool any = false;
+#pragma unroll
+  for (int f = 0; f < GNGF_MAX_FEATURES; ++f) {
+    d[f] = f < F ? dnf[(lat.loff[l] + i) * F + f] : 0.0f;
+    any |= d[f] != 0.0f;
+  }
+  if (!any) return;  // untouched node (or exactly zero gradient): contributes nothing
+  const int cx = lat.lox[l] + static_cast<int>(i / wy), cy = lat.loy[l] + static_cast<int>(i % wy);
+  const int64_t u = global_node(lat, cx, cy);
+  const float* tv = utopv + u * K;
+  const int32_t* ti = utopi + u * K;
+  const float* table = tables.ptr[l];
+  float* tgrad = tgrads.ptr[l];
+
+  // mix weights (same arithmetic as the forward node pass)
+  float mx = 0.0f, norm = 1.0f;
+  if (mode == GNGF_MIX_SOFTMAX) {
+    mx = tv[0];
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, tv[k]);
+    norm = 0.0f;
+    for (int k = 0; k < K; ++k) norm += expf(tv[k] - mx);
+  } else if (mode == GNGF_MIX_WEIGHTED_AVG) {
+    norm = 0.0f;
+    for (int k = 0; k < K; ++k) norm += tv[k];
+  }
+  // pass 1: table gradient + <dw, w>
+  float dot = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    const float w = mode == GNGF_MIX_SOFTMAX ? expf(tv[k] - mx) / norm
+                                             : (mode == GNGF_MIX_WEIGHTED_AVG ? tv[k] / norm : tv[k]);
+    const int64_t row = static_cast<int64_t>(ti[k]) * F;
+    float dw = 0.0f;
+#pragma unroll
+    for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+      if (f < F) dw = fmaf(d[f], table[row + f], dw);
+    dot = fmaf(dw, w, dot);
+    if (F == 2) {
+      red_add_v2(tgrad + row, d[0] * w, d[1] * w);
+    } else {
+#pragma unroll
+      for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+        if (f < F) atomicAdd(tgrad + row + f, d[f] * w);
+    }
+  }
+  if (!dtv) return;
+  // pass 2: adjoint of the top-k probabilities
+  for (int k = 0; k < K; ++k) {
+    const int64_t row = static_cast<int64_t>(ti[k]) * F;
+    float dw = 0.0f;
+#pragma unroll
+    for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+      if (f < F) dw = fmaf(d[f], table[row + f], dw);
+    float g;
+    if (mode == GNGF_MIX_SOFTMAX) g = (expf(tv[k] - mx) / norm) * (dw - dot);
+    else if (mode == GNGF_MIX_WEIGHTED_AVG) g = (dw - dot) / norm;
+    else g = dw;
+    atomicAdd(dtv + u * K + k, g);
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+    encode_hash_bwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
+                           const __grid_constant__ gngf_tables tgrads, int64_t T, const float* __restrict__ denc) {
+  const int L = lat.num_levels;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= P * L) return;
+  const int64_t p = i / L;
+  const int l = static_cast<int>(i - p * L);
+  const float2 xy = x[p];
+  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+  float* tgrad = tgrads.ptr[l];
+  float d[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) d[f] = denc[i * F + f];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint32_t gx = static_cast<uint32_t>(c.cx + (v & 1)), gy = static_cast<uint32_t>(c.cy + (v >> 1));
+    int64_t h = static_cast<int64_t>(static_cast<int32_t>(gx ^ (gy * 2654435761u))) % T;
+    if (h < 0) h += T;
+    const float w = c.w[v];
+    if constexpr (F % 2 == 0) {
+#pragma unroll
+      for (int f = 0; f < F; f += 2) red_add_v2(tgrad + h * F + f, d[f] * w, d[f + 1] * w);
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) atomicAdd(tgrad + h * F + f, d[f] * w);
+    }
+  }
+}
+
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_encode_bwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, const float* denc, float* dnf,
+                    void* stream) {
+  if (lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS || P < 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
+  cudaStream_t st = gngf::as_stream(stream);
+  const float2* x2 = reinterpret_cast<const float2*>(x);
+  switch (F) {
+    case 1: gngf::encode_bwd_kernel<1><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
+    case 2: gngf::encode_bwd_kernel<2><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
+    case 4: gngf::encode_bwd_kernel<4><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
+    case 8: gngf::encode_bwd_kernel<8><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
+    default: return GNGF_ERR_UNSUPPORTED;
+  }
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_node_features_bwd(gngf_lattice lat, gngf_tables tables, gngf_tables table_grads, int64_t T, int32_t F,
+                           int32_t K, int32_t mix_mode, const float* utopv, const int32_t* utopi, const float* dnf,
+                           float* dtv, void* stream) {
+  if (lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS || F <= 0 || F > GNGF_MAX_FEATURES || K <= 0 ||
+      K > GNGF_MAX_TOPK)
+    return GNGF_ERR_INVALID_ARGUMENT;
+  int64_t box = 0;
+  for (int l = 0; l < lat.num_levels; ++l) box = std::max<int64_t>(box, static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l]);
+  dim3 grid(static_cast<unsigned>(gngf::ceil_div(box, 256)), lat.num_levels);
+  gngf::node_features_bwd_kernel<<<grid, 256, 0, gngf::as_stream(stream)>>>(lat, tables, table_grads, T, F, K,
+                                                                            mix_mode, utopv, utopi, dnf, dtv);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_encode_hash_bwd(const float* x, int64_t P, gngf_lattice lat, gngf_tables table_grads, int64_t T, int32_t F,
+                         const float* denc, void* stream) {
+  if (lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS || P < 0 || T <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
+  cudaStream_t st = gngf::as_stream(stream);
+  const float2* x2 = reinterpret_cast<const float2*>(x);
+  switch (F) {
+    case 1: gngf::encode_hash_bwd_kernel<1><<<blocks, 256, 0, st>>>(x2, P, lat, table_grads, T, denc); break;
+    case 2: gngf::encode_hash_bwd_kernel<2><<<blocks, 256, 0, st>>>(x2, P, lat, table_grads, T, denc); break;
+    case 4: gngf::encode_hash_bwd_kernel<4><<<blocks, 256, 0, st>>>(x2, P, lat, table_grads, T, denc); break;
+    case 8: gngf::encode_hash_bwd_kernel<8><<<blocks, 256, 0, st>>>(x2, P, lat, table_grads, T, denc); break;
+    default: return GNGF_ERR_UNSUPPORTED;
+  }
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

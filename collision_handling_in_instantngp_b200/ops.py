@@ -1,0 +1,347 @@
+"""PyTorch-side plumbing of the GNGF hot path: output allocation, stream hand-off and autograd wiring around
+the C ABI of libgngf_sm100.so.  PyTorch owns device memory and streams; all arithmetic is in the CUDA library.
+
+The path (reference models.py:394-484 and its autograd) is organised around the *lattice* (see lattice.py):
+
+  forward   HPD MLP + softmax + top-k on the U lattice nodes            (K2, K3)
+            mixed feature per level node                                 (K4 node pass)
+            per point: corners, bilinear weights, 4 gathers per level    (K1+K4 point pass) -> enc (P, L*F)
+            decoder MLP                                                  (K6)                -> rgb
+            node multiplicities -> column sums of the (virtual) probs    (what Loss consumes, utils.py:138)
+  backward  decoder -> d enc -> per-level-node sums -> table gradients + top-k adjoint (K5a)
+            softmax / top-k / column-sum adjoint per node -> dlogits     (K5b) -> HPD layer gradients (K5c)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, MIX_RAW, MIX_SOFTMAX, MIX_WEIGHTED_AVG, GngfError,
+                   Lattice, call, make_tables)
+
+MAX_DENSE_LOGIT_BYTES = 96 << 30   # (U, T) fp32 logits are materialised by this path
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise GngfError(f"{what} must be a CUDA tensor (got {t.device}); this package has no CPU path")
+
+
+def mix_mode_of(flag) -> int:
+    """params.should_softmax_topk_features: True / False / None (models.py:212-217)."""
+    if flag is None:
+        return MIX_RAW
+    return MIX_SOFTMAX if flag else MIX_WEIGHTED_AVG
+
+
+# ----------------------------------------------------------------------------------------------------------
+# thin wrappers (one C call each)
+# ----------------------------------------------------------------------------------------------------------
+def corners_fwd(x: torch.Tensor, lat: Lattice):
+    """_scale_to_grid (models.py:486-502): scaled (P,2,L,1), grid (P,2,L,4), fp32."""
+    _require_cuda(x, "x")
+    x = _f32c(x)
+    P, L = x.shape[0], lat.num_levels
+    scaled = torch.empty((P, 2, L, 1), dtype=torch.float32, device=x.device)
+    grid = torch.empty((P, 2, L, 4), dtype=torch.float32, device=x.device)
+    call("gngf_corners_fwd", x.data_ptr(), P, lat, scaled.data_ptr(), grid.data_ptr(), _stream())
+    return scaled, grid
+
+
+def fast_hash_fwd(x: torch.Tensor, lat: Lattice, table_size: int) -> torch.Tensor:
+    """_fast_hash (models.py:504-528) of the corners of x: (P,L,4) int64."""
+    _require_cuda(x, "x")
+    x = _f32c(x)
+    idx = torch.empty((x.shape[0], lat.num_levels, 4), dtype=torch.int64, device=x.device)
+    call("gngf_fast_hash_fwd", x.data_ptr(), x.shape[0], lat, int(table_size), idx.data_ptr(), _stream())
+    return idx
+
+
+def linear_fwd(x, w, b, act) -> torch.Tensor:
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    call("gngf_linear_fwd", x.data_ptr(), w.data_ptr(), _ptr(b), M, N, K, act, y.data_ptr(), _stream())
+    return y
+
+
+def linear_bwd(dz, x, w, act_prev, dx_needed, dw, db) -> Optional[torch.Tensor]:
+    M, N = dz.shape
+    K = w.shape[1]
+    dx = torch.empty((M, K), dtype=torch.float32, device=dz.device) if dx_needed else None
+    call("gngf_linear_bwd", dz.data_ptr(), x.data_ptr(), w.data_ptr(), M, N, K, act_prev, _ptr(dx), _ptr(dw), _ptr(db),
+         _stream())
+    return dx
+
+
+def softmax_topk_fwd(logits: torch.Tensor, k: int, inplace: bool = False, want_probs: bool = True):
+    """probs = nan_to_num(softmax(logits)), (topv, topi) = topk(probs, k) with ties -> lower index."""
+    _require_cuda(logits, "logits")
+    logits = _f32c(logits)
+    R, T = logits.shape
+    probs = (logits if inplace else torch.empty_like(logits)) if want_probs else None
+    topv = torch.empty((R, k), dtype=torch.float32, device=logits.device)
+    topi = torch.empty((R, k), dtype=torch.int32, device=logits.device)
+    call("gngf_softmax_topk_fwd", logits.data_ptr(), R, T, k, _ptr(probs), topv.data_ptr(), topi.data_ptr(), None, None,
+         _stream())
+    return probs, topv, topi
+
+
+def topk_fwd(values: torch.Tensor, k: int):
+    _require_cuda(values, "input")
+    values = _f32c(values)
+    shape = values.shape
+    v2 = values.reshape(-1, shape[-1])
+    topv = torch.empty((v2.shape[0], k), dtype=torch.float32, device=values.device)
+    topi = torch.empty((v2.shape[0], k), dtype=torch.int64, device=values.device)
+    call("gngf_topk_fwd", v2.data_ptr(), v2.shape[0], v2.shape[1], k, topv.data_ptr(), topi.data_ptr(), _stream())
+    return topv.reshape(*shape[:-1], k), topi.reshape(*shape[:-1], k)
+
+
+def topk_bwd(grad_values: torch.Tensor, topi: torch.Tensor, T: int) -> torch.Tensor:
+    gv = _f32c(grad_values)
+    shape = gv.shape
+    g2 = gv.reshape(-1, shape[-1])
+    i2 = topi.reshape(-1, shape[-1]).contiguous()
+    gin = torch.empty((g2.shape[0], T), dtype=torch.float32, device=gv.device)
+    call("gngf_topk_bwd", g2.data_ptr(), i2.data_ptr(), g2.shape[0], T, shape[-1], gin.data_ptr(), _stream())
+    return gin.reshape(*shape[:-1], T)
+
+
+def gather_rows(x, lat: Lattice, uvals: torch.Tensor) -> torch.Tensor:
+    """(P,L,4,N) rows of a per-node array; int32 input gives the int64 API dtype."""
+    P, N = x.shape[0], uvals.shape[1]
+    if uvals.dtype == torch.int32:
+        out = torch.empty((P, lat.num_levels, 4, N), dtype=torch.int64, device=x.device)
+        call("gngf_lattice_gather_rows_i64", x.data_ptr(), P, lat, uvals.data_ptr(), N, out.data_ptr(), _stream())
+    else:
+        out = torch.empty((P, lat.num_levels, 4, N), dtype=torch.float32, device=x.device)
+        call("gngf_lattice_gather_rows", x.data_ptr(), P, lat, uvals.data_ptr(), N, out.data_ptr(), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the fused forward / backward
+# ----------------------------------------------------------------------------------------------------------
+@dataclass
+class PathConfig:
+    """Static description of one GeneralNeuralGaugeFields instance."""
+    table_size: int
+    feature_dim: int
+    topk_k: int
+    n_hpd: int                     # number of HPD linear layers
+    n_mlp: int                     # number of decoder linear layers
+    topk_only: bool = False        # should_keep_topk_only
+    mix_mode: int = MIX_SOFTMAX
+    leaky: bool = False            # params.should_leaky_relu
+    use_hash: bool = False         # params.should_use_hash_function
+    hpd_trainable: bool = True
+
+
+@dataclass
+class ForwardState:
+    """What one forward leaves behind for backward and for the lazily materialised outputs."""
+    x: torch.Tensor
+    lat: Lattice
+    cfg: PathConfig
+    hpd_acts: List[torch.Tensor] = field(default_factory=list)   # outputs of HPD layers 0..n-2, (U, width)
+    uprobs: Optional[torch.Tensor] = None                        # (U,T)
+    utopv: Optional[torch.Tensor] = None                         # (U,K)
+    utopi: Optional[torch.Tensor] = None                         # (U,K) int32
+    cnt: Optional[torch.Tensor] = None                           # (S,) int32
+    mlp_acts: List[torch.Tensor] = field(default_factory=list)   # enc, a1, ..., rgb
+    err_flag: Optional[torch.Tensor] = None
+
+
+def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device):
+    """HashProbDistribution.forward (models.py:90-123) on every lattice node: returns hidden activations,
+    uprobs (U,T), utopv (U,K), utopi (U,K) int32."""
+    U = lat.num_nodes
+    T = hpd_w[-1].shape[0]
+    if U * T * 4 > MAX_DENSE_LOGIT_BYTES:
+        raise GngfError(f"dense logits for U={U} nodes x T={T} slots need {U * T * 4 / 2**30:.0f} GiB; "
+                        "use the streaming HPD path")
+    n = len(hpd_w)
+    if hpd_w[0].shape[1] != 2:
+        raise GngfError("the HPD input must be 2-D grid-corner coordinates")
+    acts = []
+    h = torch.empty((U, hpd_w[0].shape[0]), dtype=torch.float32, device=device)
+    call("gngf_hpd_first_layer_fwd", lat, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(), hpd_w[0].shape[0],
+         ACT_RELU if n > 1 else ACT_NONE, h.data_ptr(), _stream())
+    for i in range(1, n):
+        acts.append(h)
+        h = linear_fwd(h, hpd_w[i], hpd_b[i], ACT_RELU if i < n - 1 else ACT_NONE)
+    uprobs, utopv, utopi = softmax_topk_fwd(h, k, inplace=True)
+    return acts, uprobs, utopv, utopi
+
+
+class GNGFPath(torch.autograd.Function):
+    """forward + backward of GeneralNeuralGaugeFields (models.py:394-484) as one autograd node.
+
+    inputs : x (P,2), a ForwardState shell (non-tensor), then the parameters
+             [hpd_w0, hpd_b0, ..., tables 0..L-1, mlp_w0, mlp_b0, ...]
+    outputs: rgb (P,C), colsum (L,N)  -- the column sums of the (virtual) `probs` tensor the reference
+             returns (N = T, or K when should_keep_topk_only) -- and uvals (U,N), the per-node rows of that
+             tensor (only used when a caller materialises `probs`).
+    """
+
+    @staticmethod
+    def forward(ctx, x, state: ForwardState, *params):
+        cfg, lat = state.cfg, state.lat
+        dev = x.device
+        L, F, K, T = lat.num_levels, cfg.feature_dim, cfg.topk_k, cfg.table_size
+        P = x.shape[0]
+        nh, nm = (0 if cfg.use_hash else cfg.n_hpd), cfg.n_mlp
+        hpd_w, hpd_b = list(params[0:2 * nh:2]), list(params[1:2 * nh:2])
+        tables = list(params[2 * nh:2 * nh + L])
+        mlp_w, mlp_b = list(params[2 * nh + L::2]), list(params[2 * nh + L + 1::2])
+        st = _stream()
+        tab = make_tables(tables)
+        enc = torch.empty((P, L * F), dtype=torch.float32, device=dev)
+
+        if cfg.use_hash:
+            call("gngf_encode_hash_fwd", x.data_ptr(), P, lat, tab, T, F, enc.data_ptr(), None, st)
+            colsum = uvals = None
+        else:
+            state.hpd_acts, state.uprobs, state.utopv, state.utopi = hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev)
+            S = lat.num_level_nodes
+            nfeat = torch.empty((S, F), dtype=torch.float32, device=dev)
+            call("gngf_node_features_fwd", lat, tab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
+                 state.utopi.data_ptr(), nfeat.data_ptr(), st)
+            # cnt (S) | err flag (1) | colsum (L*N) share one zero-initialised buffer: one memset
+            N = K if cfg.topk_only else T
+            zbuf = torch.zeros(S + 1 + L * N, dtype=torch.int32, device=dev)
+            state.cnt, state.err_flag = zbuf[:S], zbuf[S:S + 1]
+            colsum = zbuf[S + 1:].view(torch.float32).view(L, N)
+            call("gngf_encode_fwd", x.data_ptr(), P, lat, F, nfeat.data_ptr(), enc.data_ptr(), state.cnt.data_ptr(),
+                 state.err_flag.data_ptr(), st)
+            uvals = state.utopv if cfg.topk_only else state.uprobs
+            call("gngf_lattice_colsum", lat, state.cnt.data_ptr(), uvals.data_ptr(), N, colsum.data_ptr(), st)
+
+        acts = [enc]
+        h = enc
+        hidden_act = ACT_LEAKY_RELU if cfg.leaky else ACT_RELU
+        for i in range(nm):
+            h = linear_fwd(h, mlp_w[i], mlp_b[i], hidden_act if i < nm - 1 else ACT_SIGMOID)
+            acts.append(h)
+        state.mlp_acts = acts
+        state.x = x
+        ctx.state = state
+        ctx.params = params
+        ctx.n_params = len(params)
+        rgb = acts[-1]
+        if cfg.use_hash:
+            return rgb
+        ctx.mark_non_differentiable()
+        return rgb, colsum, uvals
+
+    @staticmethod
+    def backward(ctx, grad_rgb, grad_colsum=None, grad_uvals=None):
+        state: ForwardState = ctx.state
+        cfg, lat, x = state.cfg, state.lat, state.x
+        params = ctx.params
+        dev = x.device
+        L, F, K, T = lat.num_levels, cfg.feature_dim, cfg.topk_k, cfg.table_size
+        P = x.shape[0]
+        nh, nm = (0 if cfg.use_hash else cfg.n_hpd), cfg.n_mlp
+        hpd_w = list(params[0:2 * nh:2])
+        tables = list(params[2 * nh:2 * nh + L])
+        mlp_w = list(params[2 * nh + L::2])
+        st = _stream()
+        S = 0 if cfg.use_hash else lat.num_level_nodes
+        U = lat.num_nodes
+
+        # one zero-initialised buffer for every accumulated gradient
+        sizes = [p.numel() for p in params] + [S * F, 0 if cfg.use_hash else U * K]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n])
+            off += n
+        grads = [v.view(p.shape) for v, p in zip(views[:len(params)], params)]
+        dnf, dtv = views[-2], views[-1]
+        g_hpd_w, g_hpd_b = grads[0:2 * nh:2], grads[1:2 * nh:2]
+        g_tables = grads[2 * nh:2 * nh + L]
+        g_mlp_w, g_mlp_b = grads[2 * nh + L::2], grads[2 * nh + L + 1::2]
+
+        # decoder MLP (models.py:468-470)
+        acts = state.mlp_acts
+        rgb = acts[-1]
+        grad_rgb = _f32c(grad_rgb)
+        dz = torch.empty_like(rgb)
+        call("gngf_sigmoid_bwd", grad_rgb.data_ptr(), rgb.data_ptr(), rgb.numel(), dz.data_ptr(), st)
+        hidden_act = ACT_LEAKY_RELU if cfg.leaky else ACT_RELU
+        for i in range(nm - 1, -1, -1):
+            dz = linear_bwd(dz, acts[i], mlp_w[i], hidden_act if i > 0 else ACT_NONE, True, g_mlp_w[i], g_mlp_b[i])
+        denc = dz
+
+        gtab = make_tables(g_tables)
+        if cfg.use_hash:
+            call("gngf_encode_hash_bwd", x.data_ptr(), P, lat, gtab, T, F, denc.data_ptr(), st)
+            return (None, None, *grads)
+
+        call("gngf_encode_bwd", x.data_ptr(), P, lat, F, denc.data_ptr(), dnf.data_ptr(), st)
+        need_hpd = cfg.hpd_trainable
+        call("gngf_node_features_bwd", lat, make_tables(tables), gtab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
+             state.utopi.data_ptr(), dnf.data_ptr(), dtv.data_ptr() if need_hpd else None, st)
+        if not need_hpd:
+            for i in range(2 * nh):
+                grads[i] = None
+            return (None, None, *grads)
+
+        gcol = gcol_k = gdense = None
+        if grad_colsum is not None:
+            grad_colsum = _f32c(grad_colsum)
+            if cfg.topk_only:
+                gcol_k = grad_colsum
+            else:
+                gcol = grad_colsum
+        if grad_uvals is not None:
+            grad_uvals = _f32c(grad_uvals)
+            if cfg.topk_only:
+                dtv.add_(grad_uvals.reshape(-1))
+            else:
+                gdense = grad_uvals
+        dlogits = torch.empty((U, T), dtype=torch.float32, device=dev)
+        call("gngf_hpd_dlogits", lat, state.uprobs.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
+             state.cnt.data_ptr(), _ptr(gcol), _ptr(gcol_k), _ptr(gdense), dlogits.data_ptr(), st)
+        dz = dlogits
+        for i in range(nh - 1, 0, -1):
+            dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
+        call("gngf_hpd_first_layer_bwd", lat, dz.data_ptr(), hpd_w[0].shape[0], g_hpd_w[0].data_ptr(),
+             g_hpd_b[0].data_ptr(), st)
+        return (None, None, *grads)
+
+
+class GatherRows(torch.autograd.Function):
+    """Materialises (P,L,4,N) rows of a per-node array (the slow path behind LazyProbs)."""
+
+    @staticmethod
+    def forward(ctx, uvals, x, lat):
+        ctx.x, ctx.lat, ctx.shape = x, lat, uvals.shape
+        return gather_rows(x, lat, uvals)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grad_out = _f32c(grad_out)
+        dvals = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
+        call("gngf_lattice_scatter_rows", ctx.x.data_ptr(), ctx.x.shape[0], ctx.lat, grad_out.data_ptr(), ctx.shape[1],
+             dvals.data_ptr(), _stream())
+        return dvals, None, None

@@ -1,0 +1,166 @@
+/*
+ * gngf.h -- C ABI of libgngf_sm100.so: the B200 (sm_100a) kernels behind the GNGF training hot path of
+ * FedeMont/collision_handling_in_instantNGP (forward + backward of GeneralNeuralGaugeFields).
+ *
+ * The reference is pure PyTorch and has no FFI of its own; each entry point below names the reference
+ * function (file:line, relative to the reference root) whose arithmetic it replaces.  The host side
+ * (collision_handling_in_instantngp_b200/models.py) keeps the reference's class signatures and calls these
+ * through ctypes with raw device pointers.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major memory owned by the caller (PyTorch's
+ *     caching allocator); nothing is allocated or freed by the library;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), thread-safe for distinct
+ *     streams, and returns 0 or a negative gngf_status; gngf_strerror() names it;
+ *   - fp32 everywhere; indices int32 on the lattice, int64 in API outputs (torch.topk's dtype);
+ *   - corner order v in {0,1,2,3} <-> (dx,dy) = (0,0),(1,0),(0,1),(1,1)            (models.py:322-331);
+ *   - "lattice": the HPD only ever sees integer corner coordinates and is shared by all levels
+ *     (models.py:353-359,416-418), so it is evaluated once per lattice *node* u = (cx-ox)*wy + (cy-oy) of
+ *     the bounding box of all levels, and per-level quantities live on "level nodes"
+ *     s = loff[l] + (cx-lox[l])*lwy[l] + (cy-loy[l]).
+ */
+#ifndef GNGF_H
+#define GNGF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNGF_MAX_LEVELS 32
+#define GNGF_MAX_FEATURES 8
+#define GNGF_MAX_TOPK 128
+
+typedef enum {
+  GNGF_OK = 0,
+  GNGF_ERR_INVALID_ARGUMENT = -1,
+  GNGF_ERR_UNSUPPORTED = -2,
+  GNGF_ERR_CUDA = -3,
+  GNGF_ERR_NO_DEVICE = -4
+} gngf_status;
+
+/* top-k mix modes == params.should_softmax_topk_features (models.py:212-217) */
+#define GNGF_MIX_SOFTMAX 1      /* True : sum_k g * softmax_K(topk probs)           */
+#define GNGF_MIX_WEIGHTED_AVG 0 /* False: sum_k g * p / sum_k p                     */
+#define GNGF_MIX_RAW 2          /* None : sum_k g * p                               */
+
+/* activations of gngf_linear_fwd */
+#define GNGF_ACT_NONE 0
+#define GNGF_ACT_RELU 1
+#define GNGF_ACT_LEAKY_RELU 2 /* slope 0.01 (nn.LeakyReLU default, models.py:388) */
+#define GNGF_ACT_SIGMOID 3
+
+/* Geometry of one forward call; filled by the host from the level table (models.py:305-317) and the
+ * coordinate bounds of the batch.  Passed by value. */
+typedef struct {
+  int32_t num_levels;
+  int32_t n[GNGF_MAX_LEVELS];   /* n_l */
+  int32_t ox, oy, wx, wy;       /* global node box: origin and extent; U = wx*wy                      */
+  int32_t lox[GNGF_MAX_LEVELS]; /* per-level node boxes                                              */
+  int32_t loy[GNGF_MAX_LEVELS];
+  int32_t lwx[GNGF_MAX_LEVELS];
+  int32_t lwy[GNGF_MAX_LEVELS];
+  int64_t loff[GNGF_MAX_LEVELS + 1]; /* prefix offsets of the level boxes; S = loff[num_levels]       */
+} gngf_lattice;
+
+/* L table pointers, each (T, F) fp32 (encoding._hash_tables.{l}.weight, models.py:159-164) */
+typedef struct {
+  float* ptr[GNGF_MAX_LEVELS];
+} gngf_tables;
+
+const char* gngf_strerror(int status);
+/* version of this ABI; bumped on any signature change */
+int gngf_abi_version(void);
+/* number of SMs / compute capability of the current device (negative status when no device) */
+int gngf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* cumulative number of kernel launches issued by this library in this process (bench.py: gpu_launches) */
+int64_t gngf_launch_count(void);
+
+/* ---- K1: grid corners (models.py:486-502, _scale_to_grid) ------------------------------------------
+ * scaled (P,2,L,1) = x * n_l ; grid (P,2,L,4) = floor(scaled) + corner offsets; fp32, integer-valued. */
+int gngf_corners_fwd(const float* x, int64_t P, gngf_lattice lat, float* scaled, float* grid, void* stream);
+
+/* spatial hash baseline (models.py:504-528, _fast_hash): idx (P,L,4) int64 in [0,T) */
+int gngf_fast_hash_fwd(const float* x, int64_t P, gngf_lattice lat, int64_t table_size, int64_t* idx, void* stream);
+
+/* ---- K2: HPD MLP on lattice nodes (models.py:80-88,105-106) ----------------------------------------
+ * first layer (in_features = 2) evaluated directly from the node coordinates:
+ *   h (U,N) = relu(c(u) * W0^T + b0), c(u) = (ox + u / wy, oy + u % wy) as fp32                        */
+int gngf_hpd_first_layer_fwd(gngf_lattice lat, const float* w0, const float* b0, int32_t n_out, int32_t act,
+                             float* h, void* stream);
+/* generic linear layer: y (M,N) = act(x (M,K) * w(N,K)^T + b(N)); fp32 CUDA-core tiles                  */
+int gngf_linear_fwd(const float* x, const float* w, const float* b, int64_t M, int32_t N, int32_t K, int32_t act,
+                    float* y, void* stream);
+/* backward of a linear layer whose INPUT was x (M,K) (an activation of the previous layer):
+ *   dw (N,K) += dz^T x ; db (N) += colsum(dz) ; dx (M,K) = (dz * w) .* act'(x)   (dx may be NULL)
+ * act_prev describes how x was produced (GNGF_ACT_NONE: no mask).  dw/db must be zeroed by the caller.   */
+int gngf_linear_bwd(const float* dz, const float* x, const float* w, int64_t M, int32_t N, int32_t K,
+                    int32_t act_prev, float* dx, float* dw, float* db, void* stream);
+/* dz = dy .* y .* (1 - y)  (sigmoid backward of the decoder's last layer, models.py:389)               */
+int gngf_sigmoid_bwd(const float* dy, const float* y, int64_t n, float* dz, void* stream);
+/* backward of the first HPD layer: dw0 (N,2) += dz^T c(u), db0 (N) += colsum(dz)                        */
+int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, float* dw0, float* db0, void* stream);
+
+/* ---- K3: softmax + nan_to_num + top-k (models.py:85,111 and DifferentiableTopk.forward 7-19) --------
+ * logits (R,T) -> probs (R,T) (may alias logits, may be NULL), topv (R,K) sorted descending,
+ * topi (R,K) int32, ties broken towards the lower index; row_max / row_sum (R) optional.               */
+int gngf_softmax_topk_fwd(const float* logits, int64_t R, int64_t T, int32_t K, float* probs, float* topv,
+                          int32_t* topi, float* row_max, float* row_sum, void* stream);
+/* top-k only (DifferentiableTopk.forward on given values): int64 indices, API dtype                     */
+int gngf_topk_fwd(const float* values, int64_t R, int64_t T, int32_t K, float* topv, int64_t* topi, void* stream);
+/* DifferentiableTopk.backward (models.py:21-42): grad_in (R,T) = scatter(zeros, idx, grad_values)       */
+int gngf_topk_bwd(const float* grad_values, const int64_t* topi, int64_t R, int64_t T, int32_t K, float* grad_in,
+                  void* stream);
+
+/* ---- K4: fused per-level feature lookup + top-k mix + bilinear interpolation -----------------------
+ * node features (models.py:194-222 evaluated once per level node):
+ *   nfeat[s, f] = mix_k(table_l[utopi[u,k], f], utopv[u,:])                                             */
+int gngf_node_features_fwd(gngf_lattice lat, gngf_tables tables, int64_t T, int32_t F, int32_t K, int32_t mix_mode,
+                           const float* utopv, const int32_t* utopi, float* nfeat, void* stream);
+/* per point: corners + bilinear weights (models.py:621-655) + gather of 4 node features per level:
+ *   enc (P, L*F); optional cnt (S) int32 += multiplicity of every level node; err_flag (int32, optional)
+ *   is set to 1 when a coordinate falls outside the lattice box (the access is clamped).               */
+int gngf_encode_fwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, const float* nfeat, float* enc,
+                    int32_t* cnt, int32_t* err_flag, void* stream);
+/* hash-function mode (models.py:181-190 + 504-528): enc straight from table_l[hash(corner)]             */
+int gngf_encode_hash_fwd(const float* x, int64_t P, gngf_lattice lat, gngf_tables tables, int64_t T, int32_t F,
+                         float* enc, int64_t* idx_out, void* stream);
+/* column sums of the (virtual) probability tensor: out (L,N) = sum_s cnt[s] * uvals[u(s), :]
+ * (the numerator of p-bar in utils.py:138; uvals = uprobs (U,T) or utopv (U,K)); out must be zeroed      */
+int gngf_lattice_colsum(gngf_lattice lat, const int32_t* cnt, const float* uvals, int64_t N, float* out, void* stream);
+/* materialise rows of a per-node array: out (P,L,4,N) = uvals[u(p,l,v), :]
+ * (f32: top-k probs / full probs -- the module's `probs` output; i32->i64: the `idx_topk` output)        */
+int gngf_lattice_gather_rows(const float* x, int64_t P, gngf_lattice lat, const float* uvals, int64_t N, float* out,
+                             void* stream);
+int gngf_lattice_gather_rows_i64(const float* x, int64_t P, gngf_lattice lat, const int32_t* uvals, int64_t N,
+                                 int64_t* out, void* stream);
+/* and its adjoint: dvals (U,N) += sum over rows of dout (P,L,4,N)                                       */
+int gngf_lattice_scatter_rows(const float* x, int64_t P, gngf_lattice lat, const float* dout, int64_t N, float* dvals,
+                              void* stream);
+
+/* ---- K5: backward ----------------------------------------------------------------------------------
+ * K5a stage 1, per point: dnf[s, f] += denc[p, l*F+f] * w_bil[p,l,v]   (vector red.global.add)          */
+int gngf_encode_bwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, const float* denc, float* dnf,
+                    void* stream);
+/* K5a stage 2, per level node: table_grad[l][utopi[u,k], f] += dnf[s,f] * w_k ;
+ *   dtv[u,k] += mix-backward(dnf . table rows)   (closed form of models.py:212-217's autograd)          */
+int gngf_node_features_bwd(gngf_lattice lat, gngf_tables tables, gngf_tables table_grads, int64_t T, int32_t F,
+                           int32_t K, int32_t mix_mode, const float* utopv, const int32_t* utopi, const float* dnf,
+                           float* dtv, void* stream);
+int gngf_encode_hash_bwd(const float* x, int64_t P, gngf_lattice lat, gngf_tables table_grads, int64_t T, int32_t F,
+                         const float* denc, void* stream);
+/* K5b, per node: G = sum_l cnt[s(l,u)] * gcol[l,:] + gdense[u,:] + scatter(g_k at utopi[u,:]),
+ *   g_k = dtv[u,k] + sum_l cnt[s(l,u)] * gcol_k[l,k];   dlogit[u,:] = p .* (G - <G,p>)
+ * (softmax backward, models.py:85, with DifferentiableTopk.backward, models.py:21-42, and the adjoint of
+ * the loss's column sums, utils.py:138, folded in).  gcol (L,T): adjoint of the full-probability column
+ * sums; gcol_k (L,K): adjoint of the top-k column sums; gdense (U,T): dense adjoint of uprobs.  Each of
+ * the three may be NULL.                                                                                */
+int gngf_hpd_dlogits(gngf_lattice lat, const float* uprobs, int64_t T, int32_t K, const int32_t* utopi,
+                     const float* dtv, const int32_t* cnt, const float* gcol, const float* gcol_k,
+                     const float* gdense, float* dlogits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNGF_H */

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library is built, loads, and exports every symbol include/gngf.h declares."""
+import os
+import re
+
+import collision_handling_in_instantngp_b200 as pkg
+from collision_handling_in_instantngp_b200 import _lib
+from collision_handling_in_instantngp_b200.lattice import build_lattice, level_resolutions
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gngf.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gngf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = pkg.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in gngf.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.gngf_abi_version() == 1
+    assert lib.gngf_strerror(0) == b"ok"
+    assert lib.gngf_strerror(-1) == b"invalid argument"
+    assert lib.gngf_launch_count() == 0
+
+
+def test_library_has_sm100a_code_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_lattice_boxes():
+    n_ls = level_resolutions(8, 32, 4)
+    assert list(n_ls) == [8, 12, 20, 32]
+    lat = build_lattice(n_ls)
+    assert (lat.ox, lat.oy, lat.wx, lat.wy) == (0, 0, 34, 34)
+    assert [lat.lwx[l] for l in range(4)] == [10, 14, 22, 34]
+    assert lat.num_level_nodes == 100 + 196 + 484 + 1156
+    # the strawberry image: x in [0,1], y in [0, 338/507]
+    lat = build_lattice(n_ls, (0.0, 0.0), (1.0, 338 / 507))
+    assert lat.num_nodes == 34 * 23     # the 782 distinct HPD inputs of SURVEY.md section 7
+    lat = build_lattice(level_resolutions(16, 8192, 16))
+    assert lat.wx == 8193 and lat.n[15] == 8191
+    # negative coordinates (BatchNorm'd inputs): boxes follow the data
+    lat = build_lattice(n_ls, (-1.5, -0.25), (2.0, 0.5))
+    assert lat.lox[0] == -12 and lat.loy[0] == -2 and lat.lwx[0] == 16 - (-12) + 2

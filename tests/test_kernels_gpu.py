@@ -1,0 +1,156 @@
+"""GPU: per-kernel known-answer tests through the C ABI, against oracle/gngf_oracle.py and the goldens.
+Bar: integer corners, hashes and top-k indices bit-exact; fp32 values within 1e-5 relative."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import gngf_oracle as O  # noqa: E402
+from golden_util import ALL_CASES, load, rel_err  # noqa: E402
+
+from collision_handling_in_instantngp_b200 import ops  # noqa: E402
+from collision_handling_in_instantngp_b200.lattice import build_lattice, level_resolutions  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _edge_coords(n=4096, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 2), dtype=np.float32)
+    x[:8] = [[0, 0], [1, 1], [1, 0], [0, 1], [0.5, 0.5], [1 / 3, 2 / 3], [np.nextafter(np.float32(1), np.float32(0))] * 2,
+             [338 / 507, 1.0]]
+    # exact lattice hits of an 8192 grid: i / 8191
+    x[8:1032, 0] = (rng.integers(0, 8192, 1024) / np.float32(8191)).astype(np.float32)
+    x[8:1032, 1] = (rng.integers(0, 8192, 1024) / np.float32(8191)).astype(np.float32)
+    return x
+
+
+@pytest.mark.parametrize("levels", [(8, 32, 4), (16, 508, 16), (16, 8192, 16), (2, 1024, 10)])
+def test_corners_bit_exact(levels):
+    n_ls = level_resolutions(*levels)
+    assert np.array_equal(n_ls, O.level_resolutions(*levels))
+    x = _edge_coords()
+    scaled, grid = ops.corners_fwd(torch.from_numpy(x).to(DEV), build_lattice(n_ls))
+    s_ref, g_ref = O.scale_to_grid(x, n_ls)
+    assert np.array_equal(scaled.cpu().numpy(), s_ref)
+    assert np.array_equal(grid.cpu().numpy(), g_ref)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_corners_match_reference_goldens(name):
+    g = load(name)
+    scaled, grid = ops.corners_fwd(torch.from_numpy(g["x"]).to(DEV), build_lattice(g["n_ls"]))
+    assert np.array_equal(scaled.cpu().numpy(), g["scaled"])
+    assert np.array_equal(grid.cpu().numpy(), g["grid"])
+
+
+def test_corners_empty_batch():
+    scaled, grid = ops.corners_fwd(torch.empty((0, 2), device=DEV), build_lattice([8, 16]))
+    assert scaled.shape == (0, 2, 2, 1) and grid.shape == (0, 2, 2, 4)
+
+
+@pytest.mark.parametrize("T", [256, 2 ** 14, 2 ** 19, 2 ** 22, 1000])
+def test_fast_hash_bit_exact(T):
+    n_ls = level_resolutions(16, 8192, 16)
+    x = _edge_coords()
+    idx = ops.fast_hash_fwd(torch.from_numpy(x).to(DEV), build_lattice(n_ls), T).cpu().numpy()
+    _, grid = O.scale_to_grid(x, n_ls)
+    assert np.array_equal(idx, O.fast_hash(grid.astype(np.int32), T))
+
+
+def test_fast_hash_matches_reference_golden():
+    g = load("hash_mode")
+    idx = ops.fast_hash_fwd(torch.from_numpy(g["x"]).to(DEV), build_lattice(g["n_ls"]), g["cfg"]["T"])
+    assert idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+
+
+def _no_tie_rows(p, k, tol=0.0):
+    srt = -np.sort(-p, axis=-1)
+    return (srt[:, :k] - srt[:, 1:k + 1]).min(axis=-1) > tol
+
+
+@pytest.mark.parametrize("R,T,K", [(1000, 256, 4), (77, 256, 1), (64, 256, 20), (33, 256, 128), (50, 1000, 4),
+                                   (20, 4096, 32), (6, 2 ** 14, 4), (3, 2 ** 19, 4), (1, 7, 7)])
+def test_softmax_topk_matches_oracle(R, T, K):
+    rng = np.random.default_rng(R * 31 + T)
+    logits = (rng.standard_normal((R, T)) * 3).astype(np.float32)
+    probs, topv, topi = ops.softmax_topk_fwd(torch.from_numpy(logits).to(DEV), K)
+    p_ref = O.softmax_lastdim(logits)
+    assert rel_err(probs.cpu().numpy(), p_ref) < 1e-5
+    # indices: bit-exact against the oracle's top-k *on the same probabilities* (ties -> lower index)
+    p_gpu = probs.cpu().numpy()
+    v_ref, i_ref = O.topk_sorted(p_gpu, K)
+    assert np.array_equal(topi.cpu().numpy(), i_ref)
+    assert np.array_equal(topv.cpu().numpy(), v_ref)
+    # and against the oracle's own probabilities wherever its k-boundary is not a rounding-level tie
+    ok = _no_tie_rows(p_ref, min(K, T - 1), tol=4e-7 * p_ref.max())
+    assert np.array_equal(topi.cpu().numpy()[ok], O.topk_sorted(p_ref, K)[1][ok])
+
+
+def test_softmax_topk_ties_nan_and_inplace():
+    logits = np.zeros((4, 256), dtype=np.float32)                  # all ties -> indices 0..K-1
+    logits[1, 5] = logits[1, 200] = 3.0                            # two-way tie at the top
+    logits[2, :] = np.nan                                          # softmax -> NaN -> nan_to_num -> 0
+    logits[3, 17] = np.inf                                         # exp(inf - inf) = NaN row as well
+    t = torch.from_numpy(logits).to(DEV)
+    probs, topv, topi = ops.softmax_topk_fwd(t, 4, inplace=True)
+    assert probs.data_ptr() == t.data_ptr()
+    topi = topi.cpu().numpy()
+    assert list(topi[0]) == [0, 1, 2, 3]
+    assert list(topi[1]) == [5, 200, 0, 1]
+    assert list(topi[2]) == [0, 1, 2, 3] and float(probs[2].abs().sum()) == 0.0
+    assert torch.isfinite(probs).all()
+
+
+def test_topk_forward_backward_generic_values():
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((5, 7, 300)).astype(np.float32)
+    v[0, 0, :10] = -np.inf
+    v[1, 2, 3] = v[1, 2, 9] = 10.0
+    v[2] = np.round(v[2])                                           # many duplicates
+    t = torch.from_numpy(v).to(DEV).requires_grad_()
+    from collision_handling_in_instantngp_b200.models import DifferentiableTopk
+    vals, idx = DifferentiableTopk.apply(t, 6, -1)
+    v_ref, i_ref = O.topk_sorted(v, 6)
+    assert idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), i_ref) and np.array_equal(vals.detach().cpu().numpy(), v_ref)
+    gv = torch.from_numpy(rng.standard_normal(v_ref.shape).astype(np.float32)).to(DEV)
+    vals.backward(gv)
+    g_ref = np.zeros_like(v)
+    np.put_along_axis(g_ref, i_ref, gv.cpu().numpy(), axis=-1)      # models.py:27-35
+    assert np.array_equal(t.grad.cpu().numpy(), g_ref)
+    # another dim
+    vals2, idx2 = DifferentiableTopk.apply(torch.from_numpy(v).to(DEV), 2, 1)
+    v2, i2 = O.topk_sorted(np.moveaxis(v, 1, -1), 2)
+    assert np.array_equal(np.moveaxis(idx2.cpu().numpy(), 1, -1), i2)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1000, 64, 8, 1), (777, 3, 64, 3), (130, 256, 128, 0), (65, 33, 17, 2), (1, 1, 1, 1)])
+def test_linear_forward_backward(M, N, K, act):
+    rng = np.random.default_rng(M + N)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    xt, wt, bt = (torch.from_numpy(a).to(DEV) for a in (x, w, b))
+    y = ops.linear_fwd(xt, wt, bt, act)
+    z = x.astype(np.float64) @ w.astype(np.float64).T + b
+    ref = {0: z, 1: np.maximum(z, 0), 2: np.where(z > 0, z, 0.01 * z), 3: 1 / (1 + np.exp(-z))}[act]
+    assert rel_err(y.cpu().numpy(), ref) < 1e-5
+    dz = rng.standard_normal((M, N)).astype(np.float32)
+    dw, db = torch.zeros_like(wt), torch.zeros_like(bt)
+    xin = np.maximum(x, 0)                                           # pretend x is a ReLU output
+    dx = ops.linear_bwd(torch.from_numpy(dz).to(DEV), torch.from_numpy(xin).to(DEV), wt, 1, True, dw, db)
+    assert rel_err(dw.cpu().numpy(), dz.astype(np.float64).T @ xin) < 1e-5
+    assert rel_err(db.cpu().numpy(), dz.astype(np.float64).sum(0)) < 1e-5
+    assert rel_err(dx.cpu().numpy(), (dz.astype(np.float64) @ w) * (xin > 0)) < 1e-5
+
+
+def test_missing_gpu_tensor_is_rejected():
+    from collision_handling_in_instantngp_b200 import GngfError
+    with pytest.raises(GngfError):
+        ops.corners_fwd(torch.zeros(4, 2), build_lattice([8]))

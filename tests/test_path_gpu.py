@@ -1,0 +1,134 @@
+"""GPU: the whole hot path (forward + loss + backward through the drop-in module) against golden vectors of
+the unmodified reference and against the oracle.  Tolerances (BASELINE.json north_star): top-k indices exact,
+forward 1e-5 relative, gradients 1e-4 relative."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import gngf_oracle as O  # noqa: E402
+from golden_util import ALL_CASES, GNGF_CASES, load, loss_cfg, oracle_cfg, params_of, rel_err  # noqa: E402
+from parity_util import build_net, reset_flags, run_step  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, GRAD_TOL = 1e-5, 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _flags():
+    yield
+    reset_flags()
+
+
+def _check_grads(out, g, tol=GRAD_TOL):
+    for k in [k for k in g if k.startswith("grad.")]:
+        name = k[len("grad."):]
+        assert name in out["grads"], name
+        assert rel_err(out["grads"][name], g[k]) < tol, (name, rel_err(out["grads"][name], g[k]))
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_step_matches_reference_golden(name):
+    g = load(name)
+    net = build_net(g)
+    out = run_step(net, g)
+    assert np.array_equal(out["idx"], g["idx"])
+    assert out["idx"].dtype == np.int64
+    assert rel_err(out["rgb"], g["rgb"]) < FWD_TOL
+    st = out["state"]
+    assert rel_err(st.mlp_acts[0].cpu().numpy(), g["enc"]) < FWD_TOL
+    if not g["cfg"]["use_hash"]:
+        assert int(st.err_flag.item()) == 0
+        assert rel_err(out["pbar"], g["pbar"]) < FWD_TOL
+        assert abs(out["mse"] - g["mse"]) < FWD_TOL * abs(g["mse"])
+        assert rel_err(out["kl_levels"], g["kl_levels"]) < 1e-4
+    assert abs(out["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    _check_grads(out, g)
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "k20"])
+def test_materialised_probs_match_reference_and_lazy_path(name):
+    g = load(name)
+    net = build_net(g)
+    rgb, probs, idx, _ = net(torch.from_numpy(g["x"]).cuda(), 1.0)
+    dense = probs.materialize()
+    assert tuple(dense.shape) == tuple(probs.shape) == (g["x"].shape[0], g["cfg"]["L"], 4, g["ret_probs_head"].shape[-1])
+    assert rel_err(dense[:4].detach().cpu().numpy(), g["ret_probs_head"]) < FWD_TOL
+    # the loss through the materialised tensor gives the same gradients as through the symbolic column sums
+    out_dense = run_step(net, g, materialize=True)
+    _check_grads(out_dense, g)
+
+
+def test_full_size_cfg2_against_oracle():
+    """Config 2 at full batch size (P = 57 404 strawberry pixels, ID 4061 parameters)."""
+    g = load("cfg2_small")
+    img = np.load(os.path.join(os.path.dirname(__file__), "golden", "strawberry_u8.npz"))["img"]
+    h, w = img.shape[:2]
+    X = np.stack(np.meshgrid(range(h), range(w), indexing="ij"), -1).reshape(-1, 2)
+    x_all = (torch.tensor(X).float() / (max(w, h) - 1)).numpy()
+    y_all = (torch.tensor(img.reshape(-1, 3) / 255).float()).numpy()
+    perm = np.random.default_rng(65535).permutation(x_all.shape[0])[:57404]
+    g = dict(g)
+    g["x"], g["y"] = x_all[perm], y_all[perm]
+    net = build_net(g)
+    out = run_step(net, g)
+    assert out["state"].lat.num_nodes == 34 * 23
+    p = params_of(g)
+    fwd = O.gngf_forward(p, g["x"], oracle_cfg(g))
+    grads = O.gngf_backward(p, g["x"], g["y"], oracle_cfg(g), fwd, loss_cfg(g))
+    assert np.array_equal(out["idx"], fwd["idx"])
+    assert rel_err(out["rgb"], fwd["rgb"]) < FWD_TOL
+    assert rel_err(out["pbar"], fwd["pbar"]) < FWD_TOL
+    for l in range(4):
+        assert rel_err(out["grads"][f"encoding._hash_tables.{l}.weight"], grads["tables"][l]) < GRAD_TOL
+    for i in range(4):
+        assert rel_err(out["grads"][f"HPD.module_list.{i}.0.weight"], grads["hpd_w"][i]) < GRAD_TOL
+        assert rel_err(out["grads"][f"HPD.module_list.{i}.0.bias"], grads["hpd_b"][i]) < GRAD_TOL
+    for i in range(3):
+        assert rel_err(out["grads"][f"mlp.{i}.0.weight"], grads["mlp_w"][i]) < GRAD_TOL
+
+
+def test_state_dict_keys_and_optimizer_groups():
+    g = load("cfg2_small")
+    net = build_net(g)
+    keys = list(net.state_dict().keys())
+    assert keys == [k[len("param."):] if k.startswith("param.") else k for k in keys]
+    expect = ["_batch_norm.weight", "_batch_norm.bias", "_batch_norm.running_mean", "_batch_norm.running_var",
+              "_batch_norm.num_batches_tracked"] + \
+             [f"HPD.module_list.{i}.0.{n}" for i in range(4) for n in ("weight", "bias")] + \
+             [f"encoding._hash_tables.{l}.weight" for l in range(4)] + \
+             [f"mlp.{i}.0.{n}" for i in range(3) for n in ("weight", "bias")]
+    assert keys == expect
+    # functions.py:96-127
+    opt = torch.optim.Adam([{"params": net.encoding.parameters(), "lr": 1e-4},
+                            {"params": net.HPD.parameters(), "lr": 1e-3},
+                            {"params": net.mlp.parameters(), "lr": 1e-3}], betas=(0.9, 0.99), eps=1e-15)
+    out = run_step(net, g)
+    opt.step()
+    out2 = run_step(net, g)
+    assert out2["loss"] != out["loss"]
+
+
+def test_frozen_hpd_and_empty_batch():
+    g = load("cfg2_small")
+    net = build_net(g)
+    for p in net.HPD.parameters():
+        p.requires_grad = False
+    out = run_step(net, g)
+    assert not any(k.startswith("HPD") for k in out["grads"])
+    _check_grads({"grads": {**out["grads"], **{k[5:]: g[k] for k in g if k.startswith("grad.HPD")}}}, g)
+
+
+def test_out_of_bounds_coordinates_are_flagged():
+    g = load("cfg2_small")
+    net = build_net(g)
+    net.set_coord_bounds((0.0, 0.0), (0.5, 0.5))
+    x = torch.from_numpy(g["x"]).cuda()
+    net(x, 1.0)
+    assert int(net.last_state.err_flag.item()) == 1
+    net.set_coord_bounds(None)
+    net(x, 1.0)
+    assert int(net.last_state.err_flag.item()) == 0
