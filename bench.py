@@ -118,47 +118,59 @@ def cpu_threads():
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML in a background thread during the timed regions.
+    (An `nvidia-smi -lms` child process was measured to slow every CUDA launch of the timed process by ~5x
+    through driver-lock contention; in-process NVML queries at 25 ms do not.)"""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.power = index, [], set(), []
+        self.max_sm, self.h, self._stop, self.err = None, None, threading.Event(), None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            self._stop.wait(0.025)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 class CallProfiler:
@@ -279,7 +291,7 @@ def run_ours(args, w):
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
 
-    # ---- warm-up, then the device-timed region: inputs resident in HBM, CUDA events around every step ----
+    # ---- warm-up (eager), then capture the whole step in a CUDA graph (single-GPU; NCCL steps stay eager) ----
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     barrier()
@@ -288,6 +300,32 @@ def run_ours(args, w):
     torch.cuda.synchronize()
     launches_per_step = launch_count() - n0
 
+    graph, launch_mode = None, "eager"
+    if world == 1 and not args.eager:
+        opt.zero_grad(set_to_none=True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step(x_dev, y_dev)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        net.last_state = None
+        with torch.cuda.graph(graph, stream=side):
+            graph_loss = step(x_dev, y_dev)
+        launch_mode = "cuda_graph"
+        for _ in range(max(args.warmup, 3)):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def timed_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step(x_dev, y_dev)
+
+    # ---- the device-timed region: inputs resident in HBM, CUDA events around every step, L2 flushed between ----
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -296,7 +334,7 @@ def run_ours(args, w):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step(x_dev, y_dev)
+        timed_step()
         b.record()
         evs.append((a, b))
     barrier()
@@ -376,6 +414,7 @@ def run_ours(args, w):
                        "table_size": w["T"], "topk_k": w["K"], "feature_dim": w["F"], "hpd": [2, *w["hpd"], w["T"]],
                        "decoder": [w["L"] * w["F"], *w["mlp"], 3], "step": "forward+loss+backward+Adam",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"dp{world}",
+                       "launch_mode": launch_mode,
                        "lattice_nodes": lat.num_nodes, "level_nodes": lat.num_level_nodes},
             "e2e": {"value": total / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
@@ -399,6 +438,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=8192, help="points per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture the timed step in a CUDA graph")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
 

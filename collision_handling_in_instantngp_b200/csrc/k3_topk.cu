@@ -71,11 +71,15 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
     m = fmaxf(m, v);
   }
   m = warp_max(m);
-  float s = 0.0f;
+  // Kahan-compensated per-lane sum: rows are up to 2^22 entries long and the normaliser feeds every output
+  float s = 0.0f, comp = 0.0f;
   for (int64_t t = lane; t < T; t += 32) {
     const float e = expf((cache ? cache[t] : z[t]) - m);
     if (cache) cache[t] = e;
-    s += e;
+    const float yk = __fsub_rn(e, comp);
+    const float tk = __fadd_rn(s, yk);
+    comp = __fsub_rn(__fsub_rn(tk, s), yk);
+    s = tk;
   }
   s = warp_sum(s);
   // p = e / sum, NaN -> 0 (nan_to_num; +-inf cannot occur in a softmax output)

@@ -5,6 +5,8 @@ drive a step without importing the reference, and so that the (L, N) column sums
 the non-linear divergence terms (dp.py).  Only O(L*N) torch ops -- no per-row tensor is ever formed."""
 from __future__ import annotations
 
+import math
+
 import torch
 
 
@@ -17,7 +19,7 @@ def level_divergences(pbar: torch.Tensor, gamma: float, epsilon: float) -> torch
     N = pbar.shape[-1]
     q = 1.0 / N
     lp = pbar.log()
-    lq = torch.log(torch.tensor(q, dtype=pbar.dtype, device=pbar.device))
+    lq = math.log(q)
     kl = (q * (lq - lp)).sum(-1) / N
     m = (pbar + q) / 2
     lm = m.log()

@@ -246,11 +246,12 @@ class GNGFPath(torch.autograd.Function):
         ctx.state = state
         ctx.params = params
         ctx.n_params = len(params)
-        rgb = acts[-1]
+        # return fresh aliases: autograd attaches grad_fn to the returned objects, and the tensors kept in
+        # `state` must not keep the autograd graph (and the parameters' AccumulateGrad nodes) alive
+        rgb = acts[-1].detach()
         if cfg.use_hash:
             return rgb
-        ctx.mark_non_differentiable()
-        return rgb, colsum, uvals
+        return rgb, colsum.detach(), uvals.detach()
 
     @staticmethod
     def backward(ctx, grad_rgb, grad_colsum=None, grad_uvals=None):
@@ -270,11 +271,13 @@ class GNGFPath(torch.autograd.Function):
 
         # one zero-initialised buffer for every accumulated gradient
         sizes = [p.numel() for p in params] + [S * F, 0 if cfg.use_hash else U * K]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # (every view starts on a 16-byte boundary: the scatter kernels use vector reductions)
+        padded = [(n + 3) & ~3 for n in sizes]
+        flat = torch.zeros(sum(padded), dtype=torch.float32, device=dev)
         views, off = [], 0
-        for n in sizes:
+        for n, npad in zip(sizes, padded):
             views.append(flat[off:off + n])
-            off += n
+            off += npad
         grads = [v.view(p.shape) for v, p in zip(views[:len(params)], params)]
         dnf, dtv = views[-2], views[-1]
         g_hpd_w, g_hpd_b = grads[0:2 * nh:2], grads[1:2 * nh:2]
