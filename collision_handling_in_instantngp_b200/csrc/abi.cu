@@ -11,6 +11,19 @@ static thread_local char g_last_cuda_error[256] = "";
 
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
 int check_launch() {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return GNGF_OK;

@@ -11,6 +11,18 @@ namespace gngf {
 void note_launch(int n = 1);
 int check_launch();  // cudaGetLastError -> gngf_status, remembers the message for gngf_strerror
 
+int sm_count();       // multiprocessors of the current device (cached)
+
+// number of leading level nodes (the coarsest levels are stored first) that fit a shared-memory budget
+inline int private_node_count(const gngf_lattice& lat, int64_t max_nodes) {
+  int64_t n = 0;
+  for (int l = 0; l < lat.num_levels; ++l) {
+    if (lat.loff[l + 1] > max_nodes) break;
+    n = lat.loff[l + 1];
+  }
+  return static_cast<int>(n);
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

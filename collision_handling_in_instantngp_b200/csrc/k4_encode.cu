@@ -70,51 +70,72 @@ __global__ void __launch_bounds__(256)
     if (f < F) out[f] = (mode == GNGF_MIX_WEIGHTED_AVG) ? acc[f] / norm : acc[f];
 }
 
-// thread per (point, level)
+// Persistent grid, grid-stride over (point, level) items.  The node multiplicities `cnt` are a histogram with
+// heavy same-address traffic on the coarse levels (level 0 of the published configuration: 3 280 increments
+// per node and batch; an L2 atomic unit retires roughly one same-address update per 50-80 cycles), so the first
+// `private_nodes` level nodes -- the coarsest levels, which are stored first -- are counted in shared memory
+// and flushed once per CTA; finer levels go straight to global atomics where contention is naturally low.
 template <int F>
 __global__ void __launch_bounds__(256)
     encode_fwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
                       const float* __restrict__ nfeat, float* __restrict__ enc, int32_t* __restrict__ cnt,
-                      int32_t* __restrict__ err_flag) {
+                      int32_t* __restrict__ err_flag, int private_nodes) {
+  extern __shared__ int32_t cnt_s[];
   const int L = lat.num_levels;
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= P * L) return;
-  const int64_t p = i / L;
-  const int l = static_cast<int>(i - p * L);
-  const float2 xy = x[p];
-  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
-  bool outside = false;
-  int64_t s[4];
-#pragma unroll
-  for (int v = 0; v < 4; ++v) s[v] = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
-  float acc[F];
-  if constexpr (F == 2) {
-    float2 nf[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) nf[v] = __ldg(reinterpret_cast<const float2*>(nfeat) + s[v]);
-    acc[0] = 0.0f;
-    acc[1] = 0.0f;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      acc[0] = fmaf(nf[v].x, c.w[v], acc[0]);
-      acc[1] = fmaf(nf[v].y, c.w[v], acc[1]);
-    }
-    reinterpret_cast<float2*>(enc)[i] = make_float2(acc[0], acc[1]);
-  } else {
-#pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] = 0.0f;
-#pragma unroll
-    for (int v = 0; v < 4; ++v)
-#pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(nfeat + s[v] * F + f), c.w[v], acc[f]);
-#pragma unroll
-    for (int f = 0; f < F; ++f) enc[i * F + f] = acc[f];
+  const bool priv = cnt != nullptr && private_nodes > 0;
+  if (priv) {
+    for (int i = threadIdx.x; i < private_nodes; i += blockDim.x) cnt_s[i] = 0;
+    __syncthreads();
   }
-  if (cnt) {
+  bool outside = false;
+  const int64_t total = P * L, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int64_t p = i / L;
+    const int l = static_cast<int>(i - p * L);
+    const float2 xy = x[p];
+    const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+    int64_t s[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) atomicAdd(cnt + s[v], 1);
+    for (int v = 0; v < 4; ++v) s[v] = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
+    float acc[F];
+    if constexpr (F == 2) {
+      float2 nf[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) nf[v] = __ldg(reinterpret_cast<const float2*>(nfeat) + s[v]);
+      acc[0] = 0.0f;
+      acc[1] = 0.0f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        acc[0] = fmaf(nf[v].x, c.w[v], acc[0]);
+        acc[1] = fmaf(nf[v].y, c.w[v], acc[1]);
+      }
+      reinterpret_cast<float2*>(enc)[i] = make_float2(acc[0], acc[1]);
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(nfeat + s[v] * F + f), c.w[v], acc[f]);
+#pragma unroll
+      for (int f = 0; f < F; ++f) enc[i * F + f] = acc[f];
+    }
+    if (cnt) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (s[v] < private_nodes) atomicAdd(cnt_s + s[v], 1);
+        else atomicAdd(cnt + s[v], 1);
+      }
+    }
   }
   if (outside && err_flag) *err_flag = 1;
+  if (priv) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < private_nodes; i += blockDim.x) {
+      const int c = cnt_s[i];
+      if (c) atomicAdd(cnt + i, c);
+    }
+  }
 }
 
 // hash-function mode: enc straight from table_l[hash(corner)], optional idx output (P,L,4) int64
@@ -238,14 +259,17 @@ int gngf_encode_fwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, cons
                     int32_t* cnt, int32_t* err_flag, void* stream) {
   if (!gngf::valid_lat(lat) || P < 0 || F <= 0 || F > GNGF_MAX_FEATURES) return GNGF_ERR_INVALID_ARGUMENT;
   if (P == 0) return GNGF_OK;
-  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
   cudaStream_t st = gngf::as_stream(stream);
   const float2* x2 = reinterpret_cast<const float2*>(x);
+  const int priv = cnt ? gngf::private_node_count(lat, 10240) : 0;      // <= 40 KB of shared counters
+  const size_t smem = sizeof(int32_t) * priv;
+  const int64_t items = P * lat.num_levels;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(items, 256), 2 * gngf::sm_count()));
   switch (F) {
-    case 1: gngf::encode_fwd_kernel<1><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
-    case 2: gngf::encode_fwd_kernel<2><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
-    case 4: gngf::encode_fwd_kernel<4><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
-    case 8: gngf::encode_fwd_kernel<8><<<blocks, 256, 0, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag); break;
+    case 1: gngf::encode_fwd_kernel<1><<<blocks, 256, smem, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag, priv); break;
+    case 2: gngf::encode_fwd_kernel<2><<<blocks, 256, smem, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag, priv); break;
+    case 4: gngf::encode_fwd_kernel<4><<<blocks, 256, smem, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag, priv); break;
+    case 8: gngf::encode_fwd_kernel<8><<<blocks, 256, smem, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag, priv); break;
     default: return GNGF_ERR_UNSUPPORTED;
   }
   gngf::note_launch();

@@ -15,38 +15,56 @@
 
 namespace gngf {
 
+// Persistent grid; the first `private_nodes` level nodes (coarsest levels) accumulate in shared memory and
+// are flushed once per CTA -- see encode_fwd_kernel for why.
 template <int F>
 __global__ void __launch_bounds__(256)
     encode_bwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
-                      const float* __restrict__ denc, float* __restrict__ dnf) {
+                      const float* __restrict__ denc, float* __restrict__ dnf, int private_nodes) {
+  extern __shared__ float dnf_s[];
   const int L = lat.num_levels;
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= P * L) return;
-  const int64_t p = i / L;
-  const int l = static_cast<int>(i - p * L);
-  const float2 xy = x[p];
-  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
-  bool outside = false;
-  float d[F];
-  if constexpr (F == 2) {
-    const float2 t = reinterpret_cast<const float2*>(denc)[i];
-    d[0] = t.x;
-    d[1] = t.y;
-  } else {
-#pragma unroll
-    for (int f = 0; f < F; ++f) d[f] = denc[i * F + f];
+  if (private_nodes > 0) {
+    for (int i = threadIdx.x; i < private_nodes * F; i += blockDim.x) dnf_s[i] = 0.0f;
+    __syncthreads();
   }
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const int64_t s = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
-    const float w = c.w[v];
-    if (w == 0.0f) continue;  // x == 1.0 rows: the far corners carry exactly zero weight
-    if constexpr (F % 2 == 0) {
-#pragma unroll
-      for (int f = 0; f < F; f += 2) red_add_v2(dnf + s * F + f, d[f] * w, d[f + 1] * w);
+  const int64_t total = P * L, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int64_t p = i / L;
+    const int l = static_cast<int>(i - p * L);
+    const float2 xy = x[p];
+    const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+    bool outside = false;
+    float d[F];
+    if constexpr (F == 2) {
+      const float2 t = reinterpret_cast<const float2*>(denc)[i];
+      d[0] = t.x;
+      d[1] = t.y;
     } else {
 #pragma unroll
-      for (int f = 0; f < F; ++f) atomicAdd(dnf + s * F + f, d[f] * w);
+      for (int f = 0; f < F; ++f) d[f] = denc[i * F + f];
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int64_t s = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
+      const float w = c.w[v];
+      if (w == 0.0f) continue;  // x == 1.0 rows: the far corners carry exactly zero weight
+      if (s < private_nodes) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(dnf_s + s * F + f, d[f] * w);
+      } else if constexpr (F % 2 == 0) {
+#pragma unroll
+        for (int f = 0; f < F; f += 2) red_add_v2(dnf + s * F + f, d[f] * w, d[f + 1] * w);
+      } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(dnf + s * F + f, d[f] * w);
+      }
+    }
+  }
+  if (private_nodes > 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < private_nodes * F; i += blockDim.x) {
+      const float v = dnf_s[i];
+      if (v != 0.0f) atomicAdd(dnf + i, v);
     }
   }
 }
@@ -161,14 +179,17 @@ int gngf_encode_bwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, cons
                     void* stream) {
   if (lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS || P < 0) return GNGF_ERR_INVALID_ARGUMENT;
   if (P == 0) return GNGF_OK;
-  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
   cudaStream_t st = gngf::as_stream(stream);
   const float2* x2 = reinterpret_cast<const float2*>(x);
+  const int priv = gngf::private_node_count(lat, (40 * 1024) / (4 * F));   // <= 40 KB of shared accumulators
+  const size_t smem = sizeof(float) * priv * F;
+  const int64_t items = P * lat.num_levels;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(items, 256), 2 * gngf::sm_count()));
   switch (F) {
-    case 1: gngf::encode_bwd_kernel<1><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
-    case 2: gngf::encode_bwd_kernel<2><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
-    case 4: gngf::encode_bwd_kernel<4><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
-    case 8: gngf::encode_bwd_kernel<8><<<blocks, 256, 0, st>>>(x2, P, lat, denc, dnf); break;
+    case 1: gngf::encode_bwd_kernel<1><<<blocks, 256, smem, st>>>(x2, P, lat, denc, dnf, priv); break;
+    case 2: gngf::encode_bwd_kernel<2><<<blocks, 256, smem, st>>>(x2, P, lat, denc, dnf, priv); break;
+    case 4: gngf::encode_bwd_kernel<4><<<blocks, 256, smem, st>>>(x2, P, lat, denc, dnf, priv); break;
+    case 8: gngf::encode_bwd_kernel<8><<<blocks, 256, smem, st>>>(x2, P, lat, denc, dnf, priv); break;
     default: return GNGF_ERR_UNSUPPORTED;
   }
   gngf::note_launch();
