@@ -210,6 +210,10 @@ def algorithmic_cost(name, key, w, lat):
     """(bound, amount per launch, unit): ALGORITHMIC bytes (hbm) or FLOPs (tensor) of one launch."""
     P, L, F, K, T = w["P"], w["L"], w["F"], w["K"], w["T"]
     U, S = lat.num_nodes, lat.num_level_nodes
+    if name in ("gngf_mlp3_fwd", "gngf_mlp3_bwd"):
+        dims = [L * F, *w["mlp"], 3]
+        flops = 2.0 * P * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+        return "tensor", flops * (1 if name == "gngf_mlp3_fwd" else 3)   # bwd: recompute + dX + dW
     if name == "gngf_linear_fwd":
         M, N, Kd = key
         return "tensor", 2.0 * M * N * Kd

@@ -11,7 +11,7 @@
 
 namespace gngf {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+constexpr int BK = 16;  // tiles: 64x64 (4x4 per thread) for large problems, 32x32 (2x2) to spread small ones
 
 struct Epilogue {
   const float* bias;   // (N) or null
@@ -31,6 +31,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // C[m,n] = sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]
+template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                     const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                     float* __restrict__ C, int64_t ldc, int64_t M, int64_t N,
@@ -70,9 +71,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -109,14 +112,23 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 static int launch_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C,
                         int64_t ldc, int64_t M, int64_t N, int64_t K, int split, Epilogue ep, cudaStream_t st) {
   if (M == 0 || N == 0) return GNGF_OK;
+  const bool small = ceil_div(M, 64) * ceil_div(N, 64) < 2 * sm_count();
+  const int bm = small ? 32 : 64;
+  if (ep.atomic) {  // reduction-heavy (dW): enough CTAs to fill the chip
+    const int64_t tiles = ceil_div(M, bm) * ceil_div(N, bm);
+    split = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(K, 64), (4 * sm_count()) / tiles)));
+  }
   split = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(split, ceil_div(K, BK))));
   int64_t k_chunk = ceil_div(ceil_div(K, split), BK) * BK;
   split = static_cast<int>(ceil_div(K, k_chunk));
   if (split > 1 && !ep.atomic) return GNGF_ERR_INVALID_ARGUMENT;
-  const int64_t gy = ceil_div(M, BM), gx = ceil_div(N, BN);
+  const int64_t gy = ceil_div(M, bm), gx = ceil_div(N, bm);
   if (gy > 65535) return GNGF_ERR_UNSUPPORTED;
   dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy), static_cast<unsigned>(split));
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_chunk, ep);
+  if (small)
+    sgemm_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_chunk, ep);
+  else
+    sgemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_chunk, ep);
   note_launch();
   return check_launch();
 }
@@ -230,9 +242,7 @@ int gngf_linear_bwd(const float* dz, const float* x, const float* w, int64_t M, 
   if (dw) {
     // dw[n,k] = sum_m dz[m*N + n] * x[m*K + k]; rows are the reduction dimension -> split + atomics
     gngf::Epilogue ep{nullptr, 0, nullptr, 0, 1};
-    const int64_t tiles = gngf::ceil_div(N, gngf::BM) * gngf::ceil_div(K, gngf::BN);
-    int split = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(gngf::ceil_div(M, 256), (148 * 4) / tiles)));
-    rc = gngf::launch_sgemm(dz, 1, N, x, K, 1, dw, K, N, K, M, split, ep, st);
+    rc = gngf::launch_sgemm(dz, 1, N, x, K, 1, dw, K, N, K, M, 0, ep, st);
     if (rc) return rc;
   }
   if (db) {

@@ -1,0 +1,516 @@
+// K6: the decoder MLP  enc (P, IN) -> 64 -> 64 -> OUT (3 or 1), ReLU/LeakyReLU hidden, sigmoid output
+// (models.py:382-392, 468-470) fused into one forward kernel and one backward kernel for the reference's
+// shape (two hidden layers of 64).  Activations never leave the SM: a CTA takes tiles of 128 points, keeps
+// them k-major in shared memory ([feature][point], row stride 132 floats so that float4 accesses of a quarter
+// warp hit distinct banks), runs each layer as a register-tiled fp32 GEMM (true fp32 FMA = the reference's
+// cuBLAS SGEMM arithmetic), and the backward recomputes the hidden activations instead of reading them back.
+// Weight gradients are accumulated in registers across all tiles of a (persistent) CTA, written once per CTA
+// to a partials buffer and summed by a second tiny kernel -- no atomics.
+// Other decoder shapes go through the generic layers of k2_linear.cu.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gngf {
+
+constexpr int H = 64;        // hidden width
+constexpr int TP = 128;      // points per tile
+constexpr int LDP = TP + 4;  // row stride of the k-major activation buffers
+constexpr int MLP_THREADS = 256;
+
+__device__ __forceinline__ float hidden_act(float v, int leaky) { return v > 0.0f ? v : (leaky ? v * 0.01f : 0.0f); }
+
+// acc[pi][ji] += sum_k A[k][p] * B[k][j] with p in {4*tp..4*tp+3, 64+4*tp..}, j in {4*tj..4*tj+3}
+__device__ __forceinline__ void gemm_8x4(const float* __restrict__ A, const float* __restrict__ B, int bstride, int K,
+                                         int tp, int tj, float acc[8][4]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(A + k * LDP + 4 * tp);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + k * LDP + 64 + 4 * tp);
+    const float4 b = *reinterpret_cast<const float4*>(B + k * bstride + 4 * tj);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+struct MlpSmem {
+  float* X;    // [INP][LDP]   enc, k-major
+  float* A1;   // [H][LDP]
+  float* A2;   // [H][LDP]
+  float* W0t;  // [INP][H]     W0^T  (forward B operand)
+  float* W1t;  // [H][H]       W1^T
+  float* W2t;  // [H][4]       W2^T, OUT padded to 4
+  float* W0n;  // [H][INP]     W0 as stored (backward B operand)      -- backward only
+  float* W1n;  // [H][H]
+  float* W2n;  // [4][H]
+  float* b0;   // [H]
+  float* b1;   // [H]
+  float* b2;   // [4]
+  float* dz2;  // [4][LDP]                                            -- backward only
+};
+
+__host__ __device__ inline int mlp_smem_floats(int INP, bool bwd) {
+  int n = INP * LDP + 2 * H * LDP + INP * H + H * H + H * 4 + 2 * H + 4;
+  if (bwd) n += H * INP + H * H + 4 * H + 4 * LDP;
+  return n;
+}
+
+__device__ __forceinline__ MlpSmem carve(float* base, int INP, bool bwd) {
+  MlpSmem s;
+  float* p = base;
+  s.X = p; p += INP * LDP;
+  s.A1 = p; p += H * LDP;
+  s.A2 = p; p += H * LDP;
+  s.W0t = p; p += INP * H;
+  s.W1t = p; p += H * H;
+  s.W2t = p; p += H * 4;
+  s.b0 = p; p += H;
+  s.b1 = p; p += H;
+  s.b2 = p; p += 4;
+  if (bwd) {
+    s.W0n = p; p += H * INP;
+    s.W1n = p; p += H * H;
+    s.W2n = p; p += 4 * H;
+    s.dz2 = p; p += 4 * LDP;
+  } else {
+    s.W0n = s.W1n = s.W2n = s.dz2 = nullptr;
+  }
+  return s;
+}
+
+__device__ __forceinline__ void load_weights(const MlpSmem& s, int IN, int INP, int OUT, bool bwd,
+                                             const float* __restrict__ w0, const float* __restrict__ b0,
+                                             const float* __restrict__ w1, const float* __restrict__ b1,
+                                             const float* __restrict__ w2, const float* __restrict__ b2) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < H * INP; e += MLP_THREADS) {  // w0 is (H, IN)
+    const int j = e / INP, k = e % INP;
+    const float v = k < IN ? w0[j * IN + k] : 0.0f;
+    s.W0t[k * H + j] = v;
+    if (bwd) s.W0n[j * INP + k] = v;
+  }
+  for (int e = tid; e < H * H; e += MLP_THREADS) {  // w1 is (H, H)
+    const int j = e / H, k = e % H;
+    const float v = w1[e];
+    s.W1t[k * H + j] = v;
+    if (bwd) s.W1n[e] = v;
+  }
+  for (int e = tid; e < 4 * H; e += MLP_THREADS) {  // w2 is (OUT, H)
+    const int c = e / H, k = e % H;
+    const float v = c < OUT ? w2[c * H + k] : 0.0f;
+    s.W2t[k * 4 + c] = v;
+    if (bwd) s.W2n[e] = v;
+  }
+  for (int e = tid; e < H; e += MLP_THREADS) {
+    s.b0[e] = b0[e];
+    s.b1[e] = b1[e];
+  }
+  if (tid < 4) s.b2[tid] = tid < OUT ? b2[tid] : 0.0f;
+}
+
+// enc tile -> X (k-major), zero-padded rows/points
+__device__ __forceinline__ void load_enc_tile(const MlpSmem& s, const float* __restrict__ enc, int64_t p0, int64_t P,
+                                              int IN, int INP) {
+  for (int e = threadIdx.x; e < TP * INP; e += MLP_THREADS) {
+    int p, k;
+    if (IN == INP) {
+      p = e / IN;
+      k = e % IN;
+    } else {
+      p = e / INP;
+      k = e % INP;
+    }
+    float v = 0.0f;
+    if (p0 + p < P && k < IN) v = enc[(p0 + p) * IN + k];
+    s.X[k * LDP + p] = v;
+  }
+}
+
+// dst[j][p] = act(sum_k src[k][p] * Wt[k][j] + b[j])
+__device__ __forceinline__ void hidden_layer(const float* src, const float* Wt, const float* b, int K, float* dst,
+                                             int leaky) {
+  const int tp = threadIdx.x % 16, tj = threadIdx.x / 16;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  gemm_8x4(src, Wt, H, K, tp, tj, acc);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float bj = b[4 * tj + j];
+    float4 lo, hi;
+    lo.x = hidden_act(acc[0][j] + bj, leaky); lo.y = hidden_act(acc[1][j] + bj, leaky);
+    lo.z = hidden_act(acc[2][j] + bj, leaky); lo.w = hidden_act(acc[3][j] + bj, leaky);
+    hi.x = hidden_act(acc[4][j] + bj, leaky); hi.y = hidden_act(acc[5][j] + bj, leaky);
+    hi.z = hidden_act(acc[6][j] + bj, leaky); hi.w = hidden_act(acc[7][j] + bj, leaky);
+    *reinterpret_cast<float4*>(dst + (4 * tj + j) * LDP + 4 * tp) = lo;
+    *reinterpret_cast<float4*>(dst + (4 * tj + j) * LDP + 64 + 4 * tp) = hi;
+  }
+}
+
+// thread p < TP: out[c] = sigmoid(sum_k A2[k][p] * W2t[k][c] + b2[c])
+__device__ __forceinline__ void output_layer(const MlpSmem& s, int p, float out[4]) {
+  float acc[4] = {s.b2[0], s.b2[1], s.b2[2], s.b2[3]};
+#pragma unroll 8
+  for (int k = 0; k < H; ++k) {
+    const float a = s.A2[k * LDP + p];
+    const float4 w = *reinterpret_cast<const float4*>(s.W2t + k * 4);
+    acc[0] = fmaf(a, w.x, acc[0]);
+    acc[1] = fmaf(a, w.y, acc[1]);
+    acc[2] = fmaf(a, w.z, acc[2]);
+    acc[3] = fmaf(a, w.w, acc[3]);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = 1.0f / (1.0f + expf(-acc[c]));
+}
+
+__global__ void __launch_bounds__(MLP_THREADS)
+    mlp3_fwd_kernel(const float* __restrict__ enc, int64_t P, int IN, int INP, int OUT, int leaky,
+                    const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                    float* __restrict__ rgb) {
+  extern __shared__ __align__(16) float smem_f[];
+  const MlpSmem s = carve(smem_f, INP, false);
+  load_weights(s, IN, INP, OUT, false, w0, b0, w1, b1, w2, b2);
+  const int64_t tiles = (P + TP - 1) / TP;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * TP;
+    __syncthreads();  // weights visible / previous tile done with X and A2
+    load_enc_tile(s, enc, p0, P, IN, INP);
+    __syncthreads();
+    hidden_layer(s.X, s.W0t, s.b0, INP, s.A1, leaky);
+    __syncthreads();
+    hidden_layer(s.A1, s.W1t, s.b1, H, s.A2, leaky);
+    __syncthreads();
+    const int p = threadIdx.x;
+    if (p < TP && p0 + p < P) {
+      float out[4];
+      output_layer(s, p, out);
+      for (int c = 0; c < OUT; ++c) rgb[(p0 + p) * OUT + c] = out[c];
+    }
+  }
+}
+
+// partial-gradient layout per CTA (floats): dw0 [H*IN] | db0 [H] | dw1 [H*H] | db1 [H] | dw2 [OUT*H] | db2 [OUT]
+__host__ __device__ inline int mlp_param_floats(int IN, int OUT) { return H * IN + H + H * H + H + OUT * H + OUT; }
+
+__global__ void __launch_bounds__(MLP_THREADS)
+    mlp3_bwd_kernel(const float* __restrict__ enc, const float* __restrict__ drgb, int64_t P, int IN, int INP, int OUT,
+                    int leaky, const float* __restrict__ w0, const float* __restrict__ b0,
+                    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                    const float* __restrict__ b2, float* __restrict__ denc, float* __restrict__ partials) {
+  extern __shared__ __align__(16) float smem_f[];
+  const MlpSmem s = carve(smem_f, INP, true);
+  load_weights(s, IN, INP, OUT, true, w0, b0, w1, b1, w2, b2);
+  const int tid = threadIdx.x;
+  const int tp = tid % 16, tj = tid / 16;
+
+  // gradient accumulators that live in registers across all tiles of this CTA
+  float g_w1[4][4];   // dw1[j = tp + 16 a][k = tj + 16 b]
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) g_w1[a][b] = 0.0f;
+  float g_w0[16];     // dw0[j = tid % 64][i = tid / 64 + 4 m], m < INP / 4
+#pragma unroll
+  for (int m = 0; m < 16; ++m) g_w0[m] = 0.0f;
+  float g_w2 = 0.0f;  // dw2[c = tid / 64][k = tid % 64]   (tid < 4*64: c < 4)
+  float g_b = 0.0f;   // tid < 64: db1[tid]; 64 <= tid < 128: db0[tid-64]; 128 <= tid < 132: db2[tid-128]
+
+  const int64_t tiles = (P + TP - 1) / TP;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * TP;
+    __syncthreads();
+    load_enc_tile(s, enc, p0, P, IN, INP);
+    __syncthreads();
+    hidden_layer(s.X, s.W0t, s.b0, INP, s.A1, leaky);
+    __syncthreads();
+    hidden_layer(s.A1, s.W1t, s.b1, H, s.A2, leaky);
+    __syncthreads();
+    // dz2 = drgb * y * (1 - y), stored [c][p]; padded points / channels contribute zero
+    if (tid < TP) {
+      float out[4];
+      output_layer(s, tid, out);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float g = 0.0f;
+        if (c < OUT && p0 + tid < P) g = drgb[(p0 + tid) * OUT + c] * out[c] * (1.0f - out[c]);
+        s.dz2[c * LDP + tid] = g;
+      }
+    }
+    __syncthreads();
+    // dw2[c][k] += sum_p dz2[c][p] * a2[k][p] ; db2[c] += sum_p dz2[c][p]
+    {
+      const int c = tid / H, k = tid % H;  // 256 threads = 4 x 64
+      float acc = 0.0f;
+      for (int p = 0; p < TP; p += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(s.dz2 + c * LDP + p);
+        const float4 a = *reinterpret_cast<const float4*>(s.A2 + k * LDP + p);
+        acc = fmaf(d.x, a.x, acc); acc = fmaf(d.y, a.y, acc); acc = fmaf(d.z, a.z, acc); acc = fmaf(d.w, a.w, acc);
+      }
+      g_w2 += acc;
+      if (tid >= 128 && tid < 132) {
+        float sb = 0.0f;
+        for (int p = 0; p < TP; ++p) sb += s.dz2[(tid - 128) * LDP + p];
+        g_b += sb;
+      }
+    }
+    __syncthreads();
+    // dz1[j][p] = (sum_c dz2[c][p] * w2[c][j]) * act'(a2[j][p]), in place over A2
+    {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = 4 * tj + j;
+        const float w20 = s.W2n[0 * H + jj], w21 = s.W2n[1 * H + jj], w22 = s.W2n[2 * H + jj], w23 = s.W2n[3 * H + jj];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int pp = half * 64 + 4 * tp;
+          const float4 a = *reinterpret_cast<const float4*>(s.A2 + jj * LDP + pp);
+          const float4 d0 = *reinterpret_cast<const float4*>(s.dz2 + 0 * LDP + pp);
+          const float4 d1 = *reinterpret_cast<const float4*>(s.dz2 + 1 * LDP + pp);
+          const float4 d2 = *reinterpret_cast<const float4*>(s.dz2 + 2 * LDP + pp);
+          const float4 d3 = *reinterpret_cast<const float4*>(s.dz2 + 3 * LDP + pp);
+          const float slope = leaky ? 0.01f : 0.0f;
+          float4 r;
+          r.x = fmaf(d3.x, w23, fmaf(d2.x, w22, fmaf(d1.x, w21, d0.x * w20))) * (a.x > 0.0f ? 1.0f : slope);
+          r.y = fmaf(d3.y, w23, fmaf(d2.y, w22, fmaf(d1.y, w21, d0.y * w20))) * (a.y > 0.0f ? 1.0f : slope);
+          r.z = fmaf(d3.z, w23, fmaf(d2.z, w22, fmaf(d1.z, w21, d0.z * w20))) * (a.z > 0.0f ? 1.0f : slope);
+          r.w = fmaf(d3.w, w23, fmaf(d2.w, w22, fmaf(d1.w, w21, d0.w * w20))) * (a.w > 0.0f ? 1.0f : slope);
+          *reinterpret_cast<float4*>(s.A2 + jj * LDP + pp) = r;
+        }
+      }
+    }
+    __syncthreads();
+    // dw1[j][k] += sum_p dz1[j][p] * a1[k][p] ; db1[j] += sum_p dz1[j][p]
+    {
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+      for (int p = 0; p < TP; p += 4) {
+        float4 dz[4], av[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dz[a] = *reinterpret_cast<const float4*>(s.A2 + (tp + 16 * a) * LDP + p);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) av[b] = *reinterpret_cast<const float4*>(s.A1 + (tj + 16 * b) * LDP + p);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            acc[a][b] = fmaf(dz[a].x, av[b].x, acc[a][b]);
+            acc[a][b] = fmaf(dz[a].y, av[b].y, acc[a][b]);
+            acc[a][b] = fmaf(dz[a].z, av[b].z, acc[a][b]);
+            acc[a][b] = fmaf(dz[a].w, av[b].w, acc[a][b]);
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) g_w1[a][b] += acc[a][b];
+      if (tid < H) {
+        float sb = 0.0f;
+        for (int p = 0; p < TP; p += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(s.A2 + tid * LDP + p);
+          sb += (d.x + d.y) + (d.z + d.w);
+        }
+        g_b += sb;
+      }
+    }
+    // dz0[k][p] = (sum_j dz1[j][p] * w1[j][k]) * act'(a1[k][p]) -> registers, then in place over A1
+    {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+      gemm_8x4(s.A2, s.W1n, H, H, tp, tj, acc);
+      __syncthreads();  // every thread is done reading A1 (dw1) before it is overwritten
+      const float slope = leaky ? 0.01f : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = 4 * tj + j;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float* ptr = s.A1 + kk * LDP + half * 64 + 4 * tp;
+          const float4 a = *reinterpret_cast<const float4*>(ptr);
+          float4 r;
+          r.x = acc[half * 4 + 0][j] * (a.x > 0.0f ? 1.0f : slope);
+          r.y = acc[half * 4 + 1][j] * (a.y > 0.0f ? 1.0f : slope);
+          r.z = acc[half * 4 + 2][j] * (a.z > 0.0f ? 1.0f : slope);
+          r.w = acc[half * 4 + 3][j] * (a.w > 0.0f ? 1.0f : slope);
+          *reinterpret_cast<float4*>(ptr) = r;
+        }
+      }
+    }
+    __syncthreads();
+    // dw0[j][i] += sum_p dz0[j][p] * x[i][p] ; db0[j] += sum_p dz0[j][p]
+    {
+      const int j = tid % H, i0 = tid / H;  // i = i0 + 4 m
+      const int nm = INP / 4;
+      for (int p = 0; p < TP; p += 4) {
+        const float4 d = *reinterpret_cast<const float4*>(s.A1 + j * LDP + p);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          if (m < nm) {
+            const float4 xv = *reinterpret_cast<const float4*>(s.X + (i0 + 4 * m) * LDP + p);
+            g_w0[m] = fmaf(d.x, xv.x, fmaf(d.y, xv.y, fmaf(d.z, xv.z, fmaf(d.w, xv.w, g_w0[m]))));
+          }
+        }
+      }
+      if (tid >= 64 && tid < 128) {
+        float sb = 0.0f;
+        for (int p = 0; p < TP; p += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(s.A1 + (tid - 64) * LDP + p);
+          sb += (d.x + d.y) + (d.z + d.w);
+        }
+        g_b += sb;
+      }
+    }
+    // denc[p][i] = sum_k dz0[k][p] * w0[k][i]   (INP / 4 column groups of 4; thread -> 4 points x 4 columns)
+    {
+      const int groups = INP / 4;                       // column groups
+      for (int e = tid; e < (TP / 4) * groups; e += MLP_THREADS) {
+        const int pg = e % (TP / 4), cg = e / (TP / 4);
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) {
+          const float4 d = *reinterpret_cast<const float4*>(s.A1 + k * LDP + 4 * pg);
+          const float4 w = *reinterpret_cast<const float4*>(s.W0n + k * INP + 4 * cg);
+          const float dv[4] = {d.x, d.y, d.z, d.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], wv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int64_t p = p0 + 4 * pg + a;
+          if (p < P) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              if (4 * cg + b < IN) denc[p * IN + 4 * cg + b] = acc[a][b];
+          }
+        }
+      }
+    }
+  }
+
+  // one partial-gradient record per CTA
+  float* out = partials + static_cast<int64_t>(blockIdx.x) * mlp_param_floats(IN, OUT);
+  float* o_dw0 = out;
+  float* o_db0 = o_dw0 + H * IN;
+  float* o_dw1 = o_db0 + H;
+  float* o_db1 = o_dw1 + H * H;
+  float* o_dw2 = o_db1 + H;
+  float* o_db2 = o_dw2 + OUT * H;
+  {
+    const int j = tid % H, i0 = tid / H;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int i = i0 + 4 * m;
+      if (m < INP / 4 && i < IN) o_dw0[j * IN + i] = g_w0[m];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) o_dw1[(tp + 16 * a) * H + (tj + 16 * b)] = g_w1[a][b];
+  if (tid / H < OUT) o_dw2[(tid / H) * H + tid % H] = g_w2;
+  if (tid < 64) o_db1[tid] = g_b;
+  else if (tid < 128) o_db0[tid - 64] = g_b;
+  else if (tid < 128 + OUT) o_db2[tid - 128] = g_b;
+}
+
+// grads[i] += sum over CTAs of partials[cta][i], routed to the six parameter-gradient buffers
+__global__ void __launch_bounds__(256)
+    mlp3_reduce_kernel(const float* __restrict__ partials, int n_cta, int IN, int OUT, float* __restrict__ dw0,
+                       float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1,
+                       float* __restrict__ dw2, float* __restrict__ db2) {
+  const int n = mlp_param_floats(IN, OUT);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int c = 0; c < n_cta; ++c) s += partials[static_cast<int64_t>(c) * n + i];
+  int o = i;
+  if (o < H * IN) { dw0[o] += s; return; }
+  o -= H * IN;
+  if (o < H) { db0[o] += s; return; }
+  o -= H;
+  if (o < H * H) { dw1[o] += s; return; }
+  o -= H * H;
+  if (o < H) { db1[o] += s; return; }
+  o -= H;
+  if (o < OUT * H) { dw2[o] += s; return; }
+  o -= OUT * H;
+  db2[o] += s;
+}
+
+static int mlp_grid(int64_t P, size_t smem_bytes) {
+  const int per_sm = smem_bytes <= 110 * 1024 ? 2 : 1;
+  return static_cast<int>(std::min<int64_t>(ceil_div(P, TP), static_cast<int64_t>(per_sm) * sm_count()));
+}
+
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_mlp3_supported(int32_t in_dim, int32_t h1, int32_t h2, int32_t out_dim) {
+  return in_dim >= 1 && in_dim <= 64 && h1 == gngf::H && h2 == gngf::H && out_dim >= 1 && out_dim <= 4;
+}
+
+int gngf_mlp3_fwd(const float* enc, int64_t P, int32_t in_dim, int32_t out_dim, int32_t leaky, const float* w0,
+                  const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, float* rgb,
+                  void* stream) {
+  if (!gngf_mlp3_supported(in_dim, gngf::H, gngf::H, out_dim) || P < 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const int INP = (in_dim + 3) & ~3;
+  const size_t smem = sizeof(float) * gngf::mlp_smem_floats(INP, false);
+  if (cudaFuncSetAttribute(gngf::mlp3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem)) != cudaSuccess)
+    return gngf::check_launch();
+  gngf::mlp3_fwd_kernel<<<gngf::mlp_grid(P, smem), gngf::MLP_THREADS, smem, gngf::as_stream(stream)>>>(
+      enc, P, in_dim, INP, out_dim, leaky, w0, b0, w1, b1, w2, b2, rgb);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int64_t gngf_mlp3_bwd_workspace_floats(int32_t in_dim, int32_t out_dim) {
+  return static_cast<int64_t>(2 * gngf::sm_count()) * gngf::mlp_param_floats(in_dim, out_dim);
+}
+
+int gngf_mlp3_bwd(const float* enc, const float* drgb, int64_t P, int32_t in_dim, int32_t out_dim, int32_t leaky,
+                  const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                  float* denc, float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, float* workspace,
+                  void* stream) {
+  if (!gngf_mlp3_supported(in_dim, gngf::H, gngf::H, out_dim) || P < 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GNGF_OK;
+  const int INP = (in_dim + 3) & ~3;
+  const size_t smem = sizeof(float) * gngf::mlp_smem_floats(INP, true);
+  cudaStream_t st = gngf::as_stream(stream);
+  if (cudaFuncSetAttribute(gngf::mlp3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem)) != cudaSuccess)
+    return gngf::check_launch();
+  const int grid = gngf::mlp_grid(P, smem);
+  gngf::mlp3_bwd_kernel<<<grid, gngf::MLP_THREADS, smem, st>>>(enc, drgb, P, in_dim, INP, out_dim, leaky, w0, b0, w1,
+                                                                b1, w2, b2, denc, workspace);
+  gngf::note_launch();
+  int rc = gngf::check_launch();
+  if (rc) return rc;
+  const int n = gngf::mlp_param_floats(in_dim, out_dim);
+  gngf::mlp3_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, grid, in_dim, out_dim, dw0, db0, dw1, db1, dw2,
+                                                            db2);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

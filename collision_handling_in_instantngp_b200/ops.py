@@ -166,8 +166,17 @@ class ForwardState:
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
     cnt: Optional[torch.Tensor] = None                           # (S,) int32
-    mlp_acts: List[torch.Tensor] = field(default_factory=list)   # enc, a1, ..., rgb
+    mlp_acts: List[torch.Tensor] = field(default_factory=list)   # enc, a1, ..., rgb  (enc, rgb when fused)
+    mlp_fused: bool = False
     err_flag: Optional[torch.Tensor] = None
+
+
+def _mlp3_supported(mlp_w) -> bool:
+    """True when the decoder has the reference's shape IN -> 64 -> 64 -> OUT (fused kernels of k6_mlp.cu)."""
+    if len(mlp_w) != 3:
+        return False
+    return bool(_lib.load().gngf_mlp3_supported(mlp_w[0].shape[1], mlp_w[0].shape[0], mlp_w[1].shape[0],
+                                                mlp_w[2].shape[0])) and mlp_w[1].shape[1] == mlp_w[0].shape[0]
 
 
 def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device):
@@ -235,12 +244,22 @@ class GNGFPath(torch.autograd.Function):
             uvals = state.utopv if cfg.topk_only else state.uprobs
             call("gngf_lattice_colsum", lat, state.cnt.data_ptr(), uvals.data_ptr(), N, colsum.data_ptr(), st)
 
-        acts = [enc]
-        h = enc
-        hidden_act = ACT_LEAKY_RELU if cfg.leaky else ACT_RELU
-        for i in range(nm):
-            h = linear_fwd(h, mlp_w[i], mlp_b[i], hidden_act if i < nm - 1 else ACT_SIGMOID)
-            acts.append(h)
+        state.mlp_fused = _mlp3_supported(mlp_w)
+        if state.mlp_fused:
+            # K6: one kernel, hidden activations never leave the SM (recomputed in backward)
+            C = mlp_w[2].shape[0]
+            rgb_out = torch.empty((P, C), dtype=torch.float32, device=dev)
+            call("gngf_mlp3_fwd", enc.data_ptr(), P, L * F, C, int(cfg.leaky), mlp_w[0].data_ptr(), mlp_b[0].data_ptr(),
+                 mlp_w[1].data_ptr(), mlp_b[1].data_ptr(), mlp_w[2].data_ptr(), mlp_b[2].data_ptr(), rgb_out.data_ptr(),
+                 st)
+            acts = [enc, rgb_out]
+        else:
+            acts = [enc]
+            h = enc
+            hidden_act = ACT_LEAKY_RELU if cfg.leaky else ACT_RELU
+            for i in range(nm):
+                h = linear_fwd(h, mlp_w[i], mlp_b[i], hidden_act if i < nm - 1 else ACT_SIGMOID)
+                acts.append(h)
         state.mlp_acts = acts
         state.x = x
         ctx.state = state
@@ -264,7 +283,7 @@ class GNGFPath(torch.autograd.Function):
         nh, nm = (0 if cfg.use_hash else cfg.n_hpd), cfg.n_mlp
         hpd_w = list(params[0:2 * nh:2])
         tables = list(params[2 * nh:2 * nh + L])
-        mlp_w = list(params[2 * nh + L::2])
+        mlp_w, mlp_b = list(params[2 * nh + L::2]), list(params[2 * nh + L + 1::2])
         st = _stream()
         S = 0 if cfg.use_hash else lat.num_level_nodes
         U = lat.num_nodes
@@ -288,12 +307,22 @@ class GNGFPath(torch.autograd.Function):
         acts = state.mlp_acts
         rgb = acts[-1]
         grad_rgb = _f32c(grad_rgb)
-        dz = torch.empty_like(rgb)
-        call("gngf_sigmoid_bwd", grad_rgb.data_ptr(), rgb.data_ptr(), rgb.numel(), dz.data_ptr(), st)
-        hidden_act = ACT_LEAKY_RELU if cfg.leaky else ACT_RELU
-        for i in range(nm - 1, -1, -1):
-            dz = linear_bwd(dz, acts[i], mlp_w[i], hidden_act if i > 0 else ACT_NONE, True, g_mlp_w[i], g_mlp_b[i])
-        denc = dz
+        if state.mlp_fused:
+            C = rgb.shape[1]
+            denc = torch.empty((P, L * F), dtype=torch.float32, device=dev)
+            work = torch.empty(_lib.load().gngf_mlp3_bwd_workspace_floats(L * F, C), dtype=torch.float32, device=dev)
+            call("gngf_mlp3_bwd", acts[0].data_ptr(), grad_rgb.data_ptr(), P, L * F, C, int(cfg.leaky),
+                 mlp_w[0].data_ptr(), mlp_b[0].data_ptr(), mlp_w[1].data_ptr(), mlp_b[1].data_ptr(), mlp_w[2].data_ptr(),
+                 mlp_b[2].data_ptr(), denc.data_ptr(), g_mlp_w[0].data_ptr(), g_mlp_b[0].data_ptr(),
+                 g_mlp_w[1].data_ptr(), g_mlp_b[1].data_ptr(), g_mlp_w[2].data_ptr(), g_mlp_b[2].data_ptr(),
+                 work.data_ptr(), st)
+        else:
+            dz = torch.empty_like(rgb)
+            call("gngf_sigmoid_bwd", grad_rgb.data_ptr(), rgb.data_ptr(), rgb.numel(), dz.data_ptr(), st)
+            hidden_act = ACT_LEAKY_RELU if cfg.leaky else ACT_RELU
+            for i in range(nm - 1, -1, -1):
+                dz = linear_bwd(dz, acts[i], mlp_w[i], hidden_act if i > 0 else ACT_NONE, True, g_mlp_w[i], g_mlp_b[i])
+            denc = dz
 
         gtab = make_tables(g_tables)
         if cfg.use_hash:

@@ -102,6 +102,21 @@ int gngf_sigmoid_bwd(const float* dy, const float* y, int64_t n, float* dz, void
 /* backward of the first HPD layer: dw0 (N,2) += dz^T c(u), db0 (N) += colsum(dz)                        */
 int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, float* dw0, float* db0, void* stream);
 
+/* ---- K6: fused decoder MLP (models.py:382-392, 468-470) for the reference's shape IN -> 64 -> 64 -> OUT -----
+ * rgb (P,OUT) = sigmoid(W2 act(W1 act(W0 enc + b0) + b1) + b2), act = ReLU or LeakyReLU(0.01); activations stay
+ * in shared memory.  The backward recomputes them, writes denc (P,IN) and ADDS the parameter gradients into
+ * dw0 (64,IN), db0, dw1 (64,64), db1, dw2 (OUT,64), db2; workspace: gngf_mlp3_bwd_workspace_floats() floats.
+ * gngf_mlp3_supported() says whether a decoder shape is covered (otherwise use gngf_linear_fwd/bwd).        */
+int gngf_mlp3_supported(int32_t in_dim, int32_t h1, int32_t h2, int32_t out_dim);
+int gngf_mlp3_fwd(const float* enc, int64_t P, int32_t in_dim, int32_t out_dim, int32_t leaky, const float* w0,
+                  const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, float* rgb,
+                  void* stream);
+int64_t gngf_mlp3_bwd_workspace_floats(int32_t in_dim, int32_t out_dim);
+int gngf_mlp3_bwd(const float* enc, const float* drgb, int64_t P, int32_t in_dim, int32_t out_dim, int32_t leaky,
+                  const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                  float* denc, float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, float* workspace,
+                  void* stream);
+
 /* ---- K3: softmax + nan_to_num + top-k (models.py:85,111 and DifferentiableTopk.forward 7-19) --------
  * logits (R,T) -> probs (R,T) (may alias logits, may be NULL), topv (R,K) sorted descending,
  * topi (R,K) int32, ties broken towards the lower index; row_max / row_sum (R) optional.               */

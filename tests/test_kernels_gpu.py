@@ -154,3 +154,61 @@ def test_missing_gpu_tensor_is_rejected():
     from collision_handling_in_instantngp_b200 import GngfError
     with pytest.raises(GngfError):
         ops.corners_fwd(torch.zeros(4, 2), build_lattice([8]))
+
+
+@pytest.mark.parametrize("P,IN,OUT,leaky", [(1000, 8, 3, 0), (57404, 8, 3, 0), (333, 32, 3, 1), (129, 6, 1, 0),
+                                             (4097, 64, 3, 0), (1, 8, 3, 0)])
+def test_fused_decoder_mlp(P, IN, OUT, leaky):
+    """K6 against a float64 evaluation of models.py:382-392 and its gradients."""
+    from collision_handling_in_instantngp_b200 import _lib
+    rng = np.random.default_rng(P + IN)
+    enc = (rng.standard_normal((P, IN)) * 0.5).astype(np.float32)
+    ws = [(rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32) for i, o in [(IN, 64), (64, 64), (64, OUT)]]
+    bs = [(rng.standard_normal(o) * 0.1).astype(np.float32) for o in (64, 64, OUT)]
+    drgb = rng.standard_normal((P, OUT)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    enc_t, ws_t, bs_t, drgb_t = t(enc), [t(w) for w in ws], [t(b) for b in bs], t(drgb)
+    rgb = torch.empty((P, OUT), device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("gngf_mlp3_fwd", enc_t.data_ptr(), P, IN, OUT, leaky, ws_t[0].data_ptr(), bs_t[0].data_ptr(),
+              ws_t[1].data_ptr(), bs_t[1].data_ptr(), ws_t[2].data_ptr(), bs_t[2].data_ptr(), rgb.data_ptr(), st)
+    acts = O.decoder_forward(enc.astype(np.float64), [w.astype(np.float64) for w in ws],
+                             [b.astype(np.float64) for b in bs], bool(leaky))
+    assert rel_err(rgb.cpu().numpy(), acts[-1]) < 1e-5
+    denc = torch.empty((P, IN), device=DEV)
+    gw = [torch.zeros_like(w) for w in ws_t]
+    gb = [torch.zeros_like(b) for b in bs_t]
+    work = torch.empty(_lib.load().gngf_mlp3_bwd_workspace_floats(IN, OUT), device=DEV)
+    _lib.call("gngf_mlp3_bwd", enc_t.data_ptr(), drgb_t.data_ptr(), P, IN, OUT, leaky, ws_t[0].data_ptr(),
+              bs_t[0].data_ptr(), ws_t[1].data_ptr(), bs_t[1].data_ptr(), ws_t[2].data_ptr(), bs_t[2].data_ptr(),
+              denc.data_ptr(), gw[0].data_ptr(), gb[0].data_ptr(), gw[1].data_ptr(), gb[1].data_ptr(), gw[2].data_ptr(),
+              gb[2].data_ptr(), work.data_ptr(), st)
+    dz = drgb.astype(np.float64) * acts[-1] * (1 - acts[-1])
+    dws, dbs, dx = O._mlp_backward(acts[:-1], [w.astype(np.float64) for w in ws], dz, leaky=bool(leaky))
+    assert rel_err(denc.cpu().numpy(), dx) < 1e-5
+    for i in range(3):
+        assert rel_err(gw[i].cpu().numpy(), dws[i]) < 2e-5, i
+        assert rel_err(gb[i].cpu().numpy(), dbs[i]) < 2e-5, i
+
+
+def test_generic_decoder_shape_uses_linear_layers():
+    """A decoder that is not IN-64-64-OUT goes through gngf_linear_fwd/bwd and still matches the oracle."""
+    from golden_util import loss_cfg, oracle_cfg, params_of
+    from parity_util import build_net, run_step
+    g = dict(load("cfg2_small"))
+    rng = np.random.default_rng(5)
+    g["cfg"] = dict(g["cfg"], mlp=[32, 48])
+    shapes = {"mlp.0.0": (32, 8), "mlp.1.0": (48, 32), "mlp.2.0": (3, 48)}
+    for k, (o, i) in shapes.items():
+        g[f"param.{k}.weight"] = (rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32)
+        g[f"param.{k}.bias"] = (rng.standard_normal(o) * 0.1).astype(np.float32)
+    net = build_net(g)
+    out = run_step(net, g)
+    assert not out["state"].mlp_fused
+    p = params_of(g)
+    fwd = O.gngf_forward(p, g["x"], oracle_cfg(g))
+    grads = O.gngf_backward(p, g["x"], g["y"], oracle_cfg(g), fwd, loss_cfg(g))
+    assert rel_err(out["rgb"], fwd["rgb"]) < 1e-5
+    for i in range(3):
+        assert rel_err(out["grads"][f"mlp.{i}.0.weight"], grads["mlp_w"][i]) < 1e-4
+    assert rel_err(out["grads"]["encoding._hash_tables.2.weight"], grads["tables"][2]) < 1e-4
