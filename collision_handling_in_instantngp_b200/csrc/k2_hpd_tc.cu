@@ -1,0 +1,346 @@
+// K2 (tensor-core path): the wide HPD output layer  logits (U, T) = h3 (U, 128) W3^T + b3  -- the one real dense
+// contraction of the path (models.py:80-88,105-106; 79 GFLOP per batch at the published configuration when
+// evaluated per row, 134 MFLOP per row at T = 2^19) -- on the 5th-generation tensor cores:
+//
+//   * fp32 accuracy from bf16 tensor cores: every fp32 operand is split into three bf16 planes
+//     x = hi + mid + lo (8 mantissa bits each) and the product is the six partial products of order <= 2
+//     (hi.hi, hi.mid, mid.hi, hi.lo, lo.hi, mid.mid) accumulated in fp32 in TMEM.  Plain TF32 / BF16 operands
+//     flip 1-10 % of the top-k selections; the 3-way split flips none.
+//   * operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 2-stage shared-memory ring,
+//     tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16) is issued by one thread, accumulators live in
+//     TMEM (2 x 128 columns, double-buffered so that the epilogue of tile i overlaps the MMAs of tile i+1),
+//     the epilogue warps read them back with tcgen05.ld and add the bias.
+//   * persistent: one CTA per SM walks the output tiles; warp 0 = TMA producer, warp 1 = MMA issuer / TMEM
+//     owner, warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4)...).
+//
+// gngf_split_bf16x3 produces the planes (one elementwise pass; the weight planes are reusable until the next
+// optimizer step).
+#include <algorithm>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace gngf {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2, PLANES = 3;
+constexpr int UMMA_K = 16;
+constexpr uint32_t PLANE_BYTES = BM * BK * 2;                         // 16 KB (BM == BN)
+constexpr uint32_t STAGE_BYTES = 2 * PLANES * PLANE_BYTES;            // 96 KB: A planes then B planes
+constexpr uint32_t TMEM_COLS = 2 * BN;                                // two accumulators
+constexpr int THREADS = 192;
+constexpr uint32_t EPI_LD = 33;                                        // padded row of the epilogue staging tile
+constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_LD * 4;                    // one 32x32 fp32 tile per epilogue warp
+constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// kind::f16, BF16 x BF16 -> F32, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case GNGF_ACT_RELU: return fmaxf(v, 0.0f);
+    case GNGF_ACT_LEAKY_RELU: return v > 0.0f ? v : v * 0.01f;
+    case GNGF_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// C (M,N) = act(sum over plane pairs of A_i (M,K) B_j (N,K)^T + bias)
+__global__ void __launch_bounds__(THREADS, 1)
+    gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull + s, 1);
+      mbar_init(tempty + s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int tiles = num_m * num_n, kblocks = (K + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer ----
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          mbar_expect_tx(full + stage, STAGE_BYTES);
+          uint8_t* base = smem + stage * STAGE_BYTES;
+          for (int pl = 0; pl < PLANES; ++pl) {
+            tma_load_3d(base + pl * PLANE_BYTES, &map_a, kb * BK, m0, pl, full + stage);
+            tma_load_3d(base + (PLANES + pl) * PLANE_BYTES, &map_b, kb * BK, n0, pl, full + stage);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ----
+      constexpr uint32_t idesc = umma_idesc(BM, BN);
+      // partial products of order <= 2 of (hi + mid + lo)(hi + mid + lo)
+      const int pa[6] = {0, 0, 1, 0, 2, 1};
+      const int pb[6] = {0, 1, 0, 2, 0, 1};
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + PLANES * PLANE_BYTES;
+#pragma unroll
+          for (int pr = 0; pr < 6; ++pr) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ad = umma_desc(a_base + pa[pr] * PLANE_BYTES + k * UMMA_K * 2);
+              const uint64_t bd = umma_desc(b_base + pb[pr] * PLANE_BYTES + k * UMMA_K * 2);
+              umma_bf16(d, ad, bd, idesc, (kb | pr | k) != 0);
+            }
+          }
+          umma_commit(empty + stage);  // the stage may be refilled once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull + acc);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {  // ---- epilogue warps 2..5 ----
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      mbar_wait(tfull + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      float* stage_tile = epi + (warp - 2) * 32 * EPI_LD;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        // thread = accumulator row (TMEM lane); transpose through shared memory so that a warp stores
+        // 32 consecutive floats (one 128-byte line) of one output row per instruction
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage_tile[lane * EPI_LD + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        if (col < N) {
+          const float bcol = bias ? bias[col] : 0.0f;
+          const int r_end = min(32, M - (m0 + q * 32));
+          float* out = C + static_cast<int64_t>(m0 + q * 32) * N + col;
+          for (int r = 0; r < r_end; ++r) out[static_cast<int64_t>(r) * N] = act_apply(stage_tile[r * EPI_LD + lane] + bcol, act);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// x = hi + mid + lo, each bf16 (round-to-nearest): planes[0][i], planes[1][i], planes[2][i]
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int64_t n,
+                                                          __nv_bfloat16* __restrict__ planes) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float x = src[i];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  planes[i] = hi;
+  planes[n + i] = mid;
+  planes[2 * n + i] = lo;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// planes (3, rows, K) bf16 row-major -> 3-D tensor map {K, rows, 3}, box {64, 128, 1}, 128-byte swizzle
+static int make_plane_map(CUtensorMap* map, const void* planes, int64_t rows, int64_t K) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return GNGF_ERR_CUDA;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), 3};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(rows) * K * 2};
+  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GNGF_OK : GNGF_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace tc
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* stream) {
+  if (n < 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (n == 0) return GNGF_OK;
+  gngf::tc::split_bf16x3_kernel<<<static_cast<unsigned>(gngf::ceil_div(n, 256)), 256, 0, gngf::as_stream(stream)>>>(
+      src, n, reinterpret_cast<__nv_bfloat16*>(planes));
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
+                        int64_t K, int32_t act, float* C, void* stream) {
+  using namespace gngf::tc;
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || M >= (1ll << 31) || N >= (1ll << 31)) return GNGF_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b_planes)) & 15) return GNGF_ERR_INVALID_ARGUMENT;
+  CUtensorMap map_a, map_b;
+  int rc = make_plane_map(&map_a, a_planes, M, K);
+  if (rc) return rc;
+  rc = make_plane_map(&map_b, b_planes, N, K);
+  if (rc) return rc;
+  if (cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(SMEM_BYTES)) != cudaSuccess)
+    return gngf::check_launch();
+  const int64_t tiles = gngf::ceil_div(M, BM) * gngf::ceil_div(N, BN);
+  const int grid = static_cast<int>(std::min<int64_t>(tiles, gngf::sm_count()));
+  gemm_bf16x3_kernel<<<grid, THREADS, SMEM_BYTES, gngf::as_stream(stream)>>>(
+      map_a, map_b, bias, C, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), act);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

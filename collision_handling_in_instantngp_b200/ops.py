@@ -91,6 +91,25 @@ def linear_bwd(dz, x, w, act_prev, dx_needed, dw, db) -> Optional[torch.Tensor]:
     return dx
 
 
+def split_bf16x3(t: torch.Tensor) -> torch.Tensor:
+    """(3, *t.shape) bf16 planes with hi + mid + lo == t to ~2^-24 relative."""
+    t = _f32c(t)
+    planes = torch.empty((3, *t.shape), dtype=torch.bfloat16, device=t.device)
+    call("gngf_split_bf16x3", t.data_ptr(), t.numel(), planes.data_ptr(), _stream())
+    return planes
+
+
+def tc_linear_fwd(x, w, b, act, x_planes=None, w_planes=None) -> torch.Tensor:
+    """y = act(x w^T + b) on the tensor cores (tcgen05, split-bf16 operands, fp32 accumulate in TMEM)."""
+    M, K = x.shape
+    N = w.shape[0]
+    xp = split_bf16x3(x) if x_planes is None else x_planes
+    wp = split_bf16x3(w) if w_planes is None else w_planes
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    call("gngf_tc_gemm_bf16x3", xp.data_ptr(), wp.data_ptr(), _ptr(b), M, N, K, act, y.data_ptr(), _stream())
+    return y
+
+
 def softmax_topk_fwd(logits: torch.Tensor, k: int, inplace: bool = False, want_probs: bool = True):
     """probs = nan_to_num(softmax(logits)), (topv, topi) = topk(probs, k) with ties -> lower index."""
     _require_cuda(logits, "logits")

@@ -102,6 +102,16 @@ int gngf_sigmoid_bwd(const float* dy, const float* y, int64_t n, float* dz, void
 /* backward of the first HPD layer: dw0 (N,2) += dz^T c(u), db0 (N) += colsum(dz)                        */
 int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, float* dw0, float* db0, void* stream);
 
+/* ---- K2 (tensor cores): split-precision GEMM on tcgen05 ------------------------------------------------------
+ * gngf_split_bf16x3: x = hi + mid + lo in bf16; planes (3, n) row-major after src's own layout.
+ * gngf_tc_gemm_bf16x3: C (M,N) fp32 = act(sum of the six partial products of order <= 2 of
+ *   (A_hi+A_mid+A_lo)(M,K) (B_hi+B_mid+B_lo)(N,K)^T + bias(N)), fp32 accumulation in TMEM; TMA-staged operands;
+ *   a_planes (3,M,K), b_planes (3,N,K) bf16, 16-byte aligned, K % 8 == 0.  This is the HPD output layer
+ *   (models.py:80-88: Linear(128, T)) when T is large.                                                       */
+int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* stream);
+int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
+                        int64_t K, int32_t act, float* C, void* stream);
+
 /* ---- K6: fused decoder MLP (models.py:382-392, 468-470) for the reference's shape IN -> 64 -> 64 -> OUT -----
  * rgb (P,OUT) = sigmoid(W2 act(W1 act(W0 enc + b0) + b1) + b2), act = ReLU or LeakyReLU(0.01); activations stay
  * in shared memory.  The backward recomputes them, writes denc (P,IN) and ADDS the parameter gradients into
