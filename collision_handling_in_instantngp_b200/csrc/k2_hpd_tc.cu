@@ -262,6 +262,292 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K2 + K3 fused: streaming HPD output layer.  logits are never written: the epilogue keeps, per lattice node
+// (= accumulator row = one thread), the online-softmax statistics (running max, compensated running sum of
+// exp) and a sorted running top-K of the logits, while the MMA warp streams W3 tile by tile past a resident
+// 128-row tile of h3.  Work items are (row tile, column split); splits exist so that a small lattice with a
+// huge table still fills the chip, and are merged by hpd_stream_merge_kernel.
+// Selection runs on the logits (monotone in the probabilities); ties keep the lower index.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KTOP = 8;                                  // largest K handled by the fused epilogue
+constexpr int A_KBLOCKS = 2;                             // resident A tile: K <= 128
+constexpr uint32_t A_BYTES = A_KBLOCKS * PLANES * PLANE_BYTES;   // 96 KB
+constexpr uint32_t B_STAGE_BYTES = PLANES * PLANE_BYTES;         // 48 KB: one k-block of one column tile
+constexpr size_t STREAM_SMEM_BYTES = A_BYTES + STAGES * B_STAGE_BYTES + 1024 + 256;
+
+struct RowTop {
+  float v[KTOP];
+  int i[KTOP];
+};
+
+// insert (z, n) into the list sorted by (value desc, index asc); callers feed candidates in increasing index order
+__device__ __forceinline__ void top_insert(RowTop& t, int K, float z, int n) {
+  float cz = z;
+  int ci = n;
+  bool carried = false;
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    if (k < K) {
+      const bool sw = carried ? (cz >= t.v[k]) : (cz > t.v[k]);
+      const float tz = t.v[k];
+      const int tn = t.i[k];
+      t.v[k] = sw ? cz : tz;
+      t.i[k] = sw ? ci : tn;
+      cz = sw ? tz : cz;
+      ci = sw ? tn : ci;
+      carried |= sw;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+    hpd_stream_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const float* __restrict__ bias, int U, int T, int Kdim, int topk, int n_split,
+                          float* __restrict__ part_max, float* __restrict__ part_sum, float* __restrict__ part_topv,
+                          int* __restrict__ part_topi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_buf = smem;
+  uint8_t* b_ring = smem + A_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + A_BYTES + STAGES * B_STAGE_BYTES);
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* b_full = a_empty + 1;
+  uint64_t* b_empty = b_full + STAGES;
+  uint64_t* tfull = b_empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull + s, 1);
+      mbar_init(tempty + s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int row_tiles = (U + BM - 1) / BM, col_tiles = (T + BN - 1) / BN;
+  const int tiles_per_split = (col_tiles + n_split - 1) / n_split;
+  const int items = row_tiles * n_split;
+  const int kblocks = (Kdim + BK - 1) / BK;   // <= A_KBLOCKS
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer ----
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int m0 = (w / n_split) * BM, sp = w % n_split;
+        const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
+        mbar_wait(a_empty, a_phase ^ 1);
+        mbar_expect_tx(a_full, kblocks * PLANES * PLANE_BYTES);
+        for (int kb = 0; kb < kblocks; ++kb)
+          for (int pl = 0; pl < PLANES; ++pl)
+            tma_load_3d(a_buf + (kb * PLANES + pl) * PLANE_BYTES, &map_a, kb * BK, m0, pl, a_full);
+        a_phase ^= 1;
+        for (int nt = nt0; nt < nt1; ++nt) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(b_empty + stage, phase ^ 1);
+            mbar_expect_tx(b_full + stage, B_STAGE_BYTES);
+            for (int pl = 0; pl < PLANES; ++pl)
+              tma_load_3d(b_ring + stage * B_STAGE_BYTES + pl * PLANE_BYTES, &map_b, kb * BK, nt * BN, pl, b_full + stage);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ----
+      constexpr uint32_t idesc = umma_idesc(BM, BN);
+      const int pa[6] = {0, 0, 1, 0, 2, 1};
+      const int pb[6] = {0, 1, 0, 2, 0, 1};
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      const uint32_t a_base0 = smem_u32(a_buf);
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int sp = w % n_split;
+        const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int nt = nt0; nt < nt1; ++nt) {
+          mbar_wait(tempty + acc, acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * BN;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(b_full + stage, phase);
+            tc_fence_after();
+            const uint32_t a_base = a_base0 + kb * PLANES * PLANE_BYTES;
+            const uint32_t b_base = smem_u32(b_ring + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int pr = 0; pr < 6; ++pr) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t ad = umma_desc(a_base + pa[pr] * PLANE_BYTES + k * UMMA_K * 2);
+                const uint64_t bd = umma_desc(b_base + pb[pr] * PLANE_BYTES + k * UMMA_K * 2);
+                umma_bf16(d, ad, bd, idesc, (kb | pr | k) != 0);
+              }
+            }
+            umma_commit(b_empty + stage);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(tfull + acc);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        umma_commit(a_empty);  // every MMA that reads the resident A tile has completed
+      }
+    }
+  } else {  // ---- epilogue warps 2..5: thread = lattice node (row) ----
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int m0 = (w / n_split) * BM, sp = w % n_split;
+      const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
+      float m = -INFINITY, ssum = 0.0f, comp = 0.0f;
+      RowTop top;
+#pragma unroll
+      for (int k = 0; k < KTOP; ++k) {
+        top.v[k] = -INFINITY;
+        top.i[k] = 0x7fffffff;
+      }
+      for (int nt = nt0; nt < nt1; ++nt) {
+        const int n0 = nt * BN;
+        mbar_wait(tfull + acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          const int nb = n0 + c0;
+          if (nb >= T) continue;
+          float z[32];
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            z[j] = (nb + j < T) ? __uint_as_float(v[j]) + __ldg(bias + nb + j) : -INFINITY;
+            cmax = fmaxf(cmax, z[j]);
+          }
+          if (cmax > m) {  // rescale the running sum to the new maximum
+            const float sc = expf(m - cmax);
+            ssum *= sc;
+            comp *= sc;
+            m = cmax;
+          }
+          float csum = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) csum += expf(z[j] - m);
+          {  // compensated accumulation of the chunk sums (rows are up to 2^22 columns long)
+            const float y = csum - comp;
+            const float tsum = ssum + y;
+            comp = (tsum - ssum) - y;
+            ssum = tsum;
+          }
+          if (cmax > top.v[KTOP - 1]) {  // (a sorted top-KTOP is kept whatever K is; its head is the top-K)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (z[j] > top.v[KTOP - 1]) top_insert(top, KTOP, z[j], nb + j);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + acc);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      const int row = m0 + q * 32 + lane;
+      if (row < U) {
+        const int64_t o = static_cast<int64_t>(row) * n_split + sp;
+        part_max[o] = m;
+        part_sum[o] = ssum;
+#pragma unroll
+        for (int k = 0; k < KTOP; ++k) {
+          if (k < topk) {
+            part_topv[o * topk + k] = top.v[k];
+            part_topi[o * topk + k] = top.i[k];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// merges the column splits of one row: global max / normaliser, top-K of the logits, p = exp(z - max) / sum
+__global__ void __launch_bounds__(128)
+    hpd_stream_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                            const float* __restrict__ part_topv, const int* __restrict__ part_topi, int U, int n_split,
+                            int topk, float* __restrict__ row_max, float* __restrict__ row_sum,
+                            float* __restrict__ utopv, int* __restrict__ utopi) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= U) return;
+  float M = -INFINITY;
+  for (int s = 0; s < n_split; ++s) M = fmaxf(M, part_max[static_cast<int64_t>(row) * n_split + s]);
+  float S = 0.0f;
+  RowTop top;
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    top.v[k] = -INFINITY;
+    top.i[k] = 0x7fffffff;
+  }
+  for (int s = 0; s < n_split; ++s) {  // splits cover increasing column ranges: candidates arrive in index order
+    const int64_t o = static_cast<int64_t>(row) * n_split + s;
+    const float pm = part_max[o];
+    if (pm > -INFINITY) S += part_sum[o] * expf(pm - M);
+    for (int k = 0; k < topk; ++k) {
+      const float z = part_topv[o * topk + k];
+      if (z > top.v[KTOP - 1]) top_insert(top, KTOP, z, part_topi[o * topk + k]);
+    }
+  }
+  if (row_max) row_max[row] = M;
+  if (row_sum) row_sum[row] = S;
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    if (k < topk) {
+      float p = expf(top.v[k] - M) / S;
+      if (p != p) p = 0.0f;
+      utopv[static_cast<int64_t>(row) * topk + k] = p;
+      utopi[static_cast<int64_t>(row) * topk + k] = top.i[k];
+    }
+  }
+}
+
 // x = hi + mid + lo, each bf16 (round-to-nearest): planes[0][i], planes[1][i], planes[2][i]
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int64_t n,
                                                           __nv_bfloat16* __restrict__ planes) {
@@ -339,6 +625,49 @@ int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, cons
   const int grid = static_cast<int>(std::min<int64_t>(tiles, gngf::sm_count()));
   gemm_bf16x3_kernel<<<grid, THREADS, SMEM_BYTES, gngf::as_stream(stream)>>>(
       map_a, map_b, bias, C, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), act);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int64_t gngf_hpd_stream_workspace_floats(int64_t U, int64_t T, int32_t topk) {
+  using namespace gngf::tc;
+  const int64_t row_tiles = gngf::ceil_div(U, BM), col_tiles = gngf::ceil_div(T, BN);
+  int64_t n_split = std::max<int64_t>(1, std::min<int64_t>(col_tiles, (2 * gngf::sm_count()) / row_tiles));
+  return U * n_split * (2 + 2 * static_cast<int64_t>(topk)) + 1;
+}
+
+int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t U, int64_t T,
+                        int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max, float* row_sum,
+                        float* workspace, void* stream) {
+  using namespace gngf::tc;
+  if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > A_KBLOCKS * BK || topk <= 0 || topk > KTOP ||
+      topk > T || U >= (1ll << 31) || T >= (1ll << 31))
+    return GNGF_ERR_UNSUPPORTED;
+  CUtensorMap map_a, map_b;
+  int rc = make_plane_map(&map_a, a_planes, U, Kdim);
+  if (rc) return rc;
+  rc = make_plane_map(&map_b, b_planes, T, Kdim);
+  if (rc) return rc;
+  const int64_t row_tiles = gngf::ceil_div(U, BM), col_tiles = gngf::ceil_div(T, BN);
+  const int n_split =
+      static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(col_tiles, (2 * gngf::sm_count()) / row_tiles)));
+  float* part_max = workspace;
+  float* part_sum = part_max + U * n_split;
+  float* part_topv = part_sum + U * n_split;
+  int* part_topi = reinterpret_cast<int*>(part_topv + U * n_split * topk);
+  cudaStream_t st = gngf::as_stream(stream);
+  if (cudaFuncSetAttribute(hpd_stream_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(STREAM_SMEM_BYTES)) != cudaSuccess)
+    return gngf::check_launch();
+  const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
+  hpd_stream_fwd_kernel<<<grid, THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
+                                                                  static_cast<int>(T), static_cast<int>(Kdim), topk,
+                                                                  n_split, part_max, part_sum, part_topv, part_topi);
+  gngf::note_launch();
+  rc = gngf::check_launch();
+  if (rc) return rc;
+  hpd_stream_merge_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 128)), 128, 0, st>>>(
+      part_max, part_sum, part_topv, part_topi, static_cast<int>(U), n_split, topk, row_max, row_sum, utopv, utopi);
   gngf::note_launch();
   return gngf::check_launch();
 }

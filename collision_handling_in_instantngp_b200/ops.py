@@ -110,6 +110,23 @@ def tc_linear_fwd(x, w, b, act, x_planes=None, w_planes=None) -> torch.Tensor:
     return y
 
 
+def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
+    """Fused K2+K3: (utopv, utopi int32, row_max, row_sum) of softmax(h w^T + b) without the (U,T) logits."""
+    U, Kd = h.shape
+    T = w.shape[0]
+    hp = split_bf16x3(h) if h_planes is None else h_planes
+    wp = split_bf16x3(w) if w_planes is None else w_planes
+    dev = h.device
+    utopv = torch.empty((U, k), dtype=torch.float32, device=dev)
+    utopi = torch.empty((U, k), dtype=torch.int32, device=dev)
+    row_max = torch.empty(U, dtype=torch.float32, device=dev)
+    row_sum = torch.empty(U, dtype=torch.float32, device=dev)
+    work = torch.empty(_lib.load().gngf_hpd_stream_workspace_floats(U, T, k), dtype=torch.float32, device=dev)
+    call("gngf_hpd_stream_fwd", hp.data_ptr(), wp.data_ptr(), b.data_ptr(), U, T, Kd, k, utopv.data_ptr(),
+         utopi.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), work.data_ptr(), _stream())
+    return utopv, utopi, row_max, row_sum
+
+
 def softmax_topk_fwd(logits: torch.Tensor, k: int, inplace: bool = False, want_probs: bool = True):
     """probs = nan_to_num(softmax(logits)), (topv, topi) = topk(probs, k) with ties -> lower index."""
     _require_cuda(logits, "logits")

@@ -112,6 +112,16 @@ int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* strea
 int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
                         int64_t K, int32_t act, float* C, void* stream);
 
+/* K2+K3 fused, streaming: top-k probabilities/indices and softmax statistics of
+ *   softmax(h (U,Kdim) W (T,Kdim)^T + bias) per row, without materialising the (U,T) logits (Kdim <= 128,
+ *   topk <= 8).  Ties -> lower index; selection on the logits.  utopv (U,topk) = exp(z - max)/sum of the
+ *   winners; row_max/row_sum (U) are what a recomputing backward needs.  workspace:
+ *   gngf_hpd_stream_workspace_floats(U, T, topk) floats.                                                     */
+int64_t gngf_hpd_stream_workspace_floats(int64_t U, int64_t T, int32_t topk);
+int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t U, int64_t T,
+                        int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max, float* row_sum,
+                        float* workspace, void* stream);
+
 /* ---- K6: fused decoder MLP (models.py:382-392, 468-470) for the reference's shape IN -> 64 -> 64 -> OUT -----
  * rgb (P,OUT) = sigmoid(W2 act(W1 act(W0 enc + b0) + b1) + b2), act = ReLU or LeakyReLU(0.01); activations stay
  * in shared memory.  The backward recomputes them, writes denc (P,IN) and ADDS the parameter gradients into

@@ -240,3 +240,29 @@ def test_split_bf16x3_reconstructs_fp32():
     rec = planes.double().sum(0).cpu().numpy()
     assert np.abs(rec - x).max() <= np.abs(x).max() * 2.0 ** -22
     assert np.all(np.abs(rec - x) <= np.abs(x) * 2.0 ** -21)
+
+
+@pytest.mark.parametrize("U,T,Kd,K", [(300, 1000, 128, 4), (782, 256, 128, 4), (130, 4096, 64, 1), (1000, 2 ** 14, 128, 8),
+                                       (64, 2 ** 17, 128, 4), (5000, 8192, 128, 4)])
+def test_streaming_hpd_matches_unfused(U, T, Kd, K):
+    """Fused tcgen05 output layer + online softmax + running top-k == GEMM -> softmax/top-k kernel."""
+    rng = np.random.default_rng(U + T)
+    h = np.maximum(rng.standard_normal((U, Kd)), 0).astype(np.float32)
+    w = (rng.standard_normal((T, Kd)) * (3.0 / np.sqrt(Kd))).astype(np.float32)
+    b = rng.standard_normal(T).astype(np.float32)
+    ht, wt, bt = (torch.from_numpy(a).to(DEV) for a in (h, w, b))
+    utopv, utopi, rmax, rsum = ops.hpd_stream_fwd(ht, wt, bt, K)
+    logits = h.astype(np.float64) @ w.astype(np.float64).T + b
+    p_ref = O.softmax_lastdim(logits)
+    v_ref, i_ref = O.topk_sorted(p_ref, K)
+    srt = -np.sort(-p_ref, axis=-1)
+    gap = (srt[:, :K] - srt[:, 1:K + 1]).min(-1) / srt[:, 0]
+    ok = gap > 2e-5                                                  # rows whose selection is not a rounding-level tie
+    assert ok.mean() > 0.9
+    assert np.array_equal(utopi.cpu().numpy()[ok], i_ref[ok])
+    assert rel_err(utopv.cpu().numpy()[ok], v_ref[ok]) < 1e-5
+    assert rel_err(rmax.cpu().numpy(), logits.max(-1)) < 1e-5
+    assert rel_err(rsum.cpu().numpy(), np.exp(logits - logits.max(-1, keepdims=True)).sum(-1)) < 1e-5
+    # every selected index is a true top-k member up to the tie tolerance, on all rows
+    sel = np.take_along_axis(p_ref, utopi.cpu().numpy().astype(np.int64), -1)
+    assert (sel >= srt[:, K - 1:K] * (1 - 2e-5)).all()
