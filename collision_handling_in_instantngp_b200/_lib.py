@@ -88,7 +88,7 @@ SIGNATURES = {
     "gngf_encode_bwd": (c_int, [_P, c_int64, Lattice, c_int32, _P, _P, _P]),
     "gngf_node_features_bwd": (c_int, [Lattice, Tables, Tables, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "gngf_encode_hash_bwd": (c_int, [_P, c_int64, Lattice, Tables, c_int64, c_int32, _P, _P]),
-    "gngf_hpd_dlogits": (c_int, [Lattice, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gngf_hpd_dlogits": (c_int, [Lattice, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P]),
 }
 
 _lib = None

@@ -140,20 +140,23 @@ __global__ void __launch_bounds__(256) topk_scatter_kernel(const float* __restri
   if (t >= 0 && t < T) gin[r * T + t] = gv[i];
 }
 
-// K5b.  One warp per lattice node u:
+// K5b.  One warp per lattice node u (rows [u0, u0 + n_rows) of the node array; `in`/`out` are chunk-local):
 //   G[t]      = sum_l c_l * gcol[l,t] + gdense[u,t] + sum_k g_k [t == utopi[u,k]],   c_l = cnt[s(l,u)],
 //   g_k       = dtv[u,k] + sum_l c_l * gcol_k[l,k]
 //   dlogit[t] = p[t] * (G[t] - <G,p>)
+// `in` holds the probabilities, or -- when row_max/row_sum are given -- the logits, and p = exp(z - max)/sum is
+// recomputed on the fly (streaming path: the forward kept only the softmax statistics).  out may alias in.
 __global__ void __launch_bounds__(TOPK_WARPS * 32)
-    hpd_dlogits_kernel(const __grid_constant__ gngf_lattice lat, const float* __restrict__ uprobs, int64_t T, int K,
+    hpd_dlogits_kernel(const __grid_constant__ gngf_lattice lat, const float* in, int64_t T, int K,
                        const int32_t* __restrict__ utopi, const float* __restrict__ dtv,
                        const int32_t* __restrict__ cnt, const float* __restrict__ gcol,
                        const float* __restrict__ gcol_k, const float* __restrict__ gdense,
-                       float* __restrict__ dlogits) {
+                       const float* __restrict__ row_max, const float* __restrict__ row_sum, int64_t u0,
+                       int64_t n_rows, float* out_base) {
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
-  const int64_t u = static_cast<int64_t>(blockIdx.x) * TOPK_WARPS + warp;
-  if (u >= U) return;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * TOPK_WARPS + warp;
+  if (r >= n_rows) return;
+  const int64_t u = u0 + r;
   const int L = lat.num_levels;
   const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
   // cl[l] = multiplicity of this node on level l (0 when the node is outside that level's box)
@@ -169,16 +172,39 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
     cl[lane] = c;
   }
   __syncwarp();
-  const float* p = uprobs + u * T;
-  float* out = dlogits + u * T;
+  const float* p = in + r * T;
+  float* out = out_base + r * T;
+  const bool from_logits = row_max != nullptr;
+  const float mx = from_logits ? row_max[u] : 0.0f;
+  const float inv = from_logits ? 1.0f / row_sum[u] : 1.0f;
+  auto prob = [&](int64_t t) -> float {
+    float v = p[t];
+    if (from_logits) {
+      v = expf(v - mx) * inv;
+      if (v != v) v = 0.0f;
+    }
+    return v;
+  };
 
-  // <G,p>: sparse (top-k) part, lanes stride K ...
+  // sparse (top-k) part: lanes stride K; keep (t_k, g_k * p_k) so that `out` may alias `in`
   float dot = 0.0f;
-  for (int k = lane; k < K; k += 32) {
-    float g = dtv[u * K + k];
-    if (gcol_k)
-      for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
-    dot = fmaf(g, p[utopi[u * K + k]], dot);
+  float sp_add[(GNGF_MAX_TOPK + 31) / 32];
+  int sp_t[(GNGF_MAX_TOPK + 31) / 32];
+#pragma unroll
+  for (int it = 0; it < (GNGF_MAX_TOPK + 31) / 32; ++it) {
+    const int k = lane + 32 * it;
+    sp_add[it] = 0.0f;
+    sp_t[it] = -1;
+    if (k < K) {
+      float g = dtv[u * K + k];
+      if (gcol_k)
+        for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
+      const int t = utopi[u * K + k];
+      const float pk = prob(t);
+      sp_t[it] = t;
+      sp_add[it] = pk * g;
+      dot += pk * g;
+    }
   }
   // ... plus the dense column-sum part
   const float* gd = gdense ? gdense + u * T : nullptr;
@@ -187,7 +213,7 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
       float g = gd ? gd[t] : 0.0f;
       if (gcol)
         for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
-      dot = fmaf(g, p[t], dot);
+      dot = fmaf(g, prob(t), dot);
     }
   }
   dot = warp_sum(dot);
@@ -195,16 +221,12 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
     float g = gd ? gd[t] : 0.0f;
     if (gcol)
       for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
-    out[t] = p[t] * (g - dot);
+    out[t] = prob(t) * (g - dot);
   }
   __syncwarp();
-  for (int k = lane; k < K; k += 32) {
-    float g = dtv[u * K + k];
-    if (gcol_k)
-      for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
-    const int t = utopi[u * K + k];
-    out[t] = fmaf(p[t], g, out[t]);
-  }
+#pragma unroll
+  for (int it = 0; it < (GNGF_MAX_TOPK + 31) / 32; ++it)
+    if (sp_t[it] >= 0) out[sp_t[it]] += sp_add[it];
 }
 
 }  // namespace gngf
@@ -251,13 +273,17 @@ int gngf_topk_bwd(const float* grad_values, const int64_t* topi, int64_t R, int6
 
 int gngf_hpd_dlogits(gngf_lattice lat, const float* uprobs, int64_t T, int32_t K, const int32_t* utopi,
                      const float* dtv, const int32_t* cnt, const float* gcol, const float* gcol_k,
-                     const float* gdense, float* dlogits, void* stream) {
+                     const float* gdense, const float* row_max, const float* row_sum, int64_t u0, int64_t n_rows,
+                     float* dlogits, void* stream) {
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
-  if (U <= 0 || T <= 0 || K <= 0 || K > T) return GNGF_ERR_INVALID_ARGUMENT;
+  if (U <= 0 || T <= 0 || K <= 0 || K > T || K > GNGF_MAX_TOPK || u0 < 0 || n_rows < 0 || u0 + n_rows > U)
+    return GNGF_ERR_INVALID_ARGUMENT;
   if ((gcol || gcol_k) && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
-  gngf::hpd_dlogits_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::TOPK_WARPS)), gngf::TOPK_WARPS * 32, 0,
+  if ((row_max == nullptr) != (row_sum == nullptr)) return GNGF_ERR_INVALID_ARGUMENT;
+  if (n_rows == 0) return GNGF_OK;
+  gngf::hpd_dlogits_kernel<<<static_cast<unsigned>(gngf::ceil_div(n_rows, gngf::TOPK_WARPS)), gngf::TOPK_WARPS * 32, 0,
                              gngf::as_stream(stream)>>>(lat, uprobs, T, K, utopi, dtv, cnt, gcol, gcol_k, gdense,
-                                                        dlogits);
+                                                        row_max, row_sum, u0, n_rows, dlogits);
   gngf::note_launch();
   return gngf::check_launch();
 }

@@ -198,7 +198,10 @@ class ForwardState:
     lat: Lattice
     cfg: PathConfig
     hpd_acts: List[torch.Tensor] = field(default_factory=list)   # outputs of HPD layers 0..n-2, (U, width)
-    uprobs: Optional[torch.Tensor] = None                        # (U,T)
+    uprobs: Optional[torch.Tensor] = None                        # (U,T); None on the streaming path
+    row_max: Optional[torch.Tensor] = None                       # (U,) softmax statistics (streaming path)
+    row_sum: Optional[torch.Tensor] = None
+    w_planes: Optional[torch.Tensor] = None                      # (3,T,Kd) bf16 planes of the output layer
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
     cnt: Optional[torch.Tensor] = None                           # (S,) int32
@@ -215,14 +218,27 @@ def _mlp3_supported(mlp_w) -> bool:
                                                 mlp_w[2].shape[0])) and mlp_w[1].shape[1] == mlp_w[0].shape[0]
 
 
-def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device):
-    """HashProbDistribution.forward (models.py:90-123) on every lattice node: returns hidden activations,
-    uprobs (U,T), utopv (U,K), utopi (U,K) int32."""
+# streaming (never-materialised) HPD output layer: used in top-k-only mode once U*T is large; tests can force it
+STREAM_MIN_ELEMENTS = 1 << 26
+FORCE_STREAMING = None            # None: by size; True / False: override
+TC_MIN_ELEMENTS = 1 << 22         # dense logits come from the tensor-core GEMM above this size
+BWD_CHUNK_BYTES = 4 << 30         # logits recomputed per chunk of rows in the streaming backward
+
+
+def _streaming_ok(cfg, U, T, k, kd) -> bool:
+    if not cfg.topk_only or k > 8 or kd > 128 or kd % 8 != 0:
+        return False
+    if FORCE_STREAMING is not None:
+        return bool(FORCE_STREAMING)
+    return U * T >= STREAM_MIN_ELEMENTS
+
+
+def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
+    """HashProbDistribution.forward (models.py:90-123) on every lattice node.  Fills state.hpd_acts and
+    state.utopv / utopi (U,K); state.uprobs (U,T) on the dense path, state.row_max / row_sum (U) on the
+    streaming path (tcgen05 GEMM fused with online softmax + running top-k, logits never written)."""
     U = lat.num_nodes
     T = hpd_w[-1].shape[0]
-    if U * T * 4 > MAX_DENSE_LOGIT_BYTES:
-        raise GngfError(f"dense logits for U={U} nodes x T={T} slots need {U * T * 4 / 2**30:.0f} GiB; "
-                        "use the streaming HPD path")
     n = len(hpd_w)
     if hpd_w[0].shape[1] != 2:
         raise GngfError("the HPD input must be 2-D grid-corner coordinates")
@@ -230,11 +246,29 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device):
     h = torch.empty((U, hpd_w[0].shape[0]), dtype=torch.float32, device=device)
     call("gngf_hpd_first_layer_fwd", lat, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(), hpd_w[0].shape[0],
          ACT_RELU if n > 1 else ACT_NONE, h.data_ptr(), _stream())
-    for i in range(1, n):
+    for i in range(1, n - 1):
         acts.append(h)
-        h = linear_fwd(h, hpd_w[i], hpd_b[i], ACT_RELU if i < n - 1 else ACT_NONE)
-    uprobs, utopv, utopi = softmax_topk_fwd(h, k, inplace=True)
-    return acts, uprobs, utopv, utopi
+        h = linear_fwd(h, hpd_w[i], hpd_b[i], ACT_RELU)
+    state.hpd_acts = acts
+    if n == 1:                      # single-layer HPD: h already holds the logits
+        state.uprobs, state.utopv, state.utopi = softmax_topk_fwd(h, k, inplace=True)
+        return
+    acts.append(h)
+    kd = h.shape[1]
+    if _streaming_ok(cfg, U, T, k, kd):
+        state.w_planes = split_bf16x3(hpd_w[-1])
+        state.utopv, state.utopi, state.row_max, state.row_sum = hpd_stream_fwd(
+            h, hpd_w[-1], hpd_b[-1], k, w_planes=state.w_planes)
+        state.uprobs = None
+        return
+    if U * T * 4 > MAX_DENSE_LOGIT_BYTES:
+        raise GngfError(f"dense logits for U={U} nodes x T={T} slots need {U * T * 4 / 2**30:.0f} GiB; the streaming "
+                        "path needs should_keep_topk_only=True, topk_k <= 8 and a last hidden width <= 128")
+    if U * T >= TC_MIN_ELEMENTS and kd % 8 == 0:
+        logits = tc_linear_fwd(h, hpd_w[-1], hpd_b[-1], ACT_NONE)
+    else:
+        logits = linear_fwd(h, hpd_w[-1], hpd_b[-1], ACT_NONE)
+    state.uprobs, state.utopv, state.utopi = softmax_topk_fwd(logits, k, inplace=True)
 
 
 class GNGFPath(torch.autograd.Function):
@@ -265,7 +299,7 @@ class GNGFPath(torch.autograd.Function):
             call("gngf_encode_hash_fwd", x.data_ptr(), P, lat, tab, T, F, enc.data_ptr(), None, st)
             colsum = uvals = None
         else:
-            state.hpd_acts, state.uprobs, state.utopv, state.utopi = hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev)
+            hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev, cfg, state)
             S = lat.num_level_nodes
             nfeat = torch.empty((S, F), dtype=torch.float32, device=dev)
             call("gngf_node_features_fwd", lat, tab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
@@ -387,11 +421,35 @@ class GNGFPath(torch.autograd.Function):
                 dtv.add_(grad_uvals.reshape(-1))
             else:
                 gdense = grad_uvals
-        dlogits = torch.empty((U, T), dtype=torch.float32, device=dev)
-        call("gngf_hpd_dlogits", lat, state.uprobs.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
-             state.cnt.data_ptr(), _ptr(gcol), _ptr(gcol_k), _ptr(gdense), dlogits.data_ptr(), st)
-        dz = dlogits
-        for i in range(nh - 1, 0, -1):
+        if nh == 1:
+            dlogits = torch.empty((U, T), dtype=torch.float32, device=dev)
+            call("gngf_hpd_dlogits", lat, state.uprobs.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
+                 state.cnt.data_ptr(), _ptr(gcol), _ptr(gcol_k), _ptr(gdense), None, None, 0, U, dlogits.data_ptr(), st)
+            dz = dlogits
+        elif state.uprobs is not None:
+            dlogits = torch.empty((U, T), dtype=torch.float32, device=dev)
+            call("gngf_hpd_dlogits", lat, state.uprobs.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
+                 state.cnt.data_ptr(), _ptr(gcol), _ptr(gcol_k), _ptr(gdense), None, None, 0, U, dlogits.data_ptr(), st)
+            dz = linear_bwd(dlogits, state.hpd_acts[nh - 2], hpd_w[nh - 1], ACT_RELU, True, g_hpd_w[nh - 1],
+                            g_hpd_b[nh - 1])
+        else:
+            # streaming path: recompute the logits chunk by chunk on the tensor cores, turn them into dlogits in
+            # place from the saved softmax statistics, and feed the output layer's backward
+            h_last = state.hpd_acts[nh - 2]
+            kd = h_last.shape[1]
+            rows = int(max(128, min(U, BWD_CHUNK_BYTES // (T * 4))))
+            dz = torch.empty((U, kd), dtype=torch.float32, device=dev)
+            for r0 in range(0, U, rows):
+                n = min(rows, U - r0)
+                hc = h_last[r0:r0 + n]
+                buf = tc_linear_fwd(hc, hpd_w[nh - 1], params[2 * (nh - 1) + 1], ACT_NONE, w_planes=state.w_planes)
+                call("gngf_hpd_dlogits", lat, buf.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
+                     state.cnt.data_ptr(), None, _ptr(gcol_k), None, state.row_max.data_ptr(),
+                     state.row_sum.data_ptr(), r0, n, buf.data_ptr(), st)
+                dxc = linear_bwd(buf, hc, hpd_w[nh - 1], ACT_RELU, True, g_hpd_w[nh - 1], g_hpd_b[nh - 1])
+                dz[r0:r0 + n] = dxc
+                del buf
+        for i in range(nh - 2, 0, -1):
             dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
         call("gngf_hpd_first_layer_bwd", lat, dz.data_ptr(), hpd_w[0].shape[0], g_hpd_w[0].data_ptr(),
              g_hpd_b[0].data_ptr(), st)

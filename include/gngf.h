@@ -185,15 +185,17 @@ int gngf_node_features_bwd(gngf_lattice lat, gngf_tables tables, gngf_tables tab
                            float* dtv, void* stream);
 int gngf_encode_hash_bwd(const float* x, int64_t P, gngf_lattice lat, gngf_tables table_grads, int64_t T, int32_t F,
                          const float* denc, void* stream);
-/* K5b, per node: G = sum_l cnt[s(l,u)] * gcol[l,:] + gdense[u,:] + scatter(g_k at utopi[u,:]),
- *   g_k = dtv[u,k] + sum_l cnt[s(l,u)] * gcol_k[l,k];   dlogit[u,:] = p .* (G - <G,p>)
+/* K5b, per node u in [u0, u0 + n_rows): G = sum_l cnt[s(l,u)] * gcol[l,:] + gdense[u,:] + scatter(g_k at utopi[u,:]),
+ *   g_k = dtv[u,k] + sum_l cnt[s(l,u)] * gcol_k[l,k];   dlogit[r,:] = p .* (G - <G,p>)        (r = u - u0)
  * (softmax backward, models.py:85, with DifferentiableTopk.backward, models.py:21-42, and the adjoint of
  * the loss's column sums, utils.py:138, folded in).  gcol (L,T): adjoint of the full-probability column
- * sums; gcol_k (L,K): adjoint of the top-k column sums; gdense (U,T): dense adjoint of uprobs.  Each of
- * the three may be NULL.                                                                                */
+ * sums; gcol_k (L,K): adjoint of the top-k column sums; gdense (U,T): dense adjoint of uprobs; each may be
+ * NULL.  uprobs (n_rows,T) holds the probabilities of the chunk, or -- when row_max/row_sum (U) are given --
+ * the LOGITS of the chunk, and p = exp(z - max)/sum is recomputed.  dlogits (n_rows,T) may alias uprobs.   */
 int gngf_hpd_dlogits(gngf_lattice lat, const float* uprobs, int64_t T, int32_t K, const int32_t* utopi,
                      const float* dtv, const int32_t* cnt, const float* gcol, const float* gcol_k,
-                     const float* gdense, float* dlogits, void* stream);
+                     const float* gdense, const float* row_max, const float* row_sum, int64_t u0, int64_t n_rows,
+                     float* dlogits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -139,3 +139,24 @@ def test_out_of_bounds_coordinates_are_flagged():
     net.set_coord_bounds(None)
     net(x, 1.0)
     assert int(net.last_state.err_flag.item()) == 0
+
+
+@pytest.mark.parametrize("name", ["cfg2_topk_only", "l8_t4096_topk_only"])
+def test_streaming_tensor_core_path_matches_reference_golden(name):
+    """should_keep_topk_only=True through the tcgen05 streaming HPD (logits never materialised in the forward,
+    recomputed chunk-wise in the backward) against the reference's golden step."""
+    from collision_handling_in_instantngp_b200 import ops
+    g = load(name)
+    net = build_net(g)
+    ops.FORCE_STREAMING = True
+    try:
+        out = run_step(net, g)
+    finally:
+        ops.FORCE_STREAMING = None
+    st = out["state"]
+    assert st.uprobs is None and st.row_max is not None
+    assert np.array_equal(out["idx"], g["idx"])
+    assert rel_err(out["rgb"], g["rgb"]) < FWD_TOL
+    assert rel_err(out["pbar"], g["pbar"]) < FWD_TOL
+    assert abs(out["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    _check_grads(out, g)
