@@ -34,7 +34,24 @@ WORKLOADS = {
     # BASELINE.json configs[1]: strawberry.jpeg + param ID 4061 (README.md:15-18, params.py:26-51)
     "cfg2": dict(P=57404, L=4, n_min=8, n_max=32, T=256, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
                  lattice_hw=(508, 339), topk_only=False, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
-                 lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6)),
+                 lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
+                 cpu_sample=8192),
+    # BASELINE.json configs[2]: macaw.jpg (508x339 = 172 212 px < 2^18: the whole image is one batch), 16 levels,
+    # table size 2^19, top-k-only probabilities (the full distribution would be 134 MB per sample)
+    "cfg3": dict(P=172212, L=16, n_min=16, n_max=508, T=2 ** 19, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
+                 lattice_hw=(508, 339), topk_only=True, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
+                 lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
+                 cpu_sample=4),
+    # same image shape with a mid-size table (fits the dense path as well; used to compare the two HPD paths)
+    "cfg3_t14": dict(P=172212, L=16, n_min=16, n_max=508, T=2 ** 14, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
+                     lattice_hw=(508, 339), topk_only=True, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
+                     lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
+                     cpu_sample=64),
+    # BASELINE.json configs[3]: synthetic 8192 x 8192 lattice, 2^22 points per step, 16 levels x 2 features
+    "cfg4_t14": dict(P=2 ** 22, L=16, n_min=16, n_max=8192, T=2 ** 14, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
+                     lattice_hw=(8192, 8192), topk_only=True, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
+                     lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
+                     cpu_sample=64),
 }
 
 
@@ -203,6 +220,8 @@ def cost_key(name, args):
         return tuple(int(v) for v in args[3:6])
     if name == "gngf_linear_bwd":
         return tuple(int(v) for v in args[3:6]) + (args[7] is not None,)
+    if name == "gngf_tc_gemm_bf16x3":
+        return tuple(int(v) for v in args[3:6])
     return ()
 
 
@@ -220,6 +239,11 @@ def algorithmic_cost(name, key, w, lat):
     if name == "gngf_linear_bwd":
         M, N, Kd, has_dx = key
         return "tensor", 2.0 * M * N * Kd * (2 if has_dx else 1)
+    kd = w["hpd"][-1]
+    if name == "gngf_hpd_stream_fwd":
+        return "tensor", 2.0 * U * T * kd
+    if name == "gngf_tc_gemm_bf16x3":
+        return "tensor", 2.0 * float(key[0]) * key[1] * key[2]
     table = {
         # per point: x (8) + per level 4 node-feature gathers (4*F*4) + enc row (F*4) + 4 multiplicity atomics (4*4)
         "gngf_encode_fwd": P * (8 + L * (4 * F * 4 + F * 4 + 16)),
@@ -236,6 +260,7 @@ def algorithmic_cost(name, key, w, lat):
         "gngf_sigmoid_bwd": P * 3 * 4 * 3,
         "gngf_hpd_first_layer_fwd": U * w["hpd"][0] * 4,
         "gngf_hpd_first_layer_bwd": U * w["hpd"][0] * 4,
+        "gngf_split_bf16x3": 0.0,
     }
     return "hbm", float(table.get(name, 0))
 
@@ -305,7 +330,7 @@ def run_ours(args, w):
     launches_per_step = launch_count() - n0
 
     graph, launch_mode = None, "eager"
-    if world == 1 and not args.eager:
+    if world == 1 and not args.eager and w["T"] <= 4096:
         opt.zero_grad(set_to_none=True)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -402,7 +427,7 @@ def run_ours(args, w):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_P = args.cpu_sample
+        sample_P = args.cpu_sample or w["cpu_sample"]
         sec = time_cpu_port(w, sample_P, 65535, steps=3, warmup=1)
         cpu_base = {"value": sample_P / sec, "unit": "samples/s", "cores": cpu_threads(), "kind": "port",
                     "sample": f"{sample_P} of the workload's {w['P']} coordinates per step, 3 steps after 1 warm-up, "
@@ -440,7 +465,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=8192, help="points per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="points per CPU-baseline step (0: the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the timed step in a CUDA graph")
     args = ap.parse_args()
@@ -450,7 +475,7 @@ def main():
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return
-        sample_P = args.cpu_sample
+        sample_P = args.cpu_sample or w["cpu_sample"]
         sec = time_cpu_port(w, sample_P, 65535, steps=args.steps, warmup=args.warmup)
         val = sample_P / sec
         cores = cpu_threads()

@@ -38,9 +38,19 @@ def main():
     ref_shim.set_flag(ref, "epochs", args.epochs)
     ref_shim.set_flag(ref, "should_save_params", False)   # params.py:2 -- do not write weight files
     rec = {"psnr": [], "loss": [], "mse": [], "kl": [], "coll_loss": [], "collisions": [], "sec": []}
-    real_step, real_psnr = ref.functions.train_step, ref.functions.calc_psnr
+    init = {}
+    real_step, real_psnr, real_opt = ref.functions.train_step, ref.functions.calc_psnr, ref.functions.get_optimizer
+
+    def get_opt(net, *a, **k):          # called right after the model is constructed (functions.py:568)
+        for key, v in net.state_dict().items():
+            if not key.startswith("_batch_norm"):
+                init["init." + key] = v.detach().cpu().numpy().copy()
+        return real_opt(net, *a, **k)
 
     def step(*a, **k):
+        if "shuffled_indices" not in init:
+            init["shuffled_indices"] = k["shuffled_indices"].cpu().numpy().copy()
+            init["reordered_indices"] = k["reordered_indices"].cpu().numpy().copy()
         t0 = time.time()
         r = real_step(*a, **k)
         rec["sec"].append(time.time() - t0)
@@ -56,6 +66,7 @@ def main():
 
     ref.functions.train_step = step
     ref.functions.calc_psnr = psnr
+    ref.functions.get_optimizer = get_opt
     # wandb is disabled; wandb.Image() would still try to convert the stub matplotlib figures (functions.py:752)
     ref.functions.wandb.Image = lambda *a, **k: None
     # main.py star-imports from these module objects, which are already in sys.modules
@@ -66,7 +77,7 @@ def main():
     sys.argv = ["main.py", "-f", "strawberry.jpeg", "-s", str(args.param_id), "-e", str(args.param_id)]
     runpy.run_path(os.path.join(ref_shim.REFERENCE_DIR, "main.py"), run_name="__main__")
     np.savez_compressed(out_path, param_id=args.param_id, threads=args.threads,
-                        **{k: np.asarray(v) for k, v in rec.items()})
+                        **{k: np.asarray(v) for k, v in rec.items()}, **init)
     print("wrote", out_path)
 
 
