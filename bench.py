@@ -270,7 +270,7 @@ def run_ours(args, w):
     import torch.distributed as dist
 
     from collision_handling_in_instantngp_b200 import _lib, dp, launch_count
-    from collision_handling_in_instantngp_b200.loss import total_loss
+    from collision_handling_in_instantngp_b200.loss import fused_total_loss as total_loss
     from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
 
     rank = int(os.environ.get("RANK", "0"))

@@ -67,7 +67,8 @@ SIGNATURES = {
     "gngf_sigmoid_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "gngf_hpd_first_layer_bwd": (c_int, [Lattice, _P, c_int32, _P, _P, _P]),
     "gngf_split_bf16x3": (c_int, [_P, c_int64, _P, _P]),
-    "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P]),
+    "gngf_split_bf16x3_t": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "gngf_hpd_stream_workspace_floats": (c_int64, [c_int64, c_int64, c_int32]),
     "gngf_hpd_stream_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "gngf_mlp3_supported": (c_int, [c_int32, c_int32, c_int32, c_int32]),
@@ -75,6 +76,8 @@ SIGNATURES = {
     "gngf_mlp3_bwd_workspace_floats": (c_int64, [c_int32, c_int32]),
     "gngf_mlp3_bwd": (c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
+                                  _P, _P, _P, _P, _P]),
     "gngf_softmax_topk_fwd": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "gngf_topk_fwd": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "gngf_topk_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int32, _P, _P]),

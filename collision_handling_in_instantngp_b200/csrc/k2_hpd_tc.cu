@@ -118,7 +118,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // C (M,N) = act(sum over plane pairs of A_i (M,K) B_j (N,K)^T + bias)
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K, int act) {
+                       const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K, int act,
+                       int accumulate, int k_splits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -153,16 +154,22 @@ __global__ void __launch_bounds__(THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // work item = (output tile, K split); with k_splits > 1 the partial tiles are summed with atomics into a
+  // zero-initialised C (used when M x N alone cannot fill the chip, e.g. dX = dlogits W3 with K = T)
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
-  const int tiles = num_m * num_n, kblocks = (K + BK - 1) / BK;
+  const int kblocks_all = (K + BK - 1) / BK;
+  const int kb_per = (kblocks_all + k_splits - 1) / k_splits;
+  const int tiles = num_m * num_n * k_splits;
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer ----
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int ks = t % k_splits, tt = t / k_splits;
+        const int m0 = (tt / num_n) * BM, n0 = (tt % num_n) * BN;
+        const int kb0 = ks * kb_per, kb1 = min(kblocks_all, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           mbar_expect_tx(full + stage, STAGE_BYTES);
           uint8_t* base = smem + stage * STAGE_BYTES;
@@ -186,10 +193,12 @@ __global__ void __launch_bounds__(THREADS, 1)
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int ks = t % k_splits;
+        const int kb0 = ks * kb_per, kb1 = min(kblocks_all, kb0 + kb_per);
         mbar_wait(tempty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t ad = umma_desc(a_base + pa[pr] * PLANE_BYTES + k * UMMA_K * 2);
               const uint64_t bd = umma_desc(b_base + pb[pr] * PLANE_BYTES + k * UMMA_K * 2);
-              umma_bf16(d, ad, bd, idesc, (kb | pr | k) != 0);
+              umma_bf16(d, ad, bd, idesc, ((kb - kb0) | pr | k) != 0);
             }
           }
           umma_commit(empty + stage);  // the stage may be refilled once these MMAs have read it
@@ -221,7 +230,9 @@ __global__ void __launch_bounds__(THREADS, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      const int ks = t % k_splits, tt = t / k_splits;
+      const int m0 = (tt / num_n) * BM, n0 = (tt % num_n) * BN;
+      const bool empty_split = ks * kb_per >= kblocks_all;
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -236,11 +247,18 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int j = 0; j < 32; ++j) stage_tile[lane * EPI_LD + j] = __uint_as_float(v[j]);
         __syncwarp();
         const int col = n0 + c0 + lane;
-        if (col < N) {
-          const float bcol = bias ? bias[col] : 0.0f;
+        if (col < N && !empty_split) {
+          const float bcol = (bias && ks == 0) ? bias[col] : 0.0f;
           const int r_end = min(32, M - (m0 + q * 32));
           float* out = C + static_cast<int64_t>(m0 + q * 32) * N + col;
-          for (int r = 0; r < r_end; ++r) out[static_cast<int64_t>(r) * N] = act_apply(stage_tile[r * EPI_LD + lane] + bcol, act);
+          if (k_splits > 1) {
+            for (int r = 0; r < r_end; ++r) atomicAdd(out + static_cast<int64_t>(r) * N, stage_tile[r * EPI_LD + lane] + bcol);
+          } else if (accumulate) {
+            for (int r = 0; r < r_end; ++r) out[static_cast<int64_t>(r) * N] += stage_tile[r * EPI_LD + lane] + bcol;
+          } else {
+            for (int r = 0; r < r_end; ++r)
+              out[static_cast<int64_t>(r) * N] = act_apply(stage_tile[r * EPI_LD + lane] + bcol, act);
+          }
         }
         __syncwarp();
       }
@@ -564,6 +582,36 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
   planes[2 * n + i] = lo;
 }
 
+// planes[pl][c][r] = split(src[r][c]) for src (rows, cols); the plane matrices are (cols, ld) with ld >= rows,
+// columns r >= rows are zero-filled (ld keeps the row pitch a multiple of 16 bytes for TMA)
+__global__ void __launch_bounds__(256) split_bf16x3_t_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
+                                                            int64_t ld, __nv_bfloat16* __restrict__ planes) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? src[r * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  const int64_t plane = cols * ld;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < cols && r < ld) {
+      const float x = tile[tx][ty + 8 * i];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      const float r1 = x - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      planes[c * ld + r] = hi;
+      planes[plane + c * ld + r] = mid;
+      planes[2 * plane + c * ld + r] = lo;
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -608,8 +656,18 @@ int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* strea
   return gngf::check_launch();
 }
 
+int gngf_split_bf16x3_t(const float* src, int64_t rows, int64_t cols, int64_t ld, uint16_t* planes, void* stream) {
+  if (rows <= 0 || cols <= 0 || ld < rows) return GNGF_ERR_INVALID_ARGUMENT;
+  dim3 grid(static_cast<unsigned>(gngf::ceil_div(cols, 32)), static_cast<unsigned>(gngf::ceil_div(ld, 32)));
+  if (grid.y > 65535) return GNGF_ERR_UNSUPPORTED;
+  gngf::tc::split_bf16x3_t_kernel<<<grid, 256, 0, gngf::as_stream(stream)>>>(src, rows, cols, ld,
+                                                                            reinterpret_cast<__nv_bfloat16*>(planes));
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
 int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
-                        int64_t K, int32_t act, float* C, void* stream) {
+                        int64_t K, int32_t act, int32_t accumulate, int32_t k_splits, float* C, void* stream) {
   using namespace gngf::tc;
   if (M <= 0 || N <= 0 || K <= 0 || (K % 8) != 0 || M >= (1ll << 31) || N >= (1ll << 31)) return GNGF_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b_planes)) & 15) return GNGF_ERR_INVALID_ARGUMENT;
@@ -621,10 +679,16 @@ int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, cons
   if (cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(SMEM_BYTES)) != cudaSuccess)
     return gngf::check_launch();
-  const int64_t tiles = gngf::ceil_div(M, BM) * gngf::ceil_div(N, BN);
+  const int64_t out_tiles = gngf::ceil_div(M, BM) * gngf::ceil_div(N, BN);
+  const int64_t kblocks = gngf::ceil_div(K, BK);
+  if (k_splits <= 0)  // auto: split K only when the output tiles cannot fill the chip (C must then be zeroed)
+    k_splits = 1;
+  k_splits = static_cast<int32_t>(std::min<int64_t>(k_splits, kblocks));
+  if (k_splits > 1 && (act != GNGF_ACT_NONE)) return GNGF_ERR_INVALID_ARGUMENT;
+  const int64_t tiles = out_tiles * k_splits;
   const int grid = static_cast<int>(std::min<int64_t>(tiles, gngf::sm_count()));
   gemm_bf16x3_kernel<<<grid, THREADS, SMEM_BYTES, gngf::as_stream(stream)>>>(
-      map_a, map_b, bias, C, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), act);
+      map_a, map_b, bias, C, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), act, accumulate, k_splits);
   gngf::note_launch();
   return gngf::check_launch();
 }

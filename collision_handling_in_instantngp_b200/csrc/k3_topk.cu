@@ -146,22 +146,26 @@ __global__ void __launch_bounds__(256) topk_scatter_kernel(const float* __restri
 //   dlogit[t] = p[t] * (G[t] - <G,p>)
 // `in` holds the probabilities, or -- when row_max/row_sum are given -- the logits, and p = exp(z - max)/sum is
 // recomputed on the fly (streaming path: the forward kept only the softmax statistics).  out may alias in.
-__global__ void __launch_bounds__(TOPK_WARPS * 32)
+// TPR threads cooperate on one row: a warp (4 rows per CTA) for short rows, a whole 256-thread CTA for long ones.
+template <int TPR>
+__global__ void __launch_bounds__(TPR == 32 ? TOPK_WARPS * 32 : TPR)
     hpd_dlogits_kernel(const __grid_constant__ gngf_lattice lat, const float* in, int64_t T, int K,
                        const int32_t* __restrict__ utopi, const float* __restrict__ dtv,
                        const int32_t* __restrict__ cnt, const float* __restrict__ gcol,
                        const float* __restrict__ gcol_k, const float* __restrict__ gdense,
                        const float* __restrict__ row_max, const float* __restrict__ row_sum, int64_t u0,
                        int64_t n_rows, float* out_base) {
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * TOPK_WARPS + warp;
+  constexpr int ROWS = TPR == 32 ? TOPK_WARPS : 1;
+  const int sub = threadIdx.x / TPR, lane = threadIdx.x % TPR;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * ROWS + sub;
   if (r >= n_rows) return;
   const int64_t u = u0 + r;
   const int L = lat.num_levels;
   const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
   // cl[l] = multiplicity of this node on level l (0 when the node is outside that level's box)
-  __shared__ float cl_s[TOPK_WARPS][GNGF_MAX_LEVELS];
-  float* cl = cl_s[warp];
+  __shared__ float cl_s[ROWS][GNGF_MAX_LEVELS];
+  __shared__ float red_s[TPR / 32];
+  float* cl = cl_s[sub];
   if (lane < L) {
     float c = 0.0f;
     if (cnt) {
@@ -171,14 +175,13 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
     }
     cl[lane] = c;
   }
-  __syncwarp();
+  if (TPR == 32) __syncwarp(); else __syncthreads();
   const float* p = in + r * T;
   float* out = out_base + r * T;
   const bool from_logits = row_max != nullptr;
   const float mx = from_logits ? row_max[u] : 0.0f;
   const float inv = from_logits ? 1.0f / row_sum[u] : 1.0f;
-  auto prob = [&](int64_t t) -> float {
-    float v = p[t];
+  auto prob_of = [&](float v) -> float {
     if (from_logits) {
       v = expf(v - mx) * inv;
       if (v != v) v = 0.0f;
@@ -186,13 +189,14 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
     return v;
   };
 
-  // sparse (top-k) part: lanes stride K; keep (t_k, g_k * p_k) so that `out` may alias `in`
+  // sparse (top-k) part: threads stride K; keep (t_k, g_k * p_k) so that `out` may alias `in`
+  constexpr int SP = (GNGF_MAX_TOPK + TPR - 1) / TPR;
   float dot = 0.0f;
-  float sp_add[(GNGF_MAX_TOPK + 31) / 32];
-  int sp_t[(GNGF_MAX_TOPK + 31) / 32];
+  float sp_add[SP];
+  int sp_t[SP];
 #pragma unroll
-  for (int it = 0; it < (GNGF_MAX_TOPK + 31) / 32; ++it) {
-    const int k = lane + 32 * it;
+  for (int it = 0; it < SP; ++it) {
+    const int k = lane + TPR * it;
     sp_add[it] = 0.0f;
     sp_t[it] = -1;
     if (k < K) {
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
       if (gcol_k)
         for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
       const int t = utopi[u * K + k];
-      const float pk = prob(t);
+      const float pk = prob_of(p[t]);
       sp_t[it] = t;
       sp_add[it] = pk * g;
       dot += pk * g;
@@ -209,23 +213,45 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32)
   // ... plus the dense column-sum part
   const float* gd = gdense ? gdense + u * T : nullptr;
   if (gcol || gd) {
-    for (int64_t t = lane; t < T; t += 32) {
+    for (int64_t t = lane; t < T; t += TPR) {
       float g = gd ? gd[t] : 0.0f;
       if (gcol)
         for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
-      dot = fmaf(g, prob(t), dot);
+      dot = fmaf(g, prob_of(p[t]), dot);
     }
   }
   dot = warp_sum(dot);
-  for (int64_t t = lane; t < T; t += 32) {
-    float g = gd ? gd[t] : 0.0f;
-    if (gcol)
-      for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
-    out[t] = prob(t) * (g - dot);
-  }
-  __syncwarp();
+  if (TPR > 32) {
+    if ((lane & 31) == 0) red_s[lane >> 5] = dot;
+    __syncthreads();  // also orders every read of p[t_k] above before the writes below when out aliases in
+    dot = 0.0f;
 #pragma unroll
-  for (int it = 0; it < (GNGF_MAX_TOPK + 31) / 32; ++it)
+    for (int w = 0; w < TPR / 32; ++w) dot += red_s[w];
+  }
+  if (!gcol && !gd && (T & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    // streaming / top-k-only case: dlogit = -<G,p> * p, vectorised
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (int64_t t = lane; t < T / 4; t += TPR) {
+      const float4 v = p4[t];
+      float4 o;
+      o.x = -dot * prob_of(v.x);
+      o.y = -dot * prob_of(v.y);
+      o.z = -dot * prob_of(v.z);
+      o.w = -dot * prob_of(v.w);
+      o4[t] = o;
+    }
+  } else {
+    for (int64_t t = lane; t < T; t += TPR) {
+      float g = gd ? gd[t] : 0.0f;
+      if (gcol)
+        for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
+      out[t] = prob_of(p[t]) * (g - dot);
+    }
+  }
+  if (TPR == 32) __syncwarp(); else __syncthreads();
+#pragma unroll
+  for (int it = 0; it < SP; ++it)
     if (sp_t[it] >= 0) out[sp_t[it]] += sp_add[it];
 }
 
@@ -281,9 +307,15 @@ int gngf_hpd_dlogits(gngf_lattice lat, const float* uprobs, int64_t T, int32_t K
   if ((gcol || gcol_k) && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
   if ((row_max == nullptr) != (row_sum == nullptr)) return GNGF_ERR_INVALID_ARGUMENT;
   if (n_rows == 0) return GNGF_OK;
-  gngf::hpd_dlogits_kernel<<<static_cast<unsigned>(gngf::ceil_div(n_rows, gngf::TOPK_WARPS)), gngf::TOPK_WARPS * 32, 0,
-                             gngf::as_stream(stream)>>>(lat, uprobs, T, K, utopi, dtv, cnt, gcol, gcol_k, gdense,
-                                                        row_max, row_sum, u0, n_rows, dlogits);
+  if (T >= 2048) {
+    if (n_rows >= (1ll << 31)) return GNGF_ERR_UNSUPPORTED;
+    gngf::hpd_dlogits_kernel<256><<<static_cast<unsigned>(n_rows), 256, 0, gngf::as_stream(stream)>>>(
+        lat, uprobs, T, K, utopi, dtv, cnt, gcol, gcol_k, gdense, row_max, row_sum, u0, n_rows, dlogits);
+  } else {
+    gngf::hpd_dlogits_kernel<32><<<static_cast<unsigned>(gngf::ceil_div(n_rows, gngf::TOPK_WARPS)),
+                                   gngf::TOPK_WARPS * 32, 0, gngf::as_stream(stream)>>>(
+        lat, uprobs, T, K, utopi, dtv, cnt, gcol, gcol_k, gdense, row_max, row_sum, u0, n_rows, dlogits);
+  }
   gngf::note_launch();
   return gngf::check_launch();
 }

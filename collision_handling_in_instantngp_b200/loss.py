@@ -35,3 +35,34 @@ def total_loss(rgb, target, colsum, rows: int, gamma: float, epsilon: float, l_m
     levels = level_divergences(colsum / rows, gamma, epsilon)
     coll = torch.ones_like(levels) if collisions_term is None else collisions_term
     return l_mse * mse + (l_js_kl * levels + coll).sum(0), mse, levels
+
+
+class _FusedLoss(torch.autograd.Function):
+    """gngf_loss_fwd_bwd: forward value and both adjoints from one kernel."""
+
+    @staticmethod
+    def forward(ctx, rgb, target, colsum, rows, gamma, epsilon, l_mse, l_js_kl, coll_term):
+        from . import ops
+        rgb_c, tgt_c, cs_c = ops._f32c(rgb), ops._f32c(target), ops._f32c(colsum)
+        L, N = cs_c.shape
+        out = torch.empty(2 + L, dtype=torch.float32, device=rgb.device)
+        d_rgb = torch.empty_like(rgb_c)
+        d_colsum = torch.empty_like(cs_c)
+        ops.call("gngf_loss_fwd_bwd", rgb_c.data_ptr(), tgt_c.data_ptr(), rgb_c.numel(), cs_c.data_ptr(), L, N,
+                 float(rows), float(gamma), float(epsilon), float(l_mse), float(l_js_kl),
+                 None if coll_term is None else ops._f32c(coll_term).data_ptr(), out.data_ptr(), d_rgb.data_ptr(),
+                 d_colsum.data_ptr(), ops._stream())
+        ctx.save_for_backward(d_rgb, d_colsum)
+        total, mse, levels = out[0], out[1], out[2:]
+        ctx.mark_non_differentiable(mse, levels)
+        return total, mse, levels
+
+    @staticmethod
+    def backward(ctx, g_total, g_mse, g_levels):
+        d_rgb, d_colsum = ctx.saved_tensors
+        return d_rgb * g_total, None, d_colsum * g_total, None, None, None, None, None, None
+
+
+def fused_total_loss(rgb, target, colsum, rows, gamma, epsilon, l_mse=1.0, l_js_kl=1.0, collisions_term=None):
+    """Same value and gradients as :func:`total_loss`, from the single CUDA kernel of k7_loss.cu."""
+    return _FusedLoss.apply(rgb, target, colsum, rows, gamma, epsilon, l_mse, l_js_kl, collisions_term)

@@ -106,8 +106,27 @@ def tc_linear_fwd(x, w, b, act, x_planes=None, w_planes=None) -> torch.Tensor:
     xp = split_bf16x3(x) if x_planes is None else x_planes
     wp = split_bf16x3(w) if w_planes is None else w_planes
     y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    call("gngf_tc_gemm_bf16x3", xp.data_ptr(), wp.data_ptr(), _ptr(b), M, N, K, act, y.data_ptr(), _stream())
+    call("gngf_tc_gemm_bf16x3", xp.data_ptr(), wp.data_ptr(), _ptr(b), M, N, K, act, 0, 1, y.data_ptr(), _stream())
     return y
+
+
+def split_bf16x3_t(t: torch.Tensor) -> torch.Tensor:
+    """bf16 planes of t^T: (3, cols, ld) with ld = rows rounded up to 8 (16-byte row pitch), zero padded."""
+    t = _f32c(t)
+    rows, cols = t.shape
+    ld = (rows + 7) & ~7
+    planes = torch.empty((3, cols, ld), dtype=torch.bfloat16, device=t.device)
+    call("gngf_split_bf16x3_t", t.data_ptr(), rows, cols, ld, planes.data_ptr(), _stream())
+    return planes
+
+
+def tc_gemm_planes(a_planes, b_planes, out, accumulate=False, k_splits=1) -> None:
+    """out (M,N) (+)= A B^T for bf16x3 planes a (3,M,K), b (3,N,K) on the tensor cores.  k_splits > 1 sums K
+    ranges with atomics: `out` must then be zero-initialised."""
+    M, K = a_planes.shape[1], a_planes.shape[2]
+    N = b_planes.shape[1]
+    call("gngf_tc_gemm_bf16x3", a_planes.data_ptr(), b_planes.data_ptr(), None, M, N, K, ACT_NONE, int(accumulate),
+         int(k_splits), out.data_ptr(), _stream())
 
 
 def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
@@ -437,8 +456,10 @@ class GNGFPath(torch.autograd.Function):
             # place from the saved softmax statistics, and feed the output layer's backward
             h_last = state.hpd_acts[nh - 2]
             kd = h_last.shape[1]
-            rows = int(max(128, min(U, BWD_CHUNK_BYTES // (T * 4))))
-            dz = torch.empty((U, kd), dtype=torch.float32, device=dev)
+            rows = int(max(128, min(U, BWD_CHUNK_BYTES // (T * 4)))) // 8 * 8
+            dz = torch.zeros((U, kd), dtype=torch.float32, device=dev)
+            wt_planes = split_bf16x3(hpd_w[nh - 1].t().contiguous())          # (3, kd, T): B operand of dX
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
             for r0 in range(0, U, rows):
                 n = min(rows, U - r0)
                 hc = h_last[r0:r0 + n]
@@ -446,9 +467,19 @@ class GNGFPath(torch.autograd.Function):
                 call("gngf_hpd_dlogits", lat, buf.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
                      state.cnt.data_ptr(), None, _ptr(gcol_k), None, state.row_max.data_ptr(),
                      state.row_sum.data_ptr(), r0, n, buf.data_ptr(), st)
-                dxc = linear_bwd(buf, hc, hpd_w[nh - 1], ACT_RELU, True, g_hpd_w[nh - 1], g_hpd_b[nh - 1])
-                dz[r0:r0 + n] = dxc
-                del buf
+                # db += colsum(dlogits); dX = dlogits W3 (masked); dW3 += dlogits^T h  -- all on tcgen05
+                call("gngf_linear_bwd", buf.data_ptr(), hc.data_ptr(), hpd_w[nh - 1].data_ptr(), n, T, kd, ACT_NONE,
+                     None, None, g_hpd_b[nh - 1].data_ptr(), st)
+                dl_planes = split_bf16x3(buf)                                   # (3, n, T)
+                dxc = dz[r0:r0 + n]
+                out_tiles = ((n + 127) // 128) * ((kd + 127) // 128)
+                tc_gemm_planes(dl_planes, wt_planes, dxc, k_splits=max(1, (2 * sms) // out_tiles))
+                dxc.mul_(hc > 0)
+                del dl_planes
+                dlt_planes = split_bf16x3_t(buf)                                # (3, T, n8)
+                ht_planes = split_bf16x3_t(hc)                                  # (3, kd, n8)
+                tc_gemm_planes(dlt_planes, ht_planes, g_hpd_w[nh - 1], accumulate=True)
+                del buf, dlt_planes, ht_planes
         for i in range(nh - 2, 0, -1):
             dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
         call("gngf_hpd_first_layer_bwd", lat, dz.data_ptr(), hpd_w[0].shape[0], g_hpd_w[0].data_ptr(),

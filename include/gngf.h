@@ -109,8 +109,13 @@ int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, f
  *   a_planes (3,M,K), b_planes (3,N,K) bf16, 16-byte aligned, K % 8 == 0.  This is the HPD output layer
  *   (models.py:80-88: Linear(128, T)) when T is large.                                                       */
 int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* stream);
+/* transposing variant: planes (3, cols, ld) of src (rows, cols)^T, ld >= rows, columns >= rows zero-filled      */
+int gngf_split_bf16x3_t(const float* src, int64_t rows, int64_t cols, int64_t ld, uint16_t* planes, void* stream);
+/* accumulate != 0: C += product + bias (no activation) -- used for weight gradients summed over row chunks.
+ * k_splits > 1: the K range is split over CTAs and summed with atomics into a ZERO-INITIALISED C (for products
+ * whose M x N alone cannot fill the chip, e.g. dX = dlogits W3 with K = T).                                    */
 int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
-                        int64_t K, int32_t act, float* C, void* stream);
+                        int64_t K, int32_t act, int32_t accumulate, int32_t k_splits, float* C, void* stream);
 
 /* K2+K3 fused, streaming: top-k probabilities/indices and softmax statistics of
  *   softmax(h (U,Kdim) W (T,Kdim)^T + bias) per row, without materialising the (U,T) logits (Kdim <= 128,
@@ -136,6 +141,15 @@ int gngf_mlp3_bwd(const float* enc, const float* drgb, int64_t P, int32_t in_dim
                   const float* w0, const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
                   float* denc, float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, float* workspace,
                   void* stream);
+
+/* ---- loss assembly (utils.py:78-174 Loss + functions.py:243-245) with its adjoints, one kernel ---------------
+ * total = l_mse * MSE(rgb, target) + sum_l (l_js_kl * level_l + coll_l), level_l = -(gamma+epsilon) JS_l + epsilon KL_l
+ * of pbar_l = colsum_l / rows against the uniform distribution.  out (2+L): [0] total, [1] mse, [2+l] level_l;
+ * d_rgb (n_rgb) = d total / d rgb; d_colsum (L,N) = d total / d colsum.  coll_term (L) = l_collisions *
+ * collisions / (min_possible + delta) or NULL (epoch 0: the scalar 1 per level, functions.py:245).           */
+int gngf_loss_fwd_bwd(const float* rgb, const float* target, int64_t n_rgb, const float* colsum, int32_t L, int64_t N,
+                      float rows, float gamma, float epsilon, float l_mse, float l_js_kl, const float* coll_term,
+                      float* out, float* d_rgb, float* d_colsum, void* stream);
 
 /* ---- K3: softmax + nan_to_num + top-k (models.py:85,111 and DifferentiableTopk.forward 7-19) --------
  * logits (R,T) -> probs (R,T) (may alias logits, may be NULL), topv (R,K) sorted descending,

@@ -160,3 +160,31 @@ def test_streaming_tensor_core_path_matches_reference_golden(name):
     assert rel_err(out["pbar"], g["pbar"]) < FWD_TOL
     assert abs(out["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
     _check_grads(out, g)
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "cfg2_epoch1", "js_only", "kl_only", "l16_t1024"])
+def test_fused_loss_kernel_matches_reference_loss(name):
+    """k7_loss.cu (value + adjoints) against the reference's Loss / autograd recorded in the goldens."""
+    from collision_handling_in_instantngp_b200.loss import fused_total_loss, total_loss
+    g = load(name)
+    c = g["cfg"]
+    net = build_net(g)
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    coll = None
+    if "coll_losses" in g:
+        coll = c["l_collisions"] * torch.from_numpy(g["coll_losses"]).cuda()
+    net.zero_grad()
+    rgb, probs, _, _ = net(x, 1.0)
+    rows = probs.shape[0] * probs.shape[2]
+    total, mse, levels = fused_total_loss(rgb, y, probs.colsum, rows, c["gamma"], c["epsilon"], c["l_mse"], c["l_js_kl"],
+                                          coll)
+    assert abs(float(total) - g["loss"]) < 1e-5 * abs(g["loss"])
+    assert abs(float(mse) - g["mse"]) < 1e-5 * abs(g["mse"])
+    assert rel_err(levels.cpu().numpy(), g["kl_levels"]) < 1e-4
+    total.backward()
+    out = {"grads": {k: v.grad.detach().cpu().numpy() for k, v in net.named_parameters() if v.grad is not None}}
+    _check_grads(out, g)
+    # and against the torch restatement of the same formula
+    t2, _, _ = total_loss(rgb.detach(), y, probs.colsum.detach(), rows, c["gamma"], c["epsilon"], c["l_mse"],
+                          c["l_js_kl"], coll)
+    assert abs(float(t2) - float(total)) < 1e-5 * abs(float(t2))
