@@ -78,6 +78,9 @@ SIGNATURES = {
                               _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
+    "gngf_count_distinct_workspace_words": (c_int64, [c_int32, c_int32, c_int64]),
+    "gngf_count_distinct_f32": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, _P]),
+    "gngf_count_distinct_i64": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, _P]),
     "gngf_softmax_topk_fwd": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "gngf_topk_fwd": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "gngf_topk_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int32, _P, _P]),

@@ -361,21 +361,29 @@ class GeneralNeuralGaugeFields(nn.Module):
 
     @torch.no_grad()
     def calc_hash_collisions(self, indices: torch.Tensor):
-        """models.py:568-619: per level, (n_l+1)^2 minus the number of distinct slots in use."""
+        """models.py:568-619: per level, (n_l+1)^2 minus the number of distinct slots in use (mean over the top-k
+        columns, clamped at 0; raw integers in hash-function mode).  One bitmap pass on the GPU instead of one
+        torch.unique per (column, level); values that are not integers in [0, T) -- train_step's buffer is
+        torch.empty -- fall back to exact counting with torch.unique."""
+        ops._require_cuda(indices, "indices")
         dev = indices.device
-        nodes = [(int(n) + 1) ** 2 for n in self._n_ls_host]
-        if self._use_hash:
-            per_level = indices.permute(1, 0, 2).reshape(self._num_levels, -1)
-            collisions = torch.tensor([nodes[i] - torch.unique(per_level[i]).shape[0]
-                                       for i in range(self._num_levels)])
-        else:
+        L = self._num_levels
+        nodes = torch.tensor([(int(n) + 1) ** 2 for n in self._n_ls_host], device=dev)
+        idx4 = indices.unsqueeze(-1) if self._use_hash else indices
+        uniq, outliers = ops.count_distinct(idx4, self._hash_table_size)
+        if int(outliers.item()) != 0:
             cols = []
-            for k in range(indices.shape[-1]):
-                per_level = indices[..., k].permute(1, 0, 2).reshape(self._num_levels, -1)
-                cols.append([nodes[i] - torch.unique(per_level[i]).shape[0] for i in range(self._num_levels)])
-            collisions = torch.tensor(cols, dtype=torch.float32, device=dev).mean(dim=0)
+            for k in range(idx4.shape[-1]):
+                per_level = idx4[..., k].permute(1, 0, 2).reshape(L, -1)
+                cols.append([torch.unique(per_level[i]).shape[0] for i in range(L)])
+            uniq = torch.tensor(cols, device=dev)
+        if self._use_hash:
+            collisions = (nodes - uniq[0]).cpu()                                      # reference: a CPU int64 tensor
+        else:
+            collisions = (nodes.unsqueeze(0) - uniq).float().mean(dim=0)
             collisions[collisions < 0] = 0
-        minp = torch.tensor([max(n - self._hash_table_size, 0) for n in nodes], device=dev)
+        minp = nodes - self._hash_table_size
+        minp[minp < 0] = 0
         return collisions, minp
 
     def _bilinear_interpolate(self, scaled_coords, grid_coords, features):

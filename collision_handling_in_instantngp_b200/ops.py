@@ -180,6 +180,25 @@ def topk_bwd(grad_values: torch.Tensor, topi: torch.Tensor, T: int) -> torch.Ten
     return gin.reshape(*shape[:-1], T)
 
 
+def count_distinct(indices: torch.Tensor, value_range: int):
+    """Distinct integer values in [0, value_range) per (column, level) of an index tensor (P,L,V,C), float32 or
+    int64 -> (uniq (C,L) int32, outliers flag tensor).  The kernel behind calc_hash_collisions."""
+    _require_cuda(indices, "indices")
+    if indices.dtype not in (torch.float32, torch.int64):
+        indices = indices.float() if indices.is_floating_point() else indices.long()
+    indices = indices.contiguous()
+    P, L, V, C = indices.shape
+    dev = indices.device
+    words = _lib.load().gngf_count_distinct_workspace_words(L, C, int(value_range))
+    bitmap = torch.empty(words, dtype=torch.int32, device=dev)
+    uniq = torch.empty((C, L), dtype=torch.int32, device=dev)
+    outliers = torch.empty(1, dtype=torch.int32, device=dev)
+    name = "gngf_count_distinct_f32" if indices.dtype == torch.float32 else "gngf_count_distinct_i64"
+    call(name, indices.data_ptr(), P, L, V, C, int(value_range), bitmap.data_ptr(), uniq.data_ptr(),
+         outliers.data_ptr(), _stream())
+    return uniq, outliers
+
+
 def gather_rows(x, lat: Lattice, uvals: torch.Tensor) -> torch.Tensor:
     """(P,L,4,N) rows of a per-node array; int32 input gives the int64 API dtype."""
     P, N = x.shape[0], uvals.shape[1]

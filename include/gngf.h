@@ -211,6 +211,16 @@ int gngf_hpd_dlogits(gngf_lattice lat, const float* uprobs, int64_t T, int32_t K
                      const float* gdense, const float* row_max, const float* row_sum, int64_t u0, int64_t n_rows,
                      float* dlogits, void* stream);
 
+/* ---- f-1: calc_hash_collisions (models.py:568-619) ------------------------------------------------------------
+ * indices (P,L,V,C) as float32 (train_step's buffer, functions.py:179,216) or int64; uniq (C,L) int32 = number of
+ * distinct integer values in [0,range) per (column, level); *outliers is set to 1 when any value is not such an
+ * integer (the caller then counts exactly by other means).  bitmap: gngf_count_distinct_workspace_words() words. */
+int64_t gngf_count_distinct_workspace_words(int32_t L, int32_t C, int64_t range);
+int gngf_count_distinct_f32(const float* indices, int64_t P, int32_t L, int32_t V, int32_t C, int64_t range,
+                            uint32_t* bitmap, int32_t* uniq, int32_t* outliers, void* stream);
+int gngf_count_distinct_i64(const int64_t* indices, int64_t P, int32_t L, int32_t V, int32_t C, int64_t range,
+                            uint32_t* bitmap, int32_t* uniq, int32_t* outliers, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

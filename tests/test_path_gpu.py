@@ -188,3 +188,24 @@ def test_fused_loss_kernel_matches_reference_loss(name):
     t2, _, _ = total_loss(rgb.detach(), y, probs.colsum.detach(), rows, c["gamma"], c["epsilon"], c["l_mse"],
                           c["l_js_kl"], coll)
     assert abs(float(t2) - float(total)) < 1e-5 * abs(float(t2))
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_calc_hash_collisions_matches_reference(name):
+    g = load(name)
+    net = build_net(g)
+    idx = torch.from_numpy(g["idx"]).cuda()
+    coll, minp = net.calc_hash_collisions(idx if g["cfg"]["use_hash"] else idx.float())
+    # counts are exact integers; the mean over the K columns is a float32 reduction (1 ulp of order freedom)
+    np.testing.assert_allclose(coll.cpu().numpy(), g["chc_collisions"], rtol=1e-6, atol=0)
+    assert np.array_equal(minp.cpu().numpy(), g["chc_min_possible"])
+    if not g["cfg"]["use_hash"]:
+        # int64 input and a buffer with garbage (what torch.empty may hold) agree with exact counting
+        coll_i, _ = net.calc_hash_collisions(idx)
+        np.testing.assert_allclose(coll_i.cpu().numpy(), g["chc_collisions"], rtol=1e-6, atol=0)
+        junk = idx.float().clone()
+        junk[::3, :, :, 0] = 1e30
+        junk[1::7, :, :, -1] = -0.5
+        coll_j, _ = net.calc_hash_collisions(junk)
+        ref, _ = O.calc_hash_collisions(junk.cpu().numpy(), g["n_ls"], g["cfg"]["T"])
+        np.testing.assert_allclose(coll_j.cpu().numpy(), ref, rtol=1e-6, atol=0)
