@@ -73,6 +73,24 @@ class GradientAllReducer:
                 p.grad.copy_(v)
 
 
+def enable_gradient_allreduce(group=None) -> None:
+    """Averages the parameter gradients over ranks inside GNGFPath.backward: all of them are views of one flat
+    buffer there, so it is a single in-place all-reduce and no flatten / unflatten copies (vs. GradientAllReducer,
+    which works on arbitrary parameter lists)."""
+    from . import ops
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        ops.GRAD_REDUCE_HOOK = None
+        return
+    world = dist.get_world_size(group)
+
+    def hook(flat: torch.Tensor) -> None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+
+    ops.GRAD_REDUCE_HOOK = hook
+
+
 def shard_bounds(total: int, rank: int, world: int):
     """Even contiguous shards of a batch of `total` points (the last ranks get one fewer when it does not divide)."""
     base, rem = divmod(total, world)

@@ -24,6 +24,9 @@ from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, MIX_RAW, MIX
 
 MAX_DENSE_LOGIT_BYTES = 96 << 30   # (U, T) fp32 logits are materialised by this path
 
+# data parallelism: called on the flat gradient buffer at the end of GNGFPath.backward (dp.enable_gradient_allreduce)
+GRAD_REDUCE_HOOK = None
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -435,6 +438,8 @@ class GNGFPath(torch.autograd.Function):
         gtab = make_tables(g_tables)
         if cfg.use_hash:
             call("gngf_encode_hash_bwd", x.data_ptr(), P, lat, gtab, T, F, denc.data_ptr(), st)
+            if GRAD_REDUCE_HOOK is not None:
+                GRAD_REDUCE_HOOK(flat)
             return (None, None, *grads)
 
         call("gngf_encode_bwd", x.data_ptr(), P, lat, F, denc.data_ptr(), dnf.data_ptr(), st)
@@ -444,6 +449,8 @@ class GNGFPath(torch.autograd.Function):
         if not need_hpd:
             for i in range(2 * nh):
                 grads[i] = None
+            if GRAD_REDUCE_HOOK is not None:
+                GRAD_REDUCE_HOOK(flat)
             return (None, None, *grads)
 
         gcol = gcol_k = gdense = None
@@ -503,6 +510,8 @@ class GNGFPath(torch.autograd.Function):
             dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
         call("gngf_hpd_first_layer_bwd", lat, dz.data_ptr(), hpd_w[0].shape[0], g_hpd_w[0].data_ptr(),
              g_hpd_b[0].data_ptr(), st)
+        if GRAD_REDUCE_HOOK is not None:
+            GRAD_REDUCE_HOOK(flat)      # every parameter gradient is a view of `flat`: one collective for all
         return (None, None, *grads)
 
 
