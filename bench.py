@@ -35,7 +35,7 @@ WORKLOADS = {
     "cfg2": dict(P=57404, L=4, n_min=8, n_max=32, T=256, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
                  lattice_hw=(508, 339), topk_only=False, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
                  lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
-                 cpu_sample=8192),
+                 cpu_sample=16384),
     # BASELINE.json configs[2]: macaw.jpg (508x339 = 172 212 px < 2^18: the whole image is one batch), 16 levels,
     # table size 2^19, top-k-only probabilities (the full distribution would be 134 MB per sample)
     "cfg3": dict(P=172212, L=16, n_min=16, n_max=508, T=2 ** 19, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
@@ -67,51 +67,18 @@ def make_inputs(w, seed, rank=0):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (numpy restatement of the reference), forward + loss + backward + Adam
+# CPU arm: the reference's path restated on PyTorch-CPU (oracle/torch_port.py), forward + loss + backward + Adam
 # ------------------------------------------------------------------------------------------------------------
-def cpu_port_step_factory(w, sample_P, seed):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import gngf_oracle as O
-    rng = np.random.default_rng(seed)
-    n_ls = O.level_resolutions(w["n_min"], w["n_max"], w["L"])
-    widths = [2, *w["hpd"], w["T"]]
-    mw = [w["L"] * w["F"], *w["mlp"], 3]
-
-    def lin(i, o):
-        b = 1 / np.sqrt(i)
-        return rng.uniform(-b, b, (o, i)).astype(np.float32), rng.uniform(-b, b, o).astype(np.float32)
-
-    hp = [lin(widths[i], widths[i + 1]) for i in range(len(widths) - 1)]
-    ml = [lin(mw[i], mw[i + 1]) for i in range(len(mw) - 1)]
-    params = {"hpd_w": [a for a, _ in hp], "hpd_b": [b for _, b in hp],
-              "tables": [rng.uniform(-1e-4, 1e-4, (w["T"], w["F"])).astype(np.float32) for _ in range(w["L"])],
-              "mlp_w": [a for a, _ in ml], "mlp_b": [b for _, b in ml]}
-    cfg = {"n_ls": n_ls, "table_size": w["T"], "topk_k": w["K"], "mix_mode": True, "use_hash": False,
-           "leaky": False, "topk_only": w["topk_only"]}
-    lcfg = {k: w[k] for k in ("gamma", "epsilon", "l_mse", "l_js_kl")}
-    ws = dict(w, P=sample_P)
-    x, y = make_inputs(ws, seed)
-    adam = {}
-
-    def step():
-        fwd = O.gngf_forward(params, x, cfg)
-        total, _, _, _ = O.total_loss(fwd["rgb"], y, fwd["pbar"], w["gamma"], w["epsilon"], w["l_mse"], w["l_js_kl"], 0.0)
-        grads = O.gngf_backward(params, x, y, cfg, fwd, lcfg)
-        for key in ("hpd_w", "hpd_b", "tables", "mlp_w", "mlp_b"):           # Adam, functions.py:96-127
-            for i, (p, g) in enumerate(zip(params[key], grads[key])):
-                m, v, t = adam.get((key, i), (np.zeros_like(p), np.zeros_like(p), 0))
-                t += 1
-                m = 0.9 * m + 0.1 * g
-                v = 0.99 * v + 0.01 * g * g
-                p -= 1e-3 * (m / (1 - 0.9 ** t)) / (np.sqrt(v / (1 - 0.99 ** t)) + 1e-15)
-                adam[(key, i)] = (m, v, t)
-        return float(total)
-
-    return step
-
-
 def time_cpu_port(w, sample_P, seed, steps, warmup):
-    step = cpu_port_step_factory(w, sample_P, seed)
+    """Seconds per step of the PyTorch-CPU port of the reference (oracle/torch_port.py: the same ATen operations
+    and autograd the reference issues, all host threads) on `sample_P` coordinates of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import gngf_oracle as O
+    import torch_port as TP
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y = make_inputs(dict(w, P=sample_P), seed)
+    step = TP.make_step(w, x, y, O.level_resolutions(w["n_min"], w["n_max"], w["L"]), seed)
     for _ in range(warmup):
         step()
     times = []
@@ -123,12 +90,8 @@ def time_cpu_port(w, sample_P, seed, steps, warmup):
 
 
 def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        n = os.cpu_count() or 1
-    return int(n)
+    import torch
+    return int(torch.get_num_threads())
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -216,7 +179,8 @@ class CallProfiler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/r01_*_ncu_full.txt); None where no capture exists yet
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {("cfg2", "gngf_mlp3_bwd"): 2606080, ("cfg2", "gngf_mlp3_fwd"): 1892096,
+               ("cfg3_t14", "gngf_hpd_stream_fwd"): 154538000, ("cfg3_t14", "gngf_tc_gemm_bf16x3"): 2802181000}
 
 
 def cost_key(name, args):
@@ -277,6 +241,7 @@ def run_ours(args, w):
     from collision_handling_in_instantngp_b200 import _lib, dp, launch_count
     from collision_handling_in_instantngp_b200.loss import fused_total_loss as total_loss
     from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+    from collision_handling_in_instantngp_b200.trainer import GraphedTrainer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -335,7 +300,7 @@ def run_ours(args, w):
     sampler = ClockSampler(local)
     sampler.start()
 
-    # ---- end-to-end: eager module API, host (pinned) inputs copied in, loss read back, every step ----
+    # ---- eager module API end to end (what the reference's own train_step does with the drop-in module) ----
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -345,7 +310,7 @@ def run_ours(args, w):
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_eager_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     del loss, xd, yd          # (the last eager loss would keep default-stream AccumulateGrad nodes alive at capture)
 
     # ---- per-kernel device times (eager pass, CUDA events around every C-ABI call) -> dominant kernel ----
@@ -359,32 +324,16 @@ def run_ours(args, w):
     lat = net.last_state.lat
     barrier()
 
-    # ---- capture the whole step (our kernels, the fused Adam and, for N > 1, the two NCCL all-reduces) ----
-    graph, launch_mode = None, "eager"
+    # ---- the public fast path: the whole step (our kernels, fused Adam, for N > 1 the two NCCL all-reduces)
+    #      captured once in a CUDA graph over static input buffers (trainer.GraphedTrainer) ----
+    trainer, launch_mode = None, "eager"
     if not args.eager and w["T"] <= 4096:
-        opt.zero_grad(set_to_none=True)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step(x_dev, y_dev)
-        torch.cuda.current_stream().wait_stream(side)
-        barrier()
-        graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
-        net.last_state = None
-        with torch.cuda.graph(graph, stream=side):
-            graph_loss = step(x_dev, y_dev)
+        trainer = GraphedTrainer(net, opt, points=w["P"], gamma=w["gamma"], epsilon=w["epsilon"], l_mse=w["l_mse"],
+                                 l_js_kl=w["l_js_kl"], warmup_steps=3, sample_x=x_dev, sample_y=y_dev)
         launch_mode = "cuda_graph"
         for _ in range(max(args.warmup, 3)):
-            graph.replay()
+            trainer.replay()
         torch.cuda.synchronize()
-
-    def timed_step():
-        if graph is not None:
-            graph.replay()
-        else:
-            step(x_dev, y_dev)
 
     # ---- the device-timed region: inputs resident in HBM, CUDA events around every step, L2 flushed between ----
     barrier()
@@ -393,11 +342,28 @@ def run_ours(args, w):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        timed_step()
+        if trainer is not None:
+            trainer.replay()
+        else:
+            step(x_dev, y_dev)
         b.record()
         evs.append((a, b))
     barrier()
     dev_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    # ---- end to end through the public API with HOST buffers: every step copies the batch in from pinned host
+    #      memory and reads the loss back (wall clock, max over ranks) ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if trainer is not None:
+            loss = trainer.step(x_host, y_host)
+        else:
+            loss = step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
 
     per_name = {}
@@ -431,9 +397,9 @@ def run_ours(args, w):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([dev_ms, e2e_ms, e2e_eager_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dev_ms, e2e_ms, e2e_eager_ms = float(t[0]), float(t[1]), float(t[2])
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -441,7 +407,8 @@ def run_ours(args, w):
         sec = time_cpu_port(w, sample_P, 65535, steps=3, warmup=1)
         cpu_base = {"value": sample_P / sec, "unit": "samples/s", "cores": cpu_threads(), "kind": "port",
                     "sample": f"{sample_P} of the workload's {w['P']} coordinates per step, 3 steps after 1 warm-up, "
-                              "oracle/gngf_oracle.py (numpy fp32) forward+loss+backward+Adam"}
+                              "oracle/torch_port.py (PyTorch-CPU restatement of the reference: same ATen ops + autograd) "
+                              "forward+loss+backward+Adam"}
     if rank == 0:
         total = w["P"] * world
         line = {
@@ -457,7 +424,14 @@ def run_ours(args, w):
                        "lattice_nodes": lat.num_nodes, "level_nodes": lat.num_level_nodes},
             "e2e": {"value": total / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
-                    "path": "module API, eager, pinned host inputs copied in and loss read back every step"},
+                    "path": ("trainer.GraphedTrainer.step(x_host, y_host): pinned host batch copied into the static "
+                             "buffers, CUDA-graph replay of forward+loss+backward+Adam, loss read back, every step"
+                             if trainer is not None else
+                             "module API, eager, pinned host inputs copied in and loss read back every step"),
+                    "eager_module_api": {"value": total / (e2e_eager_ms / 1e3), "unit": "samples/s",
+                                         "ms_per_step": e2e_eager_ms,
+                                         "path": "net(x) / loss / backward / Adam driven eagerly from Python, as the "
+                                                 "reference's train_step drives the drop-in module"}},
             "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roofline,
         }
@@ -493,8 +467,8 @@ def main():
         sec = time_cpu_port(w, sample_P, 65535, steps=args.steps, warmup=args.warmup)
         val = sample_P / sec
         cores = cpu_threads()
-        sample = (f"{sample_P} of the workload's {w['P']} coordinates per step; oracle/gngf_oracle.py (numpy fp32 port of "
-                  "the reference's PyTorch-CPU path) forward+loss+backward+Adam")
+        sample = (f"{sample_P} of the workload's {w['P']} coordinates per step; oracle/torch_port.py (PyTorch-CPU "
+                  "restatement of the reference: same ATen ops + autograd, all host threads) forward+loss+backward+Adam")
         print(json.dumps({
             "impl": "reference", "metric": "train samples/sec (fwd+bwd GNGF hash encode+MLP)", "value": val,
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

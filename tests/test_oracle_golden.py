@@ -114,3 +114,27 @@ def test_calc_hash_collisions_matches_reference(name):
         coll, minp = O.calc_hash_collisions(g["idx"].astype(np.float32), g["n_ls"], g["cfg"]["T"])
     np.testing.assert_allclose(coll, g["chc_collisions"], rtol=0, atol=0)
     np.testing.assert_array_equal(minp, g["chc_min_possible"])
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "l16_t1024", "k20"])
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.py (the timed CPU baseline) reproduces the reference's forward, loss and gradients."""
+    import torch
+    import torch_port as TP
+    g = load(name)
+    c = g["cfg"]
+    p = params_of(g)
+    tp = {k: [torch.from_numpy(a.copy()).requires_grad_() for a in v] for k, v in p.items()}
+    cfg = {"n_ls": g["n_ls"], "topk_k": c["K"], "topk_only": c["topk_only"]}
+    rgb, probs, idx = TP.forward(tp, torch.from_numpy(g["x"]), cfg)
+    total, mse, levels = TP.loss(rgb, torch.from_numpy(g["y"]), probs, c["gamma"], c["epsilon"], c["l_mse"], c["l_js_kl"])
+    total.backward()
+    assert np.array_equal(idx.numpy(), g["idx"])
+    assert rel_err(rgb.detach().numpy(), g["rgb"]) < FWD_TOL
+    assert abs(float(total) - g["loss"]) < 1e-5 * abs(g["loss"])
+    for l in range(c["L"]):
+        assert rel_err(tp["tables"][l].grad.numpy(), g[f"grad.encoding._hash_tables.{l}.weight"]) < GRAD_TOL
+    for i in range(len(tp["hpd_w"])):
+        assert rel_err(tp["hpd_w"][i].grad.numpy(), g[f"grad.HPD.module_list.{i}.0.weight"]) < GRAD_TOL
+    for i in range(len(tp["mlp_w"])):
+        assert rel_err(tp["mlp_w"][i].grad.numpy(), g[f"grad.mlp.{i}.0.weight"]) < GRAD_TOL
