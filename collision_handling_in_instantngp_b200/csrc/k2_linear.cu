@@ -218,7 +218,8 @@ int gngf_hpd_first_layer_fwd(gngf_lattice lat, const float* w0, const float* b0,
 int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, float* dw0, float* db0, void* stream) {
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   if (U <= 0 || n_out <= 0) return GNGF_ERR_INVALID_ARGUMENT;
-  const int64_t rows_per_block = 64;
+  // enough blocks to cover the chip even for a few hundred nodes
+  const int64_t rows_per_block = std::max<int64_t>(4, gngf::ceil_div(U, 4 * gngf::sm_count()));
   gngf::first_layer_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, rows_per_block)), 128, 0,
                                  gngf::as_stream(stream)>>>(lat, dz, n_out, rows_per_block, dw0, db0);
   gngf::note_launch();
@@ -246,8 +247,10 @@ int gngf_linear_bwd(const float* dz, const float* x, const float* w, int64_t M, 
     if (rc) return rc;
   }
   if (db) {
-    const int64_t rows_per_block = 256;
-    dim3 grid(static_cast<unsigned>(gngf::ceil_div(N, 32)), static_cast<unsigned>(gngf::ceil_div(M, rows_per_block)));
+    const int64_t col_blocks = gngf::ceil_div(N, 32);
+    const int64_t rows_per_block =
+        std::min<int64_t>(256, std::max<int64_t>(32, gngf::ceil_div(M * col_blocks, 4 * gngf::sm_count())));
+    dim3 grid(static_cast<unsigned>(col_blocks), static_cast<unsigned>(gngf::ceil_div(M, rows_per_block)));
     if (grid.y > 65535) return GNGF_ERR_UNSUPPORTED;
     gngf::colsum_kernel<<<grid, 256, 0, st>>>(dz, M, N, rows_per_block, db);
     gngf::note_launch();
