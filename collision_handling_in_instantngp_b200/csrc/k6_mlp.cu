@@ -14,24 +14,28 @@
 namespace gngf {
 
 constexpr int H = 64;        // hidden width
-constexpr int TP = 128;      // points per tile
+constexpr int TP = 64;       // points per tile (64: ~77 KB of shared memory in the backward -> 2 CTAs per SM)
+constexpr int NG = TP / 64;  // float4 point groups per thread: thread tile = (4*NG points) x (4 outputs)
 constexpr int LDP = TP + 4;  // row stride of the k-major activation buffers
 constexpr int MLP_THREADS = 256;
 
 __device__ __forceinline__ float hidden_act(float v, int leaky) { return v > 0.0f ? v : (leaky ? v * 0.01f : 0.0f); }
 
-// acc[pi][ji] += sum_k A[k][p] * B[k][j] with p in {4*tp..4*tp+3, 64+4*tp..}, j in {4*tj..4*tj+3}
-__device__ __forceinline__ void gemm_8x4(const float* __restrict__ A, const float* __restrict__ B, int bstride, int K,
-                                         int tp, int tj, float acc[8][4]) {
+// acc[pi][ji] += sum_k A[k][p] * B[k][j] with p in {64*g + 4*tp .. +3, g < NG}, j in {4*tj .. 4*tj+3}
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ A, const float* __restrict__ B, int bstride, int K,
+                                          int tp, int tj, float acc[4 * NG][4]) {
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    const float4 a0 = *reinterpret_cast<const float4*>(A + k * LDP + 4 * tp);
-    const float4 a1 = *reinterpret_cast<const float4*>(A + k * LDP + 64 + 4 * tp);
+    float av[4 * NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 a = *reinterpret_cast<const float4*>(A + k * LDP + 64 * g + 4 * tp);
+      av[4 * g + 0] = a.x; av[4 * g + 1] = a.y; av[4 * g + 2] = a.z; av[4 * g + 3] = a.w;
+    }
     const float4 b = *reinterpret_cast<const float4*>(B + k * bstride + 4 * tj);
-    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4 * NG; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
   }
@@ -134,22 +138,24 @@ __device__ __forceinline__ void load_enc_tile(const MlpSmem& s, const float* __r
 __device__ __forceinline__ void hidden_layer(const float* src, const float* Wt, const float* b, int K, float* dst,
                                              int leaky) {
   const int tp = threadIdx.x % 16, tj = threadIdx.x / 16;
-  float acc[8][4];
+  float acc[4 * NG][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4 * NG; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  gemm_8x4(src, Wt, H, K, tp, tj, acc);
+  gemm_tile(src, Wt, H, K, tp, tj, acc);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float bj = b[4 * tj + j];
-    float4 lo, hi;
-    lo.x = hidden_act(acc[0][j] + bj, leaky); lo.y = hidden_act(acc[1][j] + bj, leaky);
-    lo.z = hidden_act(acc[2][j] + bj, leaky); lo.w = hidden_act(acc[3][j] + bj, leaky);
-    hi.x = hidden_act(acc[4][j] + bj, leaky); hi.y = hidden_act(acc[5][j] + bj, leaky);
-    hi.z = hidden_act(acc[6][j] + bj, leaky); hi.w = hidden_act(acc[7][j] + bj, leaky);
-    *reinterpret_cast<float4*>(dst + (4 * tj + j) * LDP + 4 * tp) = lo;
-    *reinterpret_cast<float4*>(dst + (4 * tj + j) * LDP + 64 + 4 * tp) = hi;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      float4 o;
+      o.x = hidden_act(acc[4 * g + 0][j] + bj, leaky);
+      o.y = hidden_act(acc[4 * g + 1][j] + bj, leaky);
+      o.z = hidden_act(acc[4 * g + 2][j] + bj, leaky);
+      o.w = hidden_act(acc[4 * g + 3][j] + bj, leaky);
+      *reinterpret_cast<float4*>(dst + (4 * tj + j) * LDP + 64 * g + 4 * tp) = o;
+    }
   }
 }
 
@@ -268,8 +274,8 @@ __global__ void __launch_bounds__(MLP_THREADS)
         const int jj = 4 * tj + j;
         const float w20 = s.W2n[0 * H + jj], w21 = s.W2n[1 * H + jj], w22 = s.W2n[2 * H + jj], w23 = s.W2n[3 * H + jj];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int pp = half * 64 + 4 * tp;
+        for (int g = 0; g < NG; ++g) {
+          const int pp = g * 64 + 4 * tp;
           const float4 a = *reinterpret_cast<const float4*>(s.A2 + jj * LDP + pp);
           const float4 d0 = *reinterpret_cast<const float4*>(s.dz2 + 0 * LDP + pp);
           const float4 d1 = *reinterpret_cast<const float4*>(s.dz2 + 1 * LDP + pp);
@@ -324,26 +330,26 @@ __global__ void __launch_bounds__(MLP_THREADS)
     }
     // dz0[k][p] = (sum_j dz1[j][p] * w1[j][k]) * act'(a1[k][p]) -> registers, then in place over A1
     {
-      float acc[8][4];
+      float acc[4 * NG][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4 * NG; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-      gemm_8x4(s.A2, s.W1n, H, H, tp, tj, acc);
+      gemm_tile(s.A2, s.W1n, H, H, tp, tj, acc);
       __syncthreads();  // every thread is done reading A1 (dw1) before it is overwritten
       const float slope = leaky ? 0.01f : 0.0f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int kk = 4 * tj + j;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float* ptr = s.A1 + kk * LDP + half * 64 + 4 * tp;
+        for (int g = 0; g < NG; ++g) {
+          float* ptr = s.A1 + kk * LDP + g * 64 + 4 * tp;
           const float4 a = *reinterpret_cast<const float4*>(ptr);
           float4 r;
-          r.x = acc[half * 4 + 0][j] * (a.x > 0.0f ? 1.0f : slope);
-          r.y = acc[half * 4 + 1][j] * (a.y > 0.0f ? 1.0f : slope);
-          r.z = acc[half * 4 + 2][j] * (a.z > 0.0f ? 1.0f : slope);
-          r.w = acc[half * 4 + 3][j] * (a.w > 0.0f ? 1.0f : slope);
+          r.x = acc[g * 4 + 0][j] * (a.x > 0.0f ? 1.0f : slope);
+          r.y = acc[g * 4 + 1][j] * (a.y > 0.0f ? 1.0f : slope);
+          r.z = acc[g * 4 + 2][j] * (a.z > 0.0f ? 1.0f : slope);
+          r.w = acc[g * 4 + 3][j] * (a.w > 0.0f ? 1.0f : slope);
           *reinterpret_cast<float4*>(ptr) = r;
         }
       }
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(256)
 }
 
 static int mlp_grid(int64_t P, size_t smem_bytes) {
-  const int per_sm = smem_bytes <= 110 * 1024 ? 2 : 1;
+  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem_bytes + 1024))));
   return static_cast<int>(std::min<int64_t>(ceil_div(P, TP), static_cast<int64_t>(per_sm) * sm_count()));
 }
 
@@ -485,7 +491,7 @@ int gngf_mlp3_fwd(const float* enc, int64_t P, int32_t in_dim, int32_t out_dim, 
 }
 
 int64_t gngf_mlp3_bwd_workspace_floats(int32_t in_dim, int32_t out_dim) {
-  return static_cast<int64_t>(2 * gngf::sm_count()) * gngf::mlp_param_floats(in_dim, out_dim);
+  return static_cast<int64_t>(4 * gngf::sm_count()) * gngf::mlp_param_floats(in_dim, out_dim);
 }
 
 int gngf_mlp3_bwd(const float* enc, const float* drgb, int64_t P, int32_t in_dim, int32_t out_dim, int32_t leaky,
