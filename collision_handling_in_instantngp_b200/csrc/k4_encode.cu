@@ -70,11 +70,15 @@ __global__ void __launch_bounds__(256)
     if (f < F) out[f] = (mode == GNGF_MIX_WEIGHTED_AVG) ? acc[f] / norm : acc[f];
 }
 
-// Persistent grid, grid-stride over (point, level) items.  The node multiplicities `cnt` are a histogram with
-// heavy same-address traffic on the coarse levels (level 0 of the published configuration: 3 280 increments
-// per node and batch; an L2 atomic unit retires roughly one same-address update per 50-80 cycles), so the first
-// `private_nodes` level nodes -- the coarsest levels, which are stored first -- are counted in shared memory
-// and flushed once per CTA; finer levels go straight to global atomics where contention is naturally low.
+// Persistent grid, one thread per point, levels walked by an (unrolled) loop: the level index is uniform across
+// the warp, so the per-level geometry comes from the constant bank as a broadcast (a lane-per-level mapping
+// serialises those reads 16-way), the 4*L gathers of a point are independent loads in flight together, and on
+// the coarse levels the 32 points of a warp fall into a handful of cache lines.
+// The node multiplicities `cnt` are a histogram with heavy same-address traffic on the coarse levels (level 0 of
+// the published configuration: 3 280 increments per node and batch; an L2 atomic unit retires roughly one
+// same-address update per 50-80 cycles), so the first `private_nodes` level nodes -- the coarsest levels, which
+// are stored first -- are counted in shared memory and flushed once per CTA; finer levels go straight to global
+// atomics where contention is naturally low.
 template <int F>
 __global__ void __launch_bounds__(256)
     encode_fwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
@@ -88,43 +92,44 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   }
   bool outside = false;
-  const int64_t total = P * L, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
-    const int64_t p = i / L;
-    const int l = static_cast<int>(i - p * L);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < P; p += stride) {
     const float2 xy = x[p];
-    const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
-    int64_t s[4];
+    float* out = enc + p * (L * F);
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+      const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+      int64_t s[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) s[v] = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
-    float acc[F];
-    if constexpr (F == 2) {
-      float2 nf[4];
+      for (int v = 0; v < 4; ++v) s[v] = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
+      if constexpr (F == 2) {
+        float2 nf[4];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) nf[v] = __ldg(reinterpret_cast<const float2*>(nfeat) + s[v]);
-      acc[0] = 0.0f;
-      acc[1] = 0.0f;
+        for (int v = 0; v < 4; ++v) nf[v] = __ldg(reinterpret_cast<const float2*>(nfeat) + s[v]);
+        float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        acc[0] = fmaf(nf[v].x, c.w[v], acc[0]);
-        acc[1] = fmaf(nf[v].y, c.w[v], acc[1]);
+        for (int v = 0; v < 4; ++v) {
+          a0 = fmaf(nf[v].x, c.w[v], a0);
+          a1 = fmaf(nf[v].y, c.w[v], a1);
+        }
+        reinterpret_cast<float2*>(out)[l] = make_float2(a0, a1);
+      } else {
+        float acc[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+          for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(nfeat + s[v] * F + f), c.w[v], acc[f]);
+#pragma unroll
+        for (int f = 0; f < F; ++f) out[l * F + f] = acc[f];
       }
-      reinterpret_cast<float2*>(enc)[i] = make_float2(acc[0], acc[1]);
-    } else {
+      if (cnt) {
 #pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] = 0.0f;
-#pragma unroll
-      for (int v = 0; v < 4; ++v)
-#pragma unroll
-        for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(nfeat + s[v] * F + f), c.w[v], acc[f]);
-#pragma unroll
-      for (int f = 0; f < F; ++f) enc[i * F + f] = acc[f];
-    }
-    if (cnt) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (s[v] < private_nodes) atomicAdd(cnt_s + s[v], 1);
-        else atomicAdd(cnt + s[v], 1);
+        for (int v = 0; v < 4; ++v) {
+          if (s[v] < private_nodes) atomicAdd(cnt_s + s[v], 1);
+          else atomicAdd(cnt + s[v], 1);
+        }
       }
     }
   }
@@ -138,34 +143,50 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// hash-function mode: enc straight from table_l[hash(corner)], optional idx output (P,L,4) int64
+// hash-function mode: enc straight from table_l[hash(corner)], optional idx output (P,L,4) int64;
+// thread per point, loop over levels (see encode_fwd_kernel)
 template <int F>
 __global__ void __launch_bounds__(256)
     encode_hash_fwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
                            const __grid_constant__ gngf_tables tables, int64_t T, float* __restrict__ enc,
                            int64_t* __restrict__ idx_out) {
   const int L = lat.num_levels;
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= P * L) return;
-  const int64_t p = i / L;
-  const int l = static_cast<int>(i - p * L);
-  const float2 xy = x[p];
-  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
-  const float* table = tables.ptr[l];
-  float acc[F];
+  const bool pow2 = (T & (T - 1)) == 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < P; p += stride) {
+    const float2 xy = x[p];
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+      const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+      const float* table = tables.ptr[l];
+      float acc[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+      for (int f = 0; f < F; ++f) acc[f] = 0.0f;
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint32_t gx = static_cast<uint32_t>(c.cx + (v & 1)), gy = static_cast<uint32_t>(c.cy + (v >> 1));
-    int64_t h = static_cast<int64_t>(static_cast<int32_t>(gx ^ (gy * 2654435761u))) % T;
-    if (h < 0) h += T;
-    if (idx_out) idx_out[i * 4 + v] = h;
+      for (int v = 0; v < 4; ++v) {
+        const uint32_t gx = static_cast<uint32_t>(c.cx + (v & 1)), gy = static_cast<uint32_t>(c.cy + (v >> 1));
+        const uint32_t h32 = gx ^ (gy * 2654435761u);
+        int64_t h;
+        if (pow2) {
+          h = static_cast<int64_t>(h32 & static_cast<uint32_t>(T - 1));   // == non-negative remainder of the int32
+        } else {
+          h = static_cast<int64_t>(static_cast<int32_t>(h32)) % T;
+          if (h < 0) h += T;
+        }
+        if (idx_out) idx_out[(p * L + l) * 4 + v] = h;
+        if constexpr (F == 2) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(table) + h);
+          acc[0] = fmaf(t.x, c.w[v], acc[0]);
+          acc[1] = fmaf(t.y, c.w[v], acc[1]);
+        } else {
 #pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(table + h * F + f), c.w[v], acc[f]);
+          for (int f = 0; f < F; ++f) acc[f] = fmaf(__ldg(table + h * F + f), c.w[v], acc[f]);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) enc[(p * L + l) * F + f] = acc[f];
+    }
   }
-#pragma unroll
-  for (int f = 0; f < F; ++f) enc[i * F + f] = acc[f];
 }
 
 // out[l, n] += sum over level nodes s of level l: cnt[s] * uvals[u(s), n]
@@ -263,8 +284,7 @@ int gngf_encode_fwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, cons
   const float2* x2 = reinterpret_cast<const float2*>(x);
   const int priv = cnt ? gngf::private_node_count(lat, 10240) : 0;      // <= 40 KB of shared counters
   const size_t smem = sizeof(int32_t) * priv;
-  const int64_t items = P * lat.num_levels;
-  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(items, 256), 2 * gngf::sm_count()));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(P, 256), 8 * gngf::sm_count()));
   switch (F) {
     case 1: gngf::encode_fwd_kernel<1><<<blocks, 256, smem, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag, priv); break;
     case 2: gngf::encode_fwd_kernel<2><<<blocks, 256, smem, st>>>(x2, P, lat, nfeat, enc, cnt, err_flag, priv); break;
@@ -280,7 +300,7 @@ int gngf_encode_hash_fwd(const float* x, int64_t P, gngf_lattice lat, gngf_table
                          float* enc, int64_t* idx_out, void* stream) {
   if (!gngf::valid_lat(lat) || P < 0 || T <= 0) return GNGF_ERR_INVALID_ARGUMENT;
   if (P == 0) return GNGF_OK;
-  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(P, 256), 8 * gngf::sm_count()));
   cudaStream_t st = gngf::as_stream(stream);
   const float2* x2 = reinterpret_cast<const float2*>(x);
   switch (F) {

@@ -15,8 +15,8 @@
 
 namespace gngf {
 
-// Persistent grid; the first `private_nodes` level nodes (coarsest levels) accumulate in shared memory and
-// are flushed once per CTA -- see encode_fwd_kernel for why.
+// Persistent grid, one thread per point with a loop over levels (see encode_fwd_kernel); the first
+// `private_nodes` level nodes (coarsest levels) accumulate in shared memory and are flushed once per CTA.
 template <int F>
 __global__ void __launch_bounds__(256)
     encode_bwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
@@ -27,36 +27,77 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < private_nodes * F; i += blockDim.x) dnf_s[i] = 0.0f;
     __syncthreads();
   }
-  const int64_t total = P * L, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
-    const int64_t p = i / L;
-    const int l = static_cast<int>(i - p * L);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < P; p += stride) {
     const float2 xy = x[p];
-    const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
-    bool outside = false;
-    float d[F];
-    if constexpr (F == 2) {
-      const float2 t = reinterpret_cast<const float2*>(denc)[i];
-      d[0] = t.x;
-      d[1] = t.y;
-    } else {
-#pragma unroll
-      for (int f = 0; f < F; ++f) d[f] = denc[i * F + f];
-    }
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int64_t s = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
-      const float w = c.w[v];
-      if (w == 0.0f) continue;  // x == 1.0 rows: the far corners carry exactly zero weight
-      if (s < private_nodes) {
-#pragma unroll
-        for (int f = 0; f < F; ++f) atomicAdd(dnf_s + s * F + f, d[f] * w);
-      } else if constexpr (F % 2 == 0) {
-#pragma unroll
-        for (int f = 0; f < F; f += 2) red_add_v2(dnf + s * F + f, d[f] * w, d[f + 1] * w);
+    const float* din = denc + p * (L * F);
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+      const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+      bool outside = false;
+      float d[F];
+      if constexpr (F == 2) {
+        const float2 t = reinterpret_cast<const float2*>(din)[l];
+        d[0] = t.x;
+        d[1] = t.y;
       } else {
 #pragma unroll
-        for (int f = 0; f < F; ++f) atomicAdd(dnf + s * F + f, d[f] * w);
+        for (int f = 0; f < F; ++f) d[f] = din[l * F + f];
+      }
+      if constexpr (F == 2) {
+        // corners (cx, cy) / (cx, cy+1) are adjacent level nodes: one 16-byte reduction when the pair is aligned
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int64_t s0 = level_node(lat, l, c.cx + dx, c.cy, outside);
+          const int64_t s1 = level_node(lat, l, c.cx + dx, c.cy + 1, outside);
+          const float w0 = c.w[dx], w1 = c.w[dx + 2];
+          if (s0 < private_nodes && s1 < private_nodes) {
+            if (w0 != 0.0f) {
+              atomicAdd(dnf_s + s0 * 2, d[0] * w0);
+              atomicAdd(dnf_s + s0 * 2 + 1, d[1] * w0);
+            }
+            if (w1 != 0.0f) {
+              atomicAdd(dnf_s + s1 * 2, d[0] * w1);
+              atomicAdd(dnf_s + s1 * 2 + 1, d[1] * w1);
+            }
+          } else if (s1 == s0 + 1 && (s0 & 1) == 0 && s0 >= private_nodes) {
+            red_add_v4(dnf + s0 * 2, d[0] * w0, d[1] * w0, d[0] * w1, d[1] * w1);
+          } else {
+            if (w0 != 0.0f) {
+              if (s0 < private_nodes) {
+                atomicAdd(dnf_s + s0 * 2, d[0] * w0);
+                atomicAdd(dnf_s + s0 * 2 + 1, d[1] * w0);
+              } else {
+                red_add_v2(dnf + s0 * 2, d[0] * w0, d[1] * w0);
+              }
+            }
+            if (w1 != 0.0f) {
+              if (s1 < private_nodes) {
+                atomicAdd(dnf_s + s1 * 2, d[0] * w1);
+                atomicAdd(dnf_s + s1 * 2 + 1, d[1] * w1);
+              } else {
+                red_add_v2(dnf + s1 * 2, d[0] * w1, d[1] * w1);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int64_t s = level_node(lat, l, c.cx + (v & 1), c.cy + (v >> 1), outside);
+          const float w = c.w[v];
+          if (w == 0.0f) continue;  // x == 1.0 rows: the far corners carry exactly zero weight
+          if (s < private_nodes) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) atomicAdd(dnf_s + s * F + f, d[f] * w);
+          } else if constexpr (F % 2 == 0) {
+#pragma unroll
+            for (int f = 0; f < F; f += 2) red_add_v2(dnf + s * F + f, d[f] * w, d[f + 1] * w);
+          } else {
+#pragma unroll
+            for (int f = 0; f < F; ++f) atomicAdd(dnf + s * F + f, d[f] * w);
+          }
+        }
       }
     }
   }
@@ -145,28 +186,37 @@ __global__ void __launch_bounds__(256)
     encode_hash_bwd_kernel(const float2* __restrict__ x, int64_t P, const __grid_constant__ gngf_lattice lat,
                            const __grid_constant__ gngf_tables tgrads, int64_t T, const float* __restrict__ denc) {
   const int L = lat.num_levels;
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= P * L) return;
-  const int64_t p = i / L;
-  const int l = static_cast<int>(i - p * L);
-  const float2 xy = x[p];
-  const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
-  float* tgrad = tgrads.ptr[l];
-  float d[F];
+  const bool pow2 = (T & (T - 1)) == 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < P; p += stride) {
+    const float2 xy = x[p];
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+      const Cell c = cell_of(xy.x, xy.y, lat.n[l]);
+      float* tgrad = tgrads.ptr[l];
+      float d[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) d[f] = denc[i * F + f];
+      for (int f = 0; f < F; ++f) d[f] = denc[(p * L + l) * F + f];
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint32_t gx = static_cast<uint32_t>(c.cx + (v & 1)), gy = static_cast<uint32_t>(c.cy + (v >> 1));
-    int64_t h = static_cast<int64_t>(static_cast<int32_t>(gx ^ (gy * 2654435761u))) % T;
-    if (h < 0) h += T;
-    const float w = c.w[v];
-    if constexpr (F % 2 == 0) {
+      for (int v = 0; v < 4; ++v) {
+        const uint32_t gx = static_cast<uint32_t>(c.cx + (v & 1)), gy = static_cast<uint32_t>(c.cy + (v >> 1));
+        const uint32_t h32 = gx ^ (gy * 2654435761u);
+        int64_t h;
+        if (pow2) {
+          h = static_cast<int64_t>(h32 & static_cast<uint32_t>(T - 1));
+        } else {
+          h = static_cast<int64_t>(static_cast<int32_t>(h32)) % T;
+          if (h < 0) h += T;
+        }
+        const float w = c.w[v];
+        if constexpr (F % 2 == 0) {
 #pragma unroll
-      for (int f = 0; f < F; f += 2) red_add_v2(tgrad + h * F + f, d[f] * w, d[f + 1] * w);
-    } else {
+          for (int f = 0; f < F; f += 2) red_add_v2(tgrad + h * F + f, d[f] * w, d[f + 1] * w);
+        } else {
 #pragma unroll
-      for (int f = 0; f < F; ++f) atomicAdd(tgrad + h * F + f, d[f] * w);
+          for (int f = 0; f < F; ++f) atomicAdd(tgrad + h * F + f, d[f] * w);
+        }
+      }
     }
   }
 }
@@ -183,8 +233,7 @@ int gngf_encode_bwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, cons
   const float2* x2 = reinterpret_cast<const float2*>(x);
   const int priv = gngf::private_node_count(lat, (40 * 1024) / (4 * F));   // <= 40 KB of shared accumulators
   const size_t smem = sizeof(float) * priv * F;
-  const int64_t items = P * lat.num_levels;
-  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(items, 256), 2 * gngf::sm_count()));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(P, 256), 8 * gngf::sm_count()));
   switch (F) {
     case 1: gngf::encode_bwd_kernel<1><<<blocks, 256, smem, st>>>(x2, P, lat, denc, dnf, priv); break;
     case 2: gngf::encode_bwd_kernel<2><<<blocks, 256, smem, st>>>(x2, P, lat, denc, dnf, priv); break;
@@ -215,7 +264,7 @@ int gngf_encode_hash_bwd(const float* x, int64_t P, gngf_lattice lat, gngf_table
                          const float* denc, void* stream) {
   if (lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS || P < 0 || T <= 0) return GNGF_ERR_INVALID_ARGUMENT;
   if (P == 0) return GNGF_OK;
-  const unsigned blocks = static_cast<unsigned>(gngf::ceil_div(P * lat.num_levels, 256));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(P, 256), 8 * gngf::sm_count()));
   cudaStream_t st = gngf::as_stream(stream);
   const float2* x2 = reinterpret_cast<const float2*>(x);
   switch (F) {
