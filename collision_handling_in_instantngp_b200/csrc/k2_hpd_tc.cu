@@ -106,6 +106,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
     case GNGF_ACT_RELU: return fmaxf(v, 0.0f);
@@ -293,6 +304,10 @@ constexpr int A_KBLOCKS = 2;                             // resident A tile: K <
 constexpr uint32_t A_BYTES = A_KBLOCKS * PLANES * PLANE_BYTES;   // 96 KB
 constexpr uint32_t B_STAGE_BYTES = PLANES * PLANE_BYTES;         // 48 KB: one k-block of one column tile
 constexpr size_t STREAM_SMEM_BYTES = A_BYTES + STAGES * B_STAGE_BYTES + 1024 + 256;
+constexpr int STREAM_EPI_WARPS = 16;                     // four per TMEM lane quarter: each takes 32 of a tile's 128 columns
+constexpr int STREAM_COL_PARTS = STREAM_EPI_WARPS / 4;   // column parts per tile
+constexpr int STREAM_THREADS = 64 + 32 * STREAM_EPI_WARPS;
+constexpr float LOG2E = 1.4426950408889634f;
 
 struct RowTop {
   float v[KTOP];
@@ -319,7 +334,7 @@ __device__ __forceinline__ void top_insert(RowTop& t, int K, float z, int n) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
     hpd_stream_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const float* __restrict__ bias, int U, int T, int Kdim, int topk, int n_split,
                           float* __restrict__ part_max, float* __restrict__ part_sum, float* __restrict__ part_topv,
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull + s, 1);
-      mbar_init(tempty + s, 4);
+      mbar_init(tempty + s, STREAM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -442,14 +457,20 @@ __global__ void __launch_bounds__(THREADS, 1)
         umma_commit(a_empty);  // every MMA that reads the resident A tile has completed
       }
     }
-  } else {  // ---- epilogue warps 2..5: thread = lattice node (row) ----
-    const int q = warp & 3;
+  } else {  // ---- epilogue warps 2..17: thread = (lattice node, 32-column part of every tile) ----
+    // Sixteen warps, four per scheduler, so that the dependent chains of the online softmax overlap: with a single
+    // epilogue warp per scheduler the epilogue took 7.5 k cycles per tile against 3.1 k for the MMAs (tensor pipe
+    // 41 % active); with two per scheduler 5.4 k (57 %).
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2;        // which 32 of the tile's 128 columns
+    const int n_parts = STREAM_COL_PARTS * n_split;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int m0 = (w / n_split) * BM, sp = w % n_split;
       const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
-      float m = -INFINITY, ssum = 0.0f, comp = 0.0f;
+      // running statistics in the base-2 domain: m2 = max(z) * log2(e), ssum = sum 2^(z*log2e - m2)
+      float m2 = -INFINITY, ssum = 0.0f, comp = 0.0f;
       RowTop top;
 #pragma unroll
       for (int k = 0; k < KTOP; ++k) {
@@ -457,32 +478,44 @@ __global__ void __launch_bounds__(THREADS, 1)
         top.i[k] = 0x7fffffff;
       }
       for (int nt = nt0; nt < nt1; ++nt) {
-        const int n0 = nt * BN;
+        const int n0 = nt * BN + part * 32;
         mbar_wait(tfull + acc, acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + part * 32;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
           const int nb = n0 + c0;
           if (nb >= T) continue;
-          float z[32];
+          float z[16];
           float cmax = -INFINITY;
+          if (nb + 16 <= T) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + nb);   // nb is a multiple of 16
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            z[j] = (nb + j < T) ? __uint_as_float(v[j]) + __ldg(bias + nb + j) : -INFINITY;
-            cmax = fmaxf(cmax, z[j]);
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bb = __ldg(b4 + j / 4);
+              z[j + 0] = __uint_as_float(v[j + 0]) + bb.x;
+              z[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+              z[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+              z[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = (nb + j < T) ? __uint_as_float(v[j]) + __ldg(bias + nb + j) : -INFINITY;
           }
-          if (cmax > m) {  // rescale the running sum to the new maximum
-            const float sc = expf(m - cmax);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cmax = fmaxf(cmax, z[j]);
+          const float cmax2 = cmax * LOG2E;
+          if (cmax2 > m2) {  // rescale the running sum to the new maximum
+            const float sc = exp2f(m2 - cmax2);
             ssum *= sc;
             comp *= sc;
-            m = cmax;
+            m2 = cmax2;
           }
           float csum = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) csum += expf(z[j] - m);
+          for (int j = 0; j < 16; ++j) csum += exp2f(fmaf(z[j], LOG2E, -m2));   // one FFMA + MUFU.EX2 per element
           {  // compensated accumulation of the chunk sums (rows are up to 2^22 columns long)
             const float y = csum - comp;
             const float tsum = ssum + y;
@@ -491,7 +524,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
           if (cmax > top.v[KTOP - 1]) {  // (a sorted top-KTOP is kept whatever K is; its head is the top-K)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 16; ++j)
               if (z[j] > top.v[KTOP - 1]) top_insert(top, KTOP, z[j], nb + j);
           }
         }
@@ -505,8 +538,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       const int row = m0 + q * 32 + lane;
       if (row < U) {
-        const int64_t o = static_cast<int64_t>(row) * n_split + sp;
-        part_max[o] = m;
+        const int64_t o = static_cast<int64_t>(row) * n_parts + sp * STREAM_COL_PARTS + part;
+        part_max[o] = m2;          // base-2 domain (see merge kernel)
         part_sum[o] = ssum;
 #pragma unroll
         for (int k = 0; k < KTOP; ++k) {
@@ -527,16 +560,34 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-// merges the column splits of one row: global max / normaliser, top-K of the logits, p = exp(z - max) / sum
+// insert (z, n) keeping (value desc, index asc) order for candidates that arrive in any index order
+__device__ __forceinline__ void top_insert_any(RowTop& t, float z, int n) {
+  float cz = z;
+  int ci = n;
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    const bool sw = (cz > t.v[k]) || (cz == t.v[k] && ci < t.i[k]);
+    const float tz = t.v[k];
+    const int tn = t.i[k];
+    t.v[k] = sw ? cz : tz;
+    t.i[k] = sw ? ci : tn;
+    cz = sw ? tz : cz;
+    ci = sw ? tn : ci;
+  }
+}
+
+// merges the partial results of one row (n_parts = column splits x 4 column parts of every tile): global max / normaliser,
+// top-K of the logits, p = exp(z - max) / sum.  The partial statistics are in the base-2 domain
+// (m2 = max * log2 e, sum of 2^(z log2 e - m2)); the winners' probabilities use the accurate expf.
 __global__ void __launch_bounds__(128)
     hpd_stream_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
-                            const float* __restrict__ part_topv, const int* __restrict__ part_topi, int U, int n_split,
+                            const float* __restrict__ part_topv, const int* __restrict__ part_topi, int U, int n_parts,
                             int topk, float* __restrict__ row_max, float* __restrict__ row_sum,
                             float* __restrict__ utopv, int* __restrict__ utopi) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= U) return;
-  float M = -INFINITY;
-  for (int s = 0; s < n_split; ++s) M = fmaxf(M, part_max[static_cast<int64_t>(row) * n_split + s]);
+  float M2 = -INFINITY;
+  for (int s = 0; s < n_parts; ++s) M2 = fmaxf(M2, part_max[static_cast<int64_t>(row) * n_parts + s]);
   float S = 0.0f;
   RowTop top;
 #pragma unroll
@@ -544,15 +595,18 @@ __global__ void __launch_bounds__(128)
     top.v[k] = -INFINITY;
     top.i[k] = 0x7fffffff;
   }
-  for (int s = 0; s < n_split; ++s) {  // splits cover increasing column ranges: candidates arrive in index order
-    const int64_t o = static_cast<int64_t>(row) * n_split + s;
+  for (int s = 0; s < n_parts; ++s) {
+    const int64_t o = static_cast<int64_t>(row) * n_parts + s;
     const float pm = part_max[o];
-    if (pm > -INFINITY) S += part_sum[o] * expf(pm - M);
+    if (pm > -INFINITY) S += part_sum[o] * exp2f(pm - M2);
     for (int k = 0; k < topk; ++k) {
       const float z = part_topv[o * topk + k];
-      if (z > top.v[KTOP - 1]) top_insert(top, KTOP, z, part_topi[o * topk + k]);
+      if (z >= top.v[KTOP - 1]) top_insert_any(top, z, part_topi[o * topk + k]);
     }
   }
+  const float M = top.v[0];                      // the row maximum itself (M2 == M * log2 e up to rounding)
+  // normaliser relative to M: S is relative to 2^M2, so rescale by 2^(M2 - M log2 e) (== 1 up to rounding)
+  S *= exp2f(M2 - M * LOG2E);
   if (row_max) row_max[row] = M;
   if (row_sum) row_sum[row] = S;
 #pragma unroll
@@ -697,7 +751,7 @@ int64_t gngf_hpd_stream_workspace_floats(int64_t U, int64_t T, int32_t topk) {
   using namespace gngf::tc;
   const int64_t row_tiles = gngf::ceil_div(U, BM), col_tiles = gngf::ceil_div(T, BN);
   int64_t n_split = std::max<int64_t>(1, std::min<int64_t>(col_tiles, (2 * gngf::sm_count()) / row_tiles));
-  return U * n_split * (2 + 2 * static_cast<int64_t>(topk)) + 1;
+  return U * (STREAM_COL_PARTS * n_split) * (2 + 2 * static_cast<int64_t>(topk)) + 1;
 }
 
 int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t U, int64_t T,
@@ -715,23 +769,25 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
   const int64_t row_tiles = gngf::ceil_div(U, BM), col_tiles = gngf::ceil_div(T, BN);
   const int n_split =
       static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(col_tiles, (2 * gngf::sm_count()) / row_tiles)));
+  const int64_t n_parts = static_cast<int64_t>(STREAM_COL_PARTS) * n_split;
   float* part_max = workspace;
-  float* part_sum = part_max + U * n_split;
-  float* part_topv = part_sum + U * n_split;
-  int* part_topi = reinterpret_cast<int*>(part_topv + U * n_split * topk);
+  float* part_sum = part_max + U * n_parts;
+  float* part_topv = part_sum + U * n_parts;
+  int* part_topi = reinterpret_cast<int*>(part_topv + U * n_parts * topk);
   cudaStream_t st = gngf::as_stream(stream);
   if (cudaFuncSetAttribute(hpd_stream_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(STREAM_SMEM_BYTES)) != cudaSuccess)
     return gngf::check_launch();
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
-  hpd_stream_fwd_kernel<<<grid, THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
+  hpd_stream_fwd_kernel<<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
                                                                   static_cast<int>(T), static_cast<int>(Kdim), topk,
                                                                   n_split, part_max, part_sum, part_topv, part_topi);
   gngf::note_launch();
   rc = gngf::check_launch();
   if (rc) return rc;
   hpd_stream_merge_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 128)), 128, 0, st>>>(
-      part_max, part_sum, part_topv, part_topi, static_cast<int>(U), n_split, topk, row_max, row_sum, utopv, utopi);
+      part_max, part_sum, part_topv, part_topi, static_cast<int>(U), static_cast<int>(n_parts), topk, row_max, row_sum,
+      utopv, utopi);
   gngf::note_launch();
   return gngf::check_launch();
 }
