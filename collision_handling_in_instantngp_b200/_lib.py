@@ -71,6 +71,11 @@ SIGNATURES = {
     "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "gngf_hpd_stream_workspace_floats": (c_int64, [c_int64, c_int64, c_int32]),
     "gngf_hpd_stream_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
+    "gngf_hpd_small_supported": (c_int, [c_int32, POINTER(c_int32), c_int32]),
+    "gngf_hpd_small_fwd": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
+                                   POINTER(c_void_p), c_int32, _P, _P, _P, _P]),
+    "gngf_hpd_small_bwd": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
+                                   POINTER(c_void_p), POINTER(c_void_p), _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_mlp3_supported": (c_int, [c_int32, c_int32, c_int32, c_int32]),
     "gngf_mlp3_fwd": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_mlp3_bwd_workspace_floats": (c_int64, [c_int32, c_int32]),
@@ -139,6 +144,18 @@ def call(name: str, *args) -> None:
 
 def launch_count() -> int:
     return int(load().gngf_launch_count())
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (for the `const float* const*` parameters)."""
+    arr = (c_void_p * max(1, len(tensors)))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def int_array(values):
+    return (c_int32 * len(values))(*[int(v) for v in values])
 
 
 def make_tables(tensors) -> Tables:

@@ -1,0 +1,403 @@
+// K2/K3/K5b/K5c for SMALL lattices, fused: when the HPD sees only a few hundred to a few thousand nodes (782 at the
+// published configuration) its whole forward is ~70 MFLOP -- as a chain of separate GEMM / softmax / top-k launches
+// it is pure launch latency (18 launches, ~120 us of a 320 us step).  Here one CTA owns NB = 8 nodes and walks
+//   forward : layer 0 from the node coordinates, hidden layers, output layer, softmax + nan_to_num, top-k
+//   backward: dlogits (softmax / top-k / column-sum adjoint, see k3_topk.cu), then dX through the layers with the
+//             ReLU masks, bias gradients and the first layer's gradients by atomics
+// with activations in shared memory and the weights streamed from L2 (coalesced: a warp reads one weight row).
+// The weight gradients dW_i = g_i^T h_{i-1} reduce over all nodes and stay with the generic split-K layer kernel.
+// Limits: <= 6 layers, hidden widths <= 256, T <= 1024, K <= 128; anything else takes the general path.
+#include <algorithm>
+
+#include "topk_common.cuh"
+
+namespace gngf {
+
+constexpr int NB = 8;          // nodes per CTA
+constexpr int SM_MAXW = 256;   // widest hidden layer
+constexpr int SM_MAXT = 1024;  // widest output layer
+constexpr int SM_MAXL = 6;
+constexpr int SM_THREADS = 256;
+
+struct HpdNet {
+  int n_layers;                 // linear layers, >= 2
+  int width[SM_MAXL + 1];       // width[0] = 2, ..., width[n_layers] = T
+  const float* w[SM_MAXL];      // (width[i+1], width[i]) row-major
+  const float* b[SM_MAXL];
+  float* act[SM_MAXL];          // act[i] (U, width[i+1]) outputs of hidden layers i < n_layers-1 (global, saved)
+  float* gact[SM_MAXL];         // backward: g[i] (U, width[i+1]) adjoint of layer i's pre-activation (global)
+  float* dbias[SM_MAXL];        // backward: bias gradients (+=)
+  float* dw0;                   // backward: first layer weight gradient (+=)
+};
+
+// 8 partial sums (one per node) x 32 lanes -> each 4-lane group ends with one node's total
+__device__ __forceinline__ float reduce_scatter8(const float (&acc)[NB], int lane, int& node_of_lane) {
+  const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+  float a4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = hi16 ? acc[i] : acc[i + 4];
+    const float keep = hi16 ? acc[i + 4] : acc[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float a2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = hi8 ? a4[i] : a4[i + 2];
+    const float keep = hi8 ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float a1;
+  {
+    const float send = hi4 ? a2[0] : a2[1];
+    const float keep = hi4 ? a2[1] : a2[0];
+    a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  node_of_lane = (hi16 ? 4 : 0) + (hi8 ? 2 : 0) + (hi4 ? 1 : 0);
+  return a1;
+}
+
+// One layer for the CTA's NB nodes: dst[n][j] = act(sum_k in[n][k] W[j][k] + b[j]).  A warp takes JB = 4 outputs at
+// a time; the lanes stride k (a weight row is read coalesced) and all JB * CH weight loads of a step are issued
+// before the first use, so one L2 round trip covers four outputs.  CH = ceil(K / 32) <= 8.
+template <int CH>
+__device__ __forceinline__ void small_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int N,
+                                            const float* in /*[NB][SM_MAXW]*/, float* dst, int ldd, bool relu,
+                                            float* gsave, int64_t u0, int64_t U, int warp, int lane) {
+  constexpr int JB = 4;
+  float xin[NB][CH];
+#pragma unroll
+  for (int n = 0; n < NB; ++n)
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = lane + 32 * c;
+      xin[n][c] = k < K ? in[n * SM_MAXW + k] : 0.0f;
+    }
+  for (int j0 = warp * JB; j0 < N; j0 += (SM_THREADS / 32) * JB) {
+    float wv[JB][CH];
+#pragma unroll
+    for (int jb = 0; jb < JB; ++jb)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int k = lane + 32 * c;
+        wv[jb][c] = (j0 + jb < N && k < K) ? __ldg(W + static_cast<int64_t>(j0 + jb) * K + k) : 0.0f;
+      }
+#pragma unroll
+    for (int jb = 0; jb < JB; ++jb) {
+      float acc[NB];
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        float a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) a = fmaf(wv[jb][c], xin[n][c], a);
+        acc[n] = a;
+      }
+      int node;
+      const float s = reduce_scatter8(acc, lane, node);
+      const int j = j0 + jb;
+      if ((lane & 3) == 0 && j < N) {
+        float v = s + bias[j];
+        if (relu) v = fmaxf(v, 0.0f);
+        dst[node * ldd + j] = v;
+        if (gsave && u0 + node < U) gsave[(u0 + node) * N + j] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SM_THREADS)
+    hpd_small_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net, int K,
+                         float* __restrict__ uprobs, float* __restrict__ utopv, int32_t* __restrict__ utopi) {
+  extern __shared__ float sm[];
+  float* bufA = sm;                       // [NB][SM_MAXW]
+  float* bufB = sm + NB * SM_MAXW;        // [NB][SM_MAXW]
+  float* logits = sm + 2 * NB * SM_MAXW;  // [NB][T]
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int nl = net.n_layers, T = net.width[nl];
+
+  // layer 0 from the node coordinates (models.py:416: the HPD input is the integer corner)
+  {
+    const int N0 = net.width[1];
+    const float2* w0 = reinterpret_cast<const float2*>(net.w[0]);
+    for (int e = tid; e < NB * N0; e += SM_THREADS) {
+      const int n = e / N0, j = e % N0;
+      const int64_t u = min(u0 + n, U - 1);
+      const float cx = static_cast<float>(lat.ox + static_cast<int>(u / lat.wy));
+      const float cy = static_cast<float>(lat.oy + static_cast<int>(u % lat.wy));
+      const float2 w = w0[j];
+      float v = fmaf(cy, w.y, fmaf(cx, w.x, net.b[0][j]));
+      v = fmaxf(v, 0.0f);
+      bufA[n * SM_MAXW + j] = v;
+      if (u0 + n < U) net.act[0][(u0 + n) * N0 + j] = v;
+    }
+  }
+  __syncthreads();
+  float* in = bufA;
+  float* out = bufB;
+  for (int i = 1; i < nl; ++i) {
+    const int Kd = net.width[i], N = net.width[i + 1];
+    const bool last = i == nl - 1;
+    float* dst = last ? logits : out;
+    const int ldd = last ? T : SM_MAXW;
+    float* gsave = last ? nullptr : net.act[i];
+    const int ch = (Kd + 31) / 32;
+    if (ch <= 1) small_layer<1>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
+    else if (ch <= 2) small_layer<2>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
+    else if (ch <= 4) small_layer<4>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
+    else small_layer<8>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
+    __syncthreads();
+    if (!last) {
+      float* t = in;
+      in = out;
+      out = t;
+    }
+  }
+  // softmax + nan_to_num + top-k: warp n owns node n (NB == number of warps)
+  {
+    const int n = warp;
+    const int64_t u = u0 + n;
+    if (u < U) {
+      float* z = logits + n * T;
+      float m = -INFINITY;
+      for (int t = lane; t < T; t += 32) m = fmaxf(m, z[t]);
+      m = warp_max(m);
+      float ssum = 0.0f;
+      for (int t = lane; t < T; t += 32) {
+        const float e = expf(z[t] - m);
+        z[t] = e;
+        ssum += e;
+      }
+      ssum = warp_sum(ssum);
+      for (int t = lane; t < T; t += 32) {
+        float p = z[t] / ssum;
+        if (p != p) p = 0.0f;
+        z[t] = p;
+        uprobs[u * T + t] = p;
+      }
+      __syncwarp();
+      select_topk<int32_t>(z, T, K, lane, utopv + u * K, utopi + u * K);
+    }
+  }
+}
+
+// backward over NB nodes per CTA.  gT buffers are stored transposed ([width][NB]) so that a thread reads the NB
+// adjoints of one unit with two 16-byte loads.
+__global__ void __launch_bounds__(SM_THREADS)
+    hpd_small_bwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net, int K,
+                         const float* __restrict__ uprobs, const int32_t* __restrict__ utopi,
+                         const float* __restrict__ dtv, const int32_t* __restrict__ cnt,
+                         const float* __restrict__ gcol, const float* __restrict__ gcol_k,
+                         const float* __restrict__ gdense) {
+  extern __shared__ float sm[];
+  const int nl = net.n_layers, T = net.width[nl];
+  float* gT = sm;                         // [max(T, SM_MAXW)][NB] adjoint of the current layer's pre-activation
+  float* gN = sm + SM_MAXT * NB;          // [SM_MAXW][NB] next (lower) layer's adjoint
+  float* part = gN + SM_MAXW * NB;        // [2][SM_MAXW][NB] partial sums of the two j-halves
+  __shared__ float cl_s[NB][GNGF_MAX_LEVELS];
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int L = lat.num_levels;
+
+  // ---- dlogits of node (u0 + warp): same arithmetic as hpd_dlogits_kernel ----
+  {
+    const int n = warp;
+    const int64_t u = u0 + n;
+    if (u < U) {
+      const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
+      float* cl = cl_s[n];
+      if (lane < L) {
+        float c = 0.0f;
+        if (cnt) {
+          const int i = cx - lat.lox[lane], j = cy - lat.loy[lane];
+          if (i >= 0 && i < lat.lwx[lane] && j >= 0 && j < lat.lwy[lane])
+            c = static_cast<float>(cnt[lat.loff[lane] + static_cast<int64_t>(i) * lat.lwy[lane] + j]);
+        }
+        cl[lane] = c;
+      }
+      __syncwarp();
+      const float* p = uprobs + u * T;
+      const float* gd = gdense ? gdense + u * T : nullptr;
+      float dot = 0.0f;
+      for (int k = lane; k < K; k += 32) {
+        float g = dtv[u * K + k];
+        if (gcol_k)
+          for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
+        dot = fmaf(g, p[utopi[u * K + k]], dot);
+      }
+      if (gcol || gd) {
+        for (int t = lane; t < T; t += 32) {
+          float g = gd ? gd[t] : 0.0f;
+          if (gcol)
+            for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
+          dot = fmaf(g, p[t], dot);
+        }
+      }
+      dot = warp_sum(dot);
+      for (int t = lane; t < T; t += 32) {
+        float g = gd ? gd[t] : 0.0f;
+        if (gcol)
+          for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol[l * T + t], g);
+        gT[t * NB + n] = p[t] * (g - dot);
+      }
+      __syncwarp();
+      for (int k = lane; k < K; k += 32) {
+        float g = dtv[u * K + k];
+        if (gcol_k)
+          for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
+        const int t = utopi[u * K + k];
+        gT[t * NB + n] += p[t] * g;
+      }
+    } else {
+      for (int t = lane; t < T; t += 32) gT[t * NB + n] = 0.0f;
+    }
+  }
+  __syncthreads();
+
+  // ---- walk down the layers: store g_i, bias gradient, dX with the ReLU mask ----
+  for (int i = nl - 1; i >= 0; --i) {
+    const int N = net.width[i + 1], Kd = net.width[i];
+    // g_i to global (the weight-gradient GEMM reads it) + bias gradient
+    for (int e = tid; e < N * NB; e += SM_THREADS) {
+      const int j = e / NB, n = e % NB;
+      if (u0 + n < U) net.gact[i][(u0 + n) * N + j] = gT[e];
+    }
+    for (int j = tid; j < N; j += SM_THREADS) {
+      const float4 a = *reinterpret_cast<const float4*>(gT + j * NB);
+      const float4 b = *reinterpret_cast<const float4*>(gT + j * NB + 4);
+      atomicAdd(net.dbias[i] + j, ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)));
+    }
+    if (i == 0) {
+      // first layer: dw0[j] += sum_n g0[n][j] * (cx_n, cy_n)
+      for (int j = tid; j < N; j += SM_THREADS) {
+        float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+          const int64_t u = min(u0 + n, U - 1);
+          const float g = gT[j * NB + n];   // zero for padded nodes
+          sx = fmaf(g, static_cast<float>(lat.ox + static_cast<int>(u / lat.wy)), sx);
+          sy = fmaf(g, static_cast<float>(lat.oy + static_cast<int>(u % lat.wy)), sy);
+        }
+        atomicAdd(net.dw0 + j * 2 + 0, sx);
+        atomicAdd(net.dw0 + j * 2 + 1, sy);
+      }
+      break;
+    }
+    // dX[n][k] = sum_j g_i[n][j] * W_i[j][k]; thread = (k, half of the j range); coalesced weight rows
+    {
+      const int k = tid % SM_MAXW >= Kd ? -1 : tid % SM_MAXW;   // Kd <= 256 == SM_THREADS: one k per thread ...
+      const int halves = Kd <= SM_THREADS / 2 ? 2 : 1;          // ... and two j-halves when Kd <= 128
+      const int kk = halves == 2 ? tid % (SM_THREADS / 2) : tid;
+      const int hf = halves == 2 ? tid / (SM_THREADS / 2) : 0;
+      (void)k;
+      float acc[NB];
+#pragma unroll
+      for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
+      if (kk < Kd) {
+        const int j0 = hf * (N / halves), j1 = (hf == halves - 1) ? N : j0 + N / halves;
+        const float* wcol = net.w[i] + kk;
+#pragma unroll 8
+        for (int j = j0; j < j1; ++j) {
+          const float w = __ldg(wcol + static_cast<int64_t>(j) * Kd);
+          const float4 a = *reinterpret_cast<const float4*>(gT + j * NB);
+          const float4 b = *reinterpret_cast<const float4*>(gT + j * NB + 4);
+          acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+          acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+          acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]);
+          acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n) part[(hf * SM_MAXW + kk) * NB + n] = acc[n];
+      }
+      __syncthreads();
+      // combine the halves, apply the ReLU mask of h_{i-1} (saved forward activation), -> gN
+      for (int e = tid; e < Kd * NB; e += SM_THREADS) {
+        const int k2 = e / NB, n = e % NB;
+        float v = part[e];
+        if (halves == 2) v += part[SM_MAXW * NB + e];
+        const int64_t u = u0 + n;
+        const float h = (u < U) ? net.act[i - 1][u * Kd + k2] : 0.0f;
+        gN[e] = h > 0.0f ? v : 0.0f;
+      }
+      __syncthreads();
+      for (int e = tid; e < Kd * NB; e += SM_THREADS) gT[e] = gN[e];
+      __syncthreads();
+    }
+  }
+}
+
+static size_t small_fwd_smem(int T) { return sizeof(float) * (2 * NB * SM_MAXW + NB * T); }
+static size_t small_bwd_smem() { return sizeof(float) * (SM_MAXT * NB + SM_MAXW * NB + 2 * SM_MAXW * NB); }
+
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_hpd_small_supported(int32_t n_layers, const int32_t* widths, int32_t topk) {
+  if (n_layers < 2 || n_layers > gngf::SM_MAXL || widths[0] != 2 || topk < 1 || topk > GNGF_MAX_TOPK) return 0;
+  for (int i = 1; i < n_layers; ++i)
+    if (widths[i] < 1 || widths[i] > gngf::SM_MAXW) return 0;
+  return widths[n_layers] >= topk && widths[n_layers] <= gngf::SM_MAXT;
+}
+
+// w / b / act: arrays of n_layers device pointers (act: n_layers - 1 hidden outputs, (U, width))
+int gngf_hpd_small_fwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                       const float* const* b, float* const* act, int32_t topk, float* uprobs, float* utopv,
+                       int32_t* utopi, void* stream) {
+  if (!gngf_hpd_small_supported(n_layers, widths, topk)) return GNGF_ERR_UNSUPPORTED;
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  if (U <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::HpdNet net{};
+  net.n_layers = n_layers;
+  for (int i = 0; i <= n_layers; ++i) net.width[i] = widths[i];
+  for (int i = 0; i < n_layers; ++i) {
+    net.w[i] = w[i];
+    net.b[i] = b[i];
+    net.act[i] = i < n_layers - 1 ? act[i] : nullptr;
+  }
+  const size_t smem = gngf::small_fwd_smem(widths[n_layers]);
+  if (cudaFuncSetAttribute(gngf::hpd_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem)) != cudaSuccess)
+    return gngf::check_launch();
+  gngf::hpd_small_fwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::NB)), gngf::SM_THREADS, smem,
+                               gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopv, utopi);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+// gact: n_layers outputs (U, width[i+1]) receiving the pre-activation adjoints; dbias: n_layers bias gradients (+=);
+// dw0 (width[1], 2) (+=).  The weight gradients of layers >= 1 are dW_i += gact[i]^T act[i-1] (gngf_linear_bwd).
+int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                       float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
+                       const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                       const float* gcol, const float* gcol_k, const float* gdense, void* stream) {
+  if (!gngf_hpd_small_supported(n_layers, widths, topk)) return GNGF_ERR_UNSUPPORTED;
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  if (U <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if ((gcol || gcol_k) && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::HpdNet net{};
+  net.n_layers = n_layers;
+  for (int i = 0; i <= n_layers; ++i) net.width[i] = widths[i];
+  for (int i = 0; i < n_layers; ++i) {
+    net.w[i] = w[i];
+    net.act[i] = i < n_layers - 1 ? act[i] : nullptr;
+    net.gact[i] = gact[i];
+    net.dbias[i] = dbias[i];
+  }
+  net.dw0 = dw0;
+  const size_t smem = gngf::small_bwd_smem();
+  if (cudaFuncSetAttribute(gngf::hpd_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(smem)) != cudaSuccess)
+    return gngf::check_launch();
+  gngf::hpd_small_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::NB)), gngf::SM_THREADS, smem,
+                               gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopi, dtv, cnt, gcol, gcol_k,
+                                                          gdense);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

@@ -30,9 +30,10 @@ constexpr int UMMA_K = 16;
 constexpr uint32_t PLANE_BYTES = BM * BK * 2;                         // 16 KB (BM == BN)
 constexpr uint32_t STAGE_BYTES = 2 * PLANES * PLANE_BYTES;            // 96 KB: A planes then B planes
 constexpr uint32_t TMEM_COLS = 2 * BN;                                // two accumulators
-constexpr int THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                                     // two per TMEM lane quarter / scheduler
+constexpr int THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr uint32_t EPI_LD = 33;                                        // padded row of the epilogue staging tile
-constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_LD * 4;                    // one 32x32 fp32 tile per epilogue warp
+constexpr uint32_t EPI_BYTES = GEMM_EPI_WARPS * 32 * EPI_LD * 4;       // one 32x32 fp32 tile per epilogue warp
 constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull + s, 1);
-      mbar_init(tempty + s, 4);
+      mbar_init(tempty + s, GEMM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -236,8 +237,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
     }
-  } else {  // ---- epilogue warps 2..5 ----
+  } else {  // ---- epilogue warps 2..9: (TMEM lane quarter, column half of the tile) ----
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       float* stage_tile = epi + (warp - 2) * 32 * EPI_LD;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         // thread = accumulator row (TMEM lane); transpose through shared memory so that a warp stores
         // 32 consecutive floats (one 128-byte line) of one output row per instruction
         uint32_t v[32];

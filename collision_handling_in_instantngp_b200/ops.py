@@ -243,6 +243,7 @@ class ForwardState:
     row_max: Optional[torch.Tensor] = None                       # (U,) softmax statistics (streaming path)
     row_sum: Optional[torch.Tensor] = None
     w_planes: Optional[torch.Tensor] = None                      # (3,T,Kd) bf16 planes of the output layer
+    hpd_small: bool = False                                      # fused small-lattice HPD kernels were used
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
     cnt: Optional[torch.Tensor] = None                           # (S,) int32
@@ -274,6 +275,16 @@ def _streaming_ok(cfg, U, T, k, kd) -> bool:
     return U * T >= STREAM_MIN_ELEMENTS
 
 
+SMALL_LATTICE_MAX_NODES = 8192    # fused per-node HPD kernels (k2_hpd_small.cu) below this many nodes
+
+
+def _hpd_small_ok(hpd_w, U, k) -> bool:
+    if U > SMALL_LATTICE_MAX_NODES or len(hpd_w) < 2:
+        return False
+    widths = [hpd_w[0].shape[1]] + [w.shape[0] for w in hpd_w]
+    return bool(_lib.load().gngf_hpd_small_supported(len(hpd_w), _lib.int_array(widths), k))
+
+
 def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
     """HashProbDistribution.forward (models.py:90-123) on every lattice node.  Fills state.hpd_acts and
     state.utopv / utopi (U,K); state.uprobs (U,T) on the dense path, state.row_max / row_sum (U) on the
@@ -283,6 +294,18 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
     n = len(hpd_w)
     if hpd_w[0].shape[1] != 2:
         raise GngfError("the HPD input must be 2-D grid-corner coordinates")
+    state.hpd_small = (not _streaming_ok(cfg, U, T, k, hpd_w[-1].shape[1])) and _hpd_small_ok(hpd_w, U, k)
+    if state.hpd_small:
+        # one launch: all layers + softmax + top-k, 8 nodes per CTA
+        widths = [2] + [w.shape[0] for w in hpd_w]
+        state.hpd_acts = [torch.empty((U, w.shape[0]), dtype=torch.float32, device=device) for w in hpd_w[:-1]]
+        state.uprobs = torch.empty((U, T), dtype=torch.float32, device=device)
+        state.utopv = torch.empty((U, k), dtype=torch.float32, device=device)
+        state.utopi = torch.empty((U, k), dtype=torch.int32, device=device)
+        call("gngf_hpd_small_fwd", lat, n, _lib.int_array(widths), _lib.ptr_array(hpd_w), _lib.ptr_array(hpd_b),
+             _lib.ptr_array(state.hpd_acts), k, state.uprobs.data_ptr(), state.utopv.data_ptr(),
+             state.utopi.data_ptr(), _stream())
+        return
     acts = []
     h = torch.empty((U, hpd_w[0].shape[0]), dtype=torch.float32, device=device)
     call("gngf_hpd_first_layer_fwd", lat, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(), hpd_w[0].shape[0],
@@ -466,6 +489,21 @@ class GNGFPath(torch.autograd.Function):
                 dtv.add_(grad_uvals.reshape(-1))
             else:
                 gdense = grad_uvals
+        if state.hpd_small:
+            # one launch: dlogits, dX chain with ReLU masks, bias and first-layer gradients; then the weight
+            # gradients dW_i += g_i^T h_{i-1} (reductions over all nodes) as split-K layer kernels
+            widths = [2] + [w.shape[0] for w in hpd_w]
+            gacts = [torch.empty((U, w.shape[0]), dtype=torch.float32, device=dev) for w in hpd_w]
+            call("gngf_hpd_small_bwd", lat, nh, _lib.int_array(widths), _lib.ptr_array(hpd_w),
+                 _lib.ptr_array(state.hpd_acts), _lib.ptr_array(gacts), _lib.ptr_array(g_hpd_b), g_hpd_w[0].data_ptr(), K,
+                 state.uprobs.data_ptr(), state.utopi.data_ptr(), dtv.data_ptr(), state.cnt.data_ptr(), _ptr(gcol),
+                 _ptr(gcol_k), _ptr(gdense), st)
+            for i in range(1, nh):
+                call("gngf_linear_bwd", gacts[i].data_ptr(), state.hpd_acts[i - 1].data_ptr(), hpd_w[i].data_ptr(), U,
+                     hpd_w[i].shape[0], hpd_w[i].shape[1], ACT_NONE, None, g_hpd_w[i].data_ptr(), None, st)
+            if GRAD_REDUCE_HOOK is not None:
+                GRAD_REDUCE_HOOK(flat)
+            return (None, None, *grads)
         if nh == 1:
             dlogits = torch.empty((U, T), dtype=torch.float32, device=dev)
             call("gngf_hpd_dlogits", lat, state.uprobs.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),

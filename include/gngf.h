@@ -127,6 +127,21 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
                         int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max, float* row_sum,
                         float* workspace, void* stream);
 
+/* ---- K2/K3/K5 fused for small lattices (a few hundred to a few thousand nodes, T <= 1024, hidden widths <= 256) ----
+ * One CTA per 8 nodes walks the whole HPD (models.py:80-123): layer 0 from the node coordinates, hidden layers,
+ * output layer, softmax + nan_to_num, top-k; the backward computes dlogits (as gngf_hpd_dlogits), the bias
+ * gradients, the first layer's gradients and the pre-activation adjoints gact[i] (U, width[i+1]) of every layer;
+ * the weight gradients of layers i >= 1 are dW_i += gact[i]^T act[i-1] (gngf_linear_bwd with dx = db = NULL).
+ * widths: n_layers + 1 entries (2, hidden..., T); w / b / act / gact / dbias: host arrays of device pointers.     */
+int gngf_hpd_small_supported(int32_t n_layers, const int32_t* widths, int32_t topk);
+int gngf_hpd_small_fwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                       const float* const* b, float* const* act, int32_t topk, float* uprobs, float* utopv,
+                       int32_t* utopi, void* stream);
+int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                       float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
+                       const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                       const float* gcol, const float* gcol_k, const float* gdense, void* stream);
+
 /* ---- K6: fused decoder MLP (models.py:382-392, 468-470) for the reference's shape IN -> 64 -> 64 -> OUT -----
  * rgb (P,OUT) = sigmoid(W2 act(W1 act(W0 enc + b0) + b1) + b2), act = ReLU or LeakyReLU(0.01); activations stay
  * in shared memory.  The backward recomputes them, writes denc (P,IN) and ADDS the parameter gradients into

@@ -209,3 +209,24 @@ def test_calc_hash_collisions_matches_reference(name):
         coll_j, _ = net.calc_hash_collisions(junk)
         ref, _ = O.calc_hash_collisions(junk.cpu().numpy(), g["n_ls"], g["cfg"]["T"])
         np.testing.assert_allclose(coll_j.cpu().numpy(), ref, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "k20", "mix_raw"])
+def test_fused_small_lattice_hpd_equals_general_path(name):
+    """k2_hpd_small.cu (one CTA per 8 nodes, whole HPD forward / backward) against the layer-by-layer path."""
+    from collision_handling_in_instantngp_b200 import ops
+    g = load(name)
+    net = build_net(g)
+    out_small = run_step(net, g)
+    assert out_small["state"].hpd_small
+    saved = ops.SMALL_LATTICE_MAX_NODES
+    ops.SMALL_LATTICE_MAX_NODES = 0
+    try:
+        out_gen = run_step(net, g)
+    finally:
+        ops.SMALL_LATTICE_MAX_NODES = saved
+    assert not out_gen["state"].hpd_small
+    assert np.array_equal(out_small["idx"], out_gen["idx"])
+    assert rel_err(out_small["rgb"], out_gen["rgb"]) < 1e-6
+    for k in out_gen["grads"]:
+        assert rel_err(out_small["grads"][k], out_gen["grads"][k]) < 2e-5, k
