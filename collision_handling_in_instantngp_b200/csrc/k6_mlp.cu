@@ -1,11 +1,13 @@
 // K6: the decoder MLP  enc (P, IN) -> 64 -> 64 -> OUT (3 or 1), ReLU/LeakyReLU hidden, sigmoid output
 // (models.py:382-392, 468-470) fused into one forward kernel and one backward kernel for the reference's
-// shape (two hidden layers of 64).  Activations never leave the SM: a CTA takes tiles of 128 points, keeps
-// them k-major in shared memory ([feature][point], row stride 132 floats so that float4 accesses of a quarter
-// warp hit distinct banks), runs each layer as a register-tiled fp32 GEMM (true fp32 FMA = the reference's
-// cuBLAS SGEMM arithmetic), and the backward recomputes the hidden activations instead of reading them back.
-// Weight gradients are accumulated in registers across all tiles of a (persistent) CTA, written once per CTA
-// to a partials buffer and summed by a second tiny kernel -- no atomics.
+// shape (two hidden layers of 64).  Activations never leave the SM: a CTA of 128 threads takes tiles of 128
+// points, keeps them k-major in shared memory ([feature][point], row stride 132 floats so that float4 accesses of
+// a quarter warp hit distinct banks) and runs each layer as a register-tiled fp32 GEMM (true fp32 FMA = the
+// reference's cuBLAS SGEMM arithmetic).  The thread tile is 8 points x 8 outputs: 4 shared-memory vector loads feed
+// 64 FMAs, which keeps the kernel FMA-bound rather than shared-memory-bound (a 4x4 tile needs 2 loads per 16
+// FMAs and was limited by the one-wavefront-per-cycle shared-memory pipe).  The backward recomputes the hidden
+// activations instead of reading them back; weight gradients are accumulated in registers across all tiles of a
+// (persistent) CTA, written once per CTA to a partials buffer and summed by a second tiny kernel -- no atomics.
 // Other decoder shapes go through the generic layers of k2_linear.cu.
 #include <algorithm>
 
@@ -14,32 +16,32 @@
 namespace gngf {
 
 constexpr int H = 64;        // hidden width
-constexpr int TP = 64;       // points per tile (64: ~77 KB of shared memory in the backward -> 2 CTAs per SM)
-constexpr int NG = TP / 64;  // float4 point groups per thread: thread tile = (4*NG points) x (4 outputs)
+constexpr int TP = 128;      // points per tile
 constexpr int LDP = TP + 4;  // row stride of the k-major activation buffers
-constexpr int MLP_THREADS = 256;
+constexpr int MLP_THREADS = 128;
 
 __device__ __forceinline__ float hidden_act(float v, int leaky) { return v > 0.0f ? v : (leaky ? v * 0.01f : 0.0f); }
 
-// acc[pi][ji] += sum_k A[k][p] * B[k][j] with p in {64*g + 4*tp .. +3, g < NG}, j in {4*tj .. 4*tj+3}
+// thread (tp = tid % 16, tj = tid / 16) owns points {4tp..4tp+3, 64+4tp..} x outputs {4tj..4tj+3, 32+4tj..}
+// acc[pi][ji] += sum_k A[k][p] * B[k][j]
 __device__ __forceinline__ void gemm_tile(const float* __restrict__ A, const float* __restrict__ B, int bstride, int K,
-                                          int tp, int tj, float acc[4 * NG][4]) {
-#pragma unroll 4
+                                          int tp, int tj, float acc[8][8]) {
+#pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    float av[4 * NG];
+    const float4 a0 = *reinterpret_cast<const float4*>(A + k * LDP + 4 * tp);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + k * LDP + 64 + 4 * tp);
+    const float4 b0 = *reinterpret_cast<const float4*>(B + k * bstride + 4 * tj);
+    const float4 b1 = *reinterpret_cast<const float4*>(B + k * bstride + 32 + 4 * tj);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const float4 a = *reinterpret_cast<const float4*>(A + k * LDP + 64 * g + 4 * tp);
-      av[4 * g + 0] = a.x; av[4 * g + 1] = a.y; av[4 * g + 2] = a.z; av[4 * g + 3] = a.w;
-    }
-    const float4 b = *reinterpret_cast<const float4*>(B + k * bstride + 4 * tj);
-    const float bv[4] = {b.x, b.y, b.z, b.w};
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int i = 0; i < 4 * NG; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
   }
 }
+__device__ __forceinline__ int tile_point(int tp, int i) { return (i < 4 ? 0 : 64) + 4 * tp + (i & 3); }
+__device__ __forceinline__ int tile_out(int tj, int j) { return (j < 4 ? 0 : 32) + 4 * tj + (j & 3); }
 
 struct MlpSmem {
   float* X;    // [INP][LDP]   enc, k-major
@@ -91,23 +93,27 @@ __device__ __forceinline__ void load_weights(const MlpSmem& s, int IN, int INP, 
                                              const float* __restrict__ w1, const float* __restrict__ b1,
                                              const float* __restrict__ w2, const float* __restrict__ b2) {
   const int tid = threadIdx.x;
+  // (transposed copies are written with the shared-memory index fastest: conflict-free stores, the strided
+  //  global reads come from L2)
   for (int e = tid; e < H * INP; e += MLP_THREADS) {  // w0 is (H, IN)
-    const int j = e / INP, k = e % INP;
-    const float v = k < IN ? w0[j * IN + k] : 0.0f;
-    s.W0t[k * H + j] = v;
-    if (bwd) s.W0n[j * INP + k] = v;
+    const int k = e / H, j = e % H;
+    s.W0t[e] = k < IN ? w0[j * IN + k] : 0.0f;
   }
   for (int e = tid; e < H * H; e += MLP_THREADS) {  // w1 is (H, H)
-    const int j = e / H, k = e % H;
-    const float v = w1[e];
-    s.W1t[k * H + j] = v;
-    if (bwd) s.W1n[e] = v;
+    const int k = e / H, j = e % H;
+    s.W1t[e] = w1[j * H + k];
   }
   for (int e = tid; e < 4 * H; e += MLP_THREADS) {  // w2 is (OUT, H)
-    const int c = e / H, k = e % H;
-    const float v = c < OUT ? w2[c * H + k] : 0.0f;
-    s.W2t[k * 4 + c] = v;
-    if (bwd) s.W2n[e] = v;
+    const int k = e / 4, c = e % 4;
+    s.W2t[e] = c < OUT ? w2[c * H + k] : 0.0f;
+  }
+  if (bwd) {
+    for (int e = tid; e < H * INP; e += MLP_THREADS) {
+      const int j = e / INP, k = e % INP;
+      s.W0n[e] = k < IN ? w0[j * IN + k] : 0.0f;
+    }
+    for (int e = tid; e < H * H; e += MLP_THREADS) s.W1n[e] = w1[e];
+    for (int e = tid; e < 4 * H; e += MLP_THREADS) s.W2n[e] = (e / H) < OUT ? w2[e] : 0.0f;
   }
   for (int e = tid; e < H; e += MLP_THREADS) {
     s.b0[e] = b0[e];
@@ -138,23 +144,24 @@ __device__ __forceinline__ void load_enc_tile(const MlpSmem& s, const float* __r
 __device__ __forceinline__ void hidden_layer(const float* src, const float* Wt, const float* b, int K, float* dst,
                                              int leaky) {
   const int tp = threadIdx.x % 16, tj = threadIdx.x / 16;
-  float acc[4 * NG][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4 * NG; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
   gemm_tile(src, Wt, H, K, tp, tj, acc);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float bj = b[4 * tj + j];
+  for (int j = 0; j < 8; ++j) {
+    const int jj = tile_out(tj, j);
+    const float bj = b[jj];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
+    for (int g = 0; g < 2; ++g) {
       float4 o;
       o.x = hidden_act(acc[4 * g + 0][j] + bj, leaky);
       o.y = hidden_act(acc[4 * g + 1][j] + bj, leaky);
       o.z = hidden_act(acc[4 * g + 2][j] + bj, leaky);
       o.w = hidden_act(acc[4 * g + 3][j] + bj, leaky);
-      *reinterpret_cast<float4*>(dst + (4 * tj + j) * LDP + 64 * g + 4 * tp) = o;
+      *reinterpret_cast<float4*>(dst + jj * LDP + 64 * g + 4 * tp) = o;
     }
   }
 }
@@ -205,6 +212,7 @@ __global__ void __launch_bounds__(MLP_THREADS)
 // partial-gradient layout per CTA (floats): dw0 [H*IN] | db0 [H] | dw1 [H*H] | db1 [H] | dw2 [OUT*H] | db2 [OUT]
 __host__ __device__ inline int mlp_param_floats(int IN, int OUT) { return H * IN + H + H * H + H + OUT * H + OUT; }
 
+template <int NM>  // NM = number of dw0 columns per thread = ceil(INP / 2) rounded to {4, 16, 32}
 __global__ void __launch_bounds__(MLP_THREADS)
     mlp3_bwd_kernel(const float* __restrict__ enc, const float* __restrict__ drgb, int64_t P, int IN, int INP, int OUT,
                     int leaky, const float* __restrict__ w0, const float* __restrict__ b0,
@@ -215,18 +223,19 @@ __global__ void __launch_bounds__(MLP_THREADS)
   load_weights(s, IN, INP, OUT, true, w0, b0, w1, b1, w2, b2);
   const int tid = threadIdx.x;
   const int tp = tid % 16, tj = tid / 16;
+  const float slope = leaky ? 0.01f : 0.0f;
 
   // gradient accumulators that live in registers across all tiles of this CTA
-  float g_w1[4][4];   // dw1[j = tp + 16 a][k = tj + 16 b]
+  float g_w1[8][4];   // dw1[j = tid % 8 + 8 a][k = tid / 8 + 16 b]
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) g_w1[a][b] = 0.0f;
-  float g_w0[16];     // dw0[j = tid % 64][i = tid / 64 + 4 m], m < INP / 4
+  float g_w0[NM];     // dw0[j = tid % 64][i = tid / 64 + 2 m], m < INP / 2
 #pragma unroll
-  for (int m = 0; m < 16; ++m) g_w0[m] = 0.0f;
-  float g_w2 = 0.0f;  // dw2[c = tid / 64][k = tid % 64]   (tid < 4*64: c < 4)
-  float g_b = 0.0f;   // tid < 64: db1[tid]; 64 <= tid < 128: db0[tid-64]; 128 <= tid < 132: db2[tid-128]
+  for (int m = 0; m < NM; ++m) g_w0[m] = 0.0f;
+  float g_w2[2] = {0.0f, 0.0f};  // dw2[c = tid / 64 + 2 q][k = tid % 64], q < 2
+  float g_b1 = 0.0f, g_b0 = 0.0f, g_b2 = 0.0f;  // tid < 64: db1[tid], db0[tid]; tid < 4: db2[tid]
 
   const int64_t tiles = (P + TP - 1) / TP;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -238,8 +247,8 @@ __global__ void __launch_bounds__(MLP_THREADS)
     __syncthreads();
     hidden_layer(s.A1, s.W1t, s.b1, H, s.A2, leaky);
     __syncthreads();
-    // dz2 = drgb * y * (1 - y), stored [c][p]; padded points / channels contribute zero
-    if (tid < TP) {
+    // dz2 = drgb * y * (1 - y), stored [c][p]; padded points / channels contribute zero  (thread = point)
+    {
       float out[4];
       output_layer(s, tid, out);
 #pragma unroll
@@ -252,36 +261,42 @@ __global__ void __launch_bounds__(MLP_THREADS)
     __syncthreads();
     // dw2[c][k] += sum_p dz2[c][p] * a2[k][p] ; db2[c] += sum_p dz2[c][p]
     {
-      const int c = tid / H, k = tid % H;  // 256 threads = 4 x 64
-      float acc = 0.0f;
-      for (int p = 0; p < TP; p += 4) {
-        const float4 d = *reinterpret_cast<const float4*>(s.dz2 + c * LDP + p);
-        const float4 a = *reinterpret_cast<const float4*>(s.A2 + k * LDP + p);
-        acc = fmaf(d.x, a.x, acc); acc = fmaf(d.y, a.y, acc); acc = fmaf(d.z, a.z, acc); acc = fmaf(d.w, a.w, acc);
+      const int k = tid % H;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = tid / H + 2 * q;
+        float acc = 0.0f;
+        for (int p = 0; p < TP; p += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(s.dz2 + c * LDP + p);
+          const float4 a = *reinterpret_cast<const float4*>(s.A2 + k * LDP + p);
+          acc = fmaf(d.x, a.x, acc); acc = fmaf(d.y, a.y, acc); acc = fmaf(d.z, a.z, acc); acc = fmaf(d.w, a.w, acc);
+        }
+        g_w2[q] += acc;
       }
-      g_w2 += acc;
-      if (tid >= 128 && tid < 132) {
+      if (tid < 4) {
         float sb = 0.0f;
-        for (int p = 0; p < TP; ++p) sb += s.dz2[(tid - 128) * LDP + p];
-        g_b += sb;
+        for (int p = 0; p < TP; p += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(s.dz2 + tid * LDP + p);
+          sb += (d.x + d.y) + (d.z + d.w);
+        }
+        g_b2 += sb;
       }
     }
     __syncthreads();
-    // dz1[j][p] = (sum_c dz2[c][p] * w2[c][j]) * act'(a2[j][p]), in place over A2
+    // dz1[j][p] = (sum_c dz2[c][p] * w2[c][j]) * act'(a2[j][p]), in place over A2 (each thread its own 8x8 tile)
     {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int jj = 4 * tj + j;
-        const float w20 = s.W2n[0 * H + jj], w21 = s.W2n[1 * H + jj], w22 = s.W2n[2 * H + jj], w23 = s.W2n[3 * H + jj];
+      for (int g = 0; g < 2; ++g) {
+        const int pp = g * 64 + 4 * tp;
+        const float4 d0 = *reinterpret_cast<const float4*>(s.dz2 + 0 * LDP + pp);
+        const float4 d1 = *reinterpret_cast<const float4*>(s.dz2 + 1 * LDP + pp);
+        const float4 d2 = *reinterpret_cast<const float4*>(s.dz2 + 2 * LDP + pp);
+        const float4 d3 = *reinterpret_cast<const float4*>(s.dz2 + 3 * LDP + pp);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          const int pp = g * 64 + 4 * tp;
+        for (int j = 0; j < 8; ++j) {
+          const int jj = tile_out(tj, j);
+          const float w20 = s.W2n[0 * H + jj], w21 = s.W2n[1 * H + jj], w22 = s.W2n[2 * H + jj], w23 = s.W2n[3 * H + jj];
           const float4 a = *reinterpret_cast<const float4*>(s.A2 + jj * LDP + pp);
-          const float4 d0 = *reinterpret_cast<const float4*>(s.dz2 + 0 * LDP + pp);
-          const float4 d1 = *reinterpret_cast<const float4*>(s.dz2 + 1 * LDP + pp);
-          const float4 d2 = *reinterpret_cast<const float4*>(s.dz2 + 2 * LDP + pp);
-          const float4 d3 = *reinterpret_cast<const float4*>(s.dz2 + 3 * LDP + pp);
-          const float slope = leaky ? 0.01f : 0.0f;
           float4 r;
           r.x = fmaf(d3.x, w23, fmaf(d2.x, w22, fmaf(d1.x, w21, d0.x * w20))) * (a.x > 0.0f ? 1.0f : slope);
           r.y = fmaf(d3.y, w23, fmaf(d2.y, w22, fmaf(d1.y, w21, d0.y * w20))) * (a.y > 0.0f ? 1.0f : slope);
@@ -294,19 +309,20 @@ __global__ void __launch_bounds__(MLP_THREADS)
     __syncthreads();
     // dw1[j][k] += sum_p dz1[j][p] * a1[k][p] ; db1[j] += sum_p dz1[j][p]
     {
-      float acc[4][4];
+      const int rj = tid % 8, rk = tid / 8;
+      float acc[8][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
       for (int p = 0; p < TP; p += 4) {
-        float4 dz[4], av[4];
+        float4 dz[8], av[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) dz[a] = *reinterpret_cast<const float4*>(s.A2 + (tp + 16 * a) * LDP + p);
+        for (int a = 0; a < 8; ++a) dz[a] = *reinterpret_cast<const float4*>(s.A2 + (rj + 8 * a) * LDP + p);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) av[b] = *reinterpret_cast<const float4*>(s.A1 + (tj + 16 * b) * LDP + p);
+        for (int b = 0; b < 4; ++b) av[b] = *reinterpret_cast<const float4*>(s.A1 + (rk + 16 * b) * LDP + p);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             acc[a][b] = fmaf(dz[a].x, av[b].x, acc[a][b]);
@@ -316,7 +332,7 @@ __global__ void __launch_bounds__(MLP_THREADS)
           }
       }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) g_w1[a][b] += acc[a][b];
       if (tid < H) {
@@ -325,24 +341,23 @@ __global__ void __launch_bounds__(MLP_THREADS)
           const float4 d = *reinterpret_cast<const float4*>(s.A2 + tid * LDP + p);
           sb += (d.x + d.y) + (d.z + d.w);
         }
-        g_b += sb;
+        g_b1 += sb;
       }
     }
     // dz0[k][p] = (sum_j dz1[j][p] * w1[j][k]) * act'(a1[k][p]) -> registers, then in place over A1
     {
-      float acc[4 * NG][4];
+      float acc[8][8];
 #pragma unroll
-      for (int i = 0; i < 4 * NG; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
       gemm_tile(s.A2, s.W1n, H, H, tp, tj, acc);
       __syncthreads();  // every thread is done reading A1 (dw1) before it is overwritten
-      const float slope = leaky ? 0.01f : 0.0f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int kk = 4 * tj + j;
+      for (int j = 0; j < 8; ++j) {
+        const int kk = tile_out(tj, j);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
+        for (int g = 0; g < 2; ++g) {
           float* ptr = s.A1 + kk * LDP + g * 64 + 4 * tp;
           const float4 a = *reinterpret_cast<const float4*>(ptr);
           float4 r;
@@ -357,25 +372,25 @@ __global__ void __launch_bounds__(MLP_THREADS)
     __syncthreads();
     // dw0[j][i] += sum_p dz0[j][p] * x[i][p] ; db0[j] += sum_p dz0[j][p]
     {
-      const int j = tid % H, i0 = tid / H;  // i = i0 + 4 m
-      const int nm = INP / 4;
+      const int j = tid % H, i0 = tid / H;  // i = i0 + 2 m
+      const int nm = INP / 2;
       for (int p = 0; p < TP; p += 4) {
         const float4 d = *reinterpret_cast<const float4*>(s.A1 + j * LDP + p);
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
+        for (int m = 0; m < NM; ++m) {
           if (m < nm) {
-            const float4 xv = *reinterpret_cast<const float4*>(s.X + (i0 + 4 * m) * LDP + p);
+            const float4 xv = *reinterpret_cast<const float4*>(s.X + (i0 + 2 * m) * LDP + p);
             g_w0[m] = fmaf(d.x, xv.x, fmaf(d.y, xv.y, fmaf(d.z, xv.z, fmaf(d.w, xv.w, g_w0[m]))));
           }
         }
       }
-      if (tid >= 64 && tid < 128) {
+      if (tid < H) {
         float sb = 0.0f;
         for (int p = 0; p < TP; p += 4) {
-          const float4 d = *reinterpret_cast<const float4*>(s.A1 + (tid - 64) * LDP + p);
+          const float4 d = *reinterpret_cast<const float4*>(s.A1 + tid * LDP + p);
           sb += (d.x + d.y) + (d.z + d.w);
         }
-        g_b += sb;
+        g_b0 += sb;
       }
     }
     // denc[p][i] = sum_k dz0[k][p] * w0[k][i]   (INP / 4 column groups of 4; thread -> 4 points x 4 columns)
@@ -422,19 +437,28 @@ __global__ void __launch_bounds__(MLP_THREADS)
   {
     const int j = tid % H, i0 = tid / H;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int i = i0 + 4 * m;
-      if (m < INP / 4 && i < IN) o_dw0[j * IN + i] = g_w0[m];
+    for (int m = 0; m < NM; ++m) {
+      const int i = i0 + 2 * m;
+      if (m < INP / 2 && i < IN) o_dw0[j * IN + i] = g_w0[m];
     }
   }
+  {
+    const int rj = tid % 8, rk = tid / 8;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) o_dw1[(tp + 16 * a) * H + (tj + 16 * b)] = g_w1[a][b];
-  if (tid / H < OUT) o_dw2[(tid / H) * H + tid % H] = g_w2;
-  if (tid < 64) o_db1[tid] = g_b;
-  else if (tid < 128) o_db0[tid - 64] = g_b;
-  else if (tid < 128 + OUT) o_db2[tid - 128] = g_b;
+      for (int b = 0; b < 4; ++b) o_dw1[(rj + 8 * a) * H + (rk + 16 * b)] = g_w1[a][b];
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int c = tid / H + 2 * q;
+    if (c < OUT) o_dw2[c * H + tid % H] = g_w2[q];
+  }
+  if (tid < H) {
+    o_db1[tid] = g_b1;
+    o_db0[tid] = g_b0;
+  }
+  if (tid < OUT) o_db2[tid] = g_b2;
 }
 
 // grads[i] += sum over CTAs of partials[cta][i], routed to the six parameter-gradient buffers
@@ -503,12 +527,17 @@ int gngf_mlp3_bwd(const float* enc, const float* drgb, int64_t P, int32_t in_dim
   const int INP = (in_dim + 3) & ~3;
   const size_t smem = sizeof(float) * gngf::mlp_smem_floats(INP, true);
   cudaStream_t st = gngf::as_stream(stream);
-  if (cudaFuncSetAttribute(gngf::mlp3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(smem)) != cudaSuccess)
-    return gngf::check_launch();
   const int grid = gngf::mlp_grid(P, smem);
-  gngf::mlp3_bwd_kernel<<<grid, gngf::MLP_THREADS, smem, st>>>(enc, drgb, P, in_dim, INP, out_dim, leaky, w0, b0, w1,
-                                                                b1, w2, b2, denc, workspace);
+  auto launch = [&](auto kernel) -> int {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return gngf::check_launch();
+    kernel<<<grid, gngf::MLP_THREADS, smem, st>>>(enc, drgb, P, in_dim, INP, out_dim, leaky, w0, b0, w1, b1, w2, b2,
+                                                   denc, workspace);
+    return GNGF_OK;
+  };
+  int lrc = INP <= 8 ? launch(gngf::mlp3_bwd_kernel<4>)
+                     : (INP <= 32 ? launch(gngf::mlp3_bwd_kernel<16>) : launch(gngf::mlp3_bwd_kernel<32>));
+  if (lrc) return lrc;
   gngf::note_launch();
   int rc = gngf::check_launch();
   if (rc) return rc;
