@@ -49,19 +49,21 @@ struct MlpSmem {
   float* A2;   // [H][LDP]
   float* W0t;  // [INP][H]     W0^T  (forward B operand)
   float* W1t;  // [H][H]       W1^T
-  float* W2t;  // [H][4]       W2^T, OUT padded to 4
   float* W0n;  // [H][INP]     W0 as stored (backward B operand)      -- backward only
   float* W1n;  // [H][H]
-  float* W2n;  // [4][H]
-  float* b0;   // [H]
-  float* b1;   // [H]
-  float* b2;   // [4]
   float* dz2;  // [4][LDP]                                            -- backward only
+  // the output layer's weights and all biases (~650 floats) are read through the read-only path instead:
+  // that keeps the backward at 110.8 KB of shared memory, i.e. two CTAs per SM
+  const float* w2;  // (OUT, H) global
+  const float* b0;
+  const float* b1;
+  const float* b2;
+  int OUT;
 };
 
 __host__ __device__ inline int mlp_smem_floats(int INP, bool bwd) {
-  int n = INP * LDP + 2 * H * LDP + INP * H + H * H + H * 4 + 2 * H + 4;
-  if (bwd) n += H * INP + H * H + 4 * H + 4 * LDP;
+  int n = INP * LDP + 2 * H * LDP + INP * H + H * H;
+  if (bwd) n += H * INP + H * H + 4 * LDP;
   return n;
 }
 
@@ -73,22 +75,19 @@ __device__ __forceinline__ MlpSmem carve(float* base, int INP, bool bwd) {
   s.A2 = p; p += H * LDP;
   s.W0t = p; p += INP * H;
   s.W1t = p; p += H * H;
-  s.W2t = p; p += H * 4;
-  s.b0 = p; p += H;
-  s.b1 = p; p += H;
-  s.b2 = p; p += 4;
   if (bwd) {
     s.W0n = p; p += H * INP;
     s.W1n = p; p += H * H;
-    s.W2n = p; p += 4 * H;
     s.dz2 = p; p += 4 * LDP;
   } else {
-    s.W0n = s.W1n = s.W2n = s.dz2 = nullptr;
+    s.W0n = s.W1n = s.dz2 = nullptr;
   }
+  s.w2 = s.b0 = s.b1 = s.b2 = nullptr;
+  s.OUT = 0;
   return s;
 }
 
-__device__ __forceinline__ void load_weights(const MlpSmem& s, int IN, int INP, int OUT, bool bwd,
+__device__ __forceinline__ void load_weights(MlpSmem& s, int IN, int INP, int OUT, bool bwd,
                                              const float* __restrict__ w0, const float* __restrict__ b0,
                                              const float* __restrict__ w1, const float* __restrict__ b1,
                                              const float* __restrict__ w2, const float* __restrict__ b2) {
@@ -103,23 +102,18 @@ __device__ __forceinline__ void load_weights(const MlpSmem& s, int IN, int INP, 
     const int k = e / H, j = e % H;
     s.W1t[e] = w1[j * H + k];
   }
-  for (int e = tid; e < 4 * H; e += MLP_THREADS) {  // w2 is (OUT, H)
-    const int k = e / 4, c = e % 4;
-    s.W2t[e] = c < OUT ? w2[c * H + k] : 0.0f;
-  }
   if (bwd) {
     for (int e = tid; e < H * INP; e += MLP_THREADS) {
       const int j = e / INP, k = e % INP;
       s.W0n[e] = k < IN ? w0[j * IN + k] : 0.0f;
     }
     for (int e = tid; e < H * H; e += MLP_THREADS) s.W1n[e] = w1[e];
-    for (int e = tid; e < 4 * H; e += MLP_THREADS) s.W2n[e] = (e / H) < OUT ? w2[e] : 0.0f;
   }
-  for (int e = tid; e < H; e += MLP_THREADS) {
-    s.b0[e] = b0[e];
-    s.b1[e] = b1[e];
-  }
-  if (tid < 4) s.b2[tid] = tid < OUT ? b2[tid] : 0.0f;
+  s.w2 = w2;
+  s.b0 = b0;
+  s.b1 = b1;
+  s.b2 = b2;
+  s.OUT = OUT;
 }
 
 // enc tile -> X (k-major), zero-padded rows/points
@@ -153,7 +147,7 @@ __device__ __forceinline__ void hidden_layer(const float* src, const float* Wt, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int jj = tile_out(tj, j);
-    const float bj = b[jj];
+    const float bj = __ldg(b + jj);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       float4 o;
@@ -166,17 +160,17 @@ __device__ __forceinline__ void hidden_layer(const float* src, const float* Wt, 
   }
 }
 
-// thread p < TP: out[c] = sigmoid(sum_k A2[k][p] * W2t[k][c] + b2[c])
+// thread p < TP: out[c] = sigmoid(sum_k A2[k][p] * w2[c][k] + b2[c]), c < OUT (others 0.5, never used)
 __device__ __forceinline__ void output_layer(const MlpSmem& s, int p, float out[4]) {
-  float acc[4] = {s.b2[0], s.b2[1], s.b2[2], s.b2[3]};
+  float acc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = c < s.OUT ? __ldg(s.b2 + c) : 0.0f;
 #pragma unroll 8
   for (int k = 0; k < H; ++k) {
     const float a = s.A2[k * LDP + p];
-    const float4 w = *reinterpret_cast<const float4*>(s.W2t + k * 4);
-    acc[0] = fmaf(a, w.x, acc[0]);
-    acc[1] = fmaf(a, w.y, acc[1]);
-    acc[2] = fmaf(a, w.z, acc[2]);
-    acc[3] = fmaf(a, w.w, acc[3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < s.OUT) acc[c] = fmaf(a, __ldg(s.w2 + c * H + k), acc[c]);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) out[c] = 1.0f / (1.0f + expf(-acc[c]));
@@ -188,7 +182,7 @@ __global__ void __launch_bounds__(MLP_THREADS)
                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                     float* __restrict__ rgb) {
   extern __shared__ __align__(16) float smem_f[];
-  const MlpSmem s = carve(smem_f, INP, false);
+  MlpSmem s = carve(smem_f, INP, false);
   load_weights(s, IN, INP, OUT, false, w0, b0, w1, b1, w2, b2);
   const int64_t tiles = (P + TP - 1) / TP;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -219,7 +213,7 @@ __global__ void __launch_bounds__(MLP_THREADS)
                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                     const float* __restrict__ b2, float* __restrict__ denc, float* __restrict__ partials) {
   extern __shared__ __align__(16) float smem_f[];
-  const MlpSmem s = carve(smem_f, INP, true);
+  MlpSmem s = carve(smem_f, INP, true);
   load_weights(s, IN, INP, OUT, true, w0, b0, w1, b1, w2, b2);
   const int tid = threadIdx.x;
   const int tp = tid % 16, tj = tid / 16;
@@ -295,7 +289,8 @@ __global__ void __launch_bounds__(MLP_THREADS)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int jj = tile_out(tj, j);
-          const float w20 = s.W2n[0 * H + jj], w21 = s.W2n[1 * H + jj], w22 = s.W2n[2 * H + jj], w23 = s.W2n[3 * H + jj];
+          const float w20 = __ldg(s.w2 + jj), w21 = OUT > 1 ? __ldg(s.w2 + H + jj) : 0.0f;
+          const float w22 = OUT > 2 ? __ldg(s.w2 + 2 * H + jj) : 0.0f, w23 = OUT > 3 ? __ldg(s.w2 + 3 * H + jj) : 0.0f;
           const float4 a = *reinterpret_cast<const float4*>(s.A2 + jj * LDP + pp);
           float4 r;
           r.x = fmaf(d3.x, w23, fmaf(d2.x, w22, fmaf(d1.x, w21, d0.x * w20))) * (a.x > 0.0f ? 1.0f : slope);
@@ -486,7 +481,7 @@ __global__ void __launch_bounds__(256)
 }
 
 static int mlp_grid(int64_t P, size_t smem_bytes) {
-  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem_bytes + 1024))));
+  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem_bytes + 1024))));
   return static_cast<int>(std::min<int64_t>(ceil_div(P, TP), static_cast<int64_t>(per_sm) * sm_count()));
 }
 
