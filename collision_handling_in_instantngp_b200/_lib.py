@@ -71,6 +71,9 @@ SIGNATURES = {
     "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "gngf_hpd_stream_workspace_floats": (c_int64, [c_int64, c_int64, c_int32]),
     "gngf_hpd_stream_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
+    "gngf_hpd_stream_bwd_workspace_floats": (c_int64, [c_int64, c_int32]),
+    "gngf_hpd_stream_bwd": (c_int, [Lattice, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P,
+                                    _P, _P, c_int32, _P, _P, _P, _P, _P]),
     "gngf_hpd_small_supported": (c_int, [c_int32, POINTER(c_int32), c_int32]),
     "gngf_hpd_small_fwd": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_void_p), c_int32, _P, _P, _P, _P]),

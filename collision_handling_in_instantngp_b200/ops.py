@@ -149,6 +149,21 @@ def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
     return utopv, utopi, row_max, row_sum
 
 
+def hpd_stream_bwd(lat: Lattice, h, w, b, h_planes, w_planes, utopv, utopi, dtv, cnt, gcol_k, row_max, row_sum,
+                   dw, db, act_prev=ACT_RELU) -> torch.Tensor:
+    """Fused K5c (k2_hpd_tc_bwd.cu): returns dh (U,Kd) = (dlogits w) .* act'(h); accumulates dlogits^T h into dw and
+    colsum(dlogits) into db, with dlogits = -<g,p_top> p + scatter(p_k g_k) never materialised."""
+    U, kd = h.shape
+    T, K = w.shape[0], utopv.shape[1]
+    dh = torch.zeros((U, kd), dtype=torch.float32, device=h.device)
+    work = torch.empty(_lib.load().gngf_hpd_stream_bwd_workspace_floats(U, K), dtype=torch.float32, device=h.device)
+    call("gngf_hpd_stream_bwd", lat, h_planes.data_ptr(), w_planes.data_ptr(), h.data_ptr(), w.data_ptr(),
+         b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(), _ptr(cnt), _ptr(gcol_k),
+         row_max.data_ptr(), row_sum.data_ptr(), act_prev, dh.data_ptr(), dw.data_ptr(), db.data_ptr(),
+         work.data_ptr(), _stream())
+    return dh
+
+
 def softmax_topk_fwd(logits: torch.Tensor, k: int, inplace: bool = False, want_probs: bool = True):
     """probs = nan_to_num(softmax(logits)), (topv, topi) = topk(probs, k) with ties -> lower index."""
     _require_cuda(logits, "logits")
@@ -243,6 +258,7 @@ class ForwardState:
     row_max: Optional[torch.Tensor] = None                       # (U,) softmax statistics (streaming path)
     row_sum: Optional[torch.Tensor] = None
     w_planes: Optional[torch.Tensor] = None                      # (3,T,Kd) bf16 planes of the output layer
+    h_planes: Optional[torch.Tensor] = None                      # (3,U,Kd) bf16 planes of its input (streaming path)
     hpd_small: bool = False                                      # fused small-lattice HPD kernels were used
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
@@ -264,7 +280,9 @@ def _mlp3_supported(mlp_w) -> bool:
 STREAM_MIN_ELEMENTS = 1 << 26
 FORCE_STREAMING = None            # None: by size; True / False: override
 TC_MIN_ELEMENTS = 1 << 22         # dense logits come from the tensor-core GEMM above this size
-BWD_CHUNK_BYTES = 4 << 30         # logits recomputed per chunk of rows in the streaming backward
+BWD_CHUNK_BYTES = 4 << 30         # logits recomputed per chunk of rows in the (un-fused) streaming backward
+STREAM_BWD_FUSED = True           # streaming backward as the fused tcgen05 kernels of k2_hpd_tc_bwd.cu (False: the
+                                  # chunked recompute through the plain GEMM, kept as a cross-check for the tests)
 
 
 def _streaming_ok(cfg, U, T, k, kd) -> bool:
@@ -321,8 +339,9 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
     kd = h.shape[1]
     if _streaming_ok(cfg, U, T, k, kd):
         state.w_planes = split_bf16x3(hpd_w[-1])
+        state.h_planes = split_bf16x3(h)
         state.utopv, state.utopi, state.row_max, state.row_sum = hpd_stream_fwd(
-            h, hpd_w[-1], hpd_b[-1], k, w_planes=state.w_planes)
+            h, hpd_w[-1], hpd_b[-1], k, h_planes=state.h_planes, w_planes=state.w_planes)
         state.uprobs = None
         return
     if U * T * 4 > MAX_DENSE_LOGIT_BYTES:
@@ -515,6 +534,14 @@ class GNGFPath(torch.autograd.Function):
                  state.cnt.data_ptr(), _ptr(gcol), _ptr(gcol_k), _ptr(gdense), None, None, 0, U, dlogits.data_ptr(), st)
             dz = linear_bwd(dlogits, state.hpd_acts[nh - 2], hpd_w[nh - 1], ACT_RELU, True, g_hpd_w[nh - 1],
                             g_hpd_b[nh - 1])
+        elif STREAM_BWD_FUSED:
+            # streaming path, fused: logits are recomputed tile by tile in TMEM, turned into dlogits by the epilogue
+            # warps and contracted again (dlogits W3, dlogits^T h) without leaving the SM (k2_hpd_tc_bwd.cu)
+            h_last = state.hpd_acts[nh - 2]
+            kd = h_last.shape[1]
+            dz = hpd_stream_bwd(lat, h_last, hpd_w[nh - 1], params[2 * (nh - 1) + 1], state.h_planes, state.w_planes,
+                                state.utopv, state.utopi, dtv, state.cnt, gcol_k, state.row_max, state.row_sum,
+                                g_hpd_w[nh - 1], g_hpd_b[nh - 1])
         else:
             # streaming path: recompute the logits chunk by chunk on the tensor cores, turn them into dlogits in
             # place from the saved softmax statistics, and feed the output layer's backward

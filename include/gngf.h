@@ -127,6 +127,23 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
                         int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max, float* row_sum,
                         float* workspace, void* stream);
 
+/* K5c fused, streaming (top-k-only mode): backward of gngf_hpd_stream_fwd's layer + softmax + top-k
+ *   (models.py:80-88, 105-123; DifferentiableTopk.backward, models.py:21-42; column-sum adjoint of utils.py:138)
+ *   without materialising logits, probabilities or dlogits.  Per node u
+ *     g_k = dtv[u,k] + sum_l cnt[s(l,u)] gcol_k[l,k],   dlogit[u,:] = -<g,p_top> p[u,:] + scatter_k(p_k g_k),
+ *   and   dh (U,Kdim) = (dlogit W) .* act_prev'(h),   dw (T,Kdim) += dlogit^T h,   db (T) += colsum(dlogit).
+ *   The dense products run on tcgen05 (two bf16 planes, hi.hi + hi.mid + mid.hi, relative error ~1e-5), recomputing
+ *   the logits tile by tile from the planes and the forward's row_max / row_sum.
+ *   h_planes (3,U,Kdim) / w_planes (3,T,Kdim): gngf_split_bf16x3 planes; h (U,Kdim), w (T,Kdim): the fp32 originals
+ *   (used by the K-sparse part); utopv / utopi (U,topk): the forward's outputs; dh must be ZERO-INITIALISED, dw / db
+ *   are accumulated into; workspace: gngf_hpd_stream_bwd_workspace_floats(U, topk) floats, 16-byte aligned.      */
+int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk);
+int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16_t* w_planes, const float* h,
+                        const float* w, const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk,
+                        const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                        const float* gcol_k, const float* row_max, const float* row_sum, int32_t act_prev, float* dh,
+                        float* dw, float* db, float* workspace, void* stream);
+
 /* ---- K2/K3/K5 fused for small lattices (a few hundred to a few thousand nodes, T <= 1024, hidden widths <= 256) ----
  * One CTA per 8 nodes walks the whole HPD (models.py:80-123): layer 0 from the node coordinates, hidden layers,
  * output layer, softmax + nan_to_num, top-k; the backward computes dlogits (as gngf_hpd_dlogits), the bias

@@ -266,3 +266,49 @@ def test_streaming_hpd_matches_unfused(U, T, Kd, K):
     # every selected index is a true top-k member up to the tie tolerance, on all rows
     sel = np.take_along_axis(p_ref, utopi.cpu().numpy().astype(np.int64), -1)
     assert (sel >= srt[:, K - 1:K] * (1 - 2e-5)).all()
+
+
+def _flat_lattice(U):
+    """A one-level lattice whose node box is U x 1 (the kernel-level tests need node ids only)."""
+    from collision_handling_in_instantngp_b200._lib import Lattice
+    lat = Lattice()
+    lat.num_levels = 1
+    lat.n[0] = max(U - 1, 1)
+    lat.ox = lat.oy = lat.lox[0] = lat.loy[0] = 0
+    lat.wx, lat.wy, lat.lwx[0], lat.lwy[0] = U, 1, U, 1
+    lat.loff[0], lat.loff[1] = 0, U
+    return lat
+
+
+@pytest.mark.parametrize("U,T,Kd,K", [(300, 1000, 128, 4), (782, 256, 128, 4), (130, 4096, 64, 1), (1000, 2 ** 14, 128, 8),
+                                       (64, 2 ** 17, 128, 4), (5000, 8192, 128, 4), (129, 72, 72, 2)])
+def test_streaming_hpd_backward_matches_fp64(U, T, Kd, K):
+    """Fused tcgen05 backward of the streaming output layer (logits recomputed in TMEM, dlogits never written; second
+    product reads the streamed tile MN-major) against a float64 restatement.  Gradient bar: 1e-4 relative."""
+    rng = np.random.default_rng(U * 7 + T)
+    h = np.maximum(rng.standard_normal((U, Kd)), 0).astype(np.float32)
+    w = (rng.standard_normal((T, Kd)) * (3.0 / np.sqrt(Kd))).astype(np.float32)
+    b = rng.standard_normal(T).astype(np.float32)
+    dtv = rng.standard_normal((U, K)).astype(np.float32)
+    ht, wt, bt, dtvt = (torch.from_numpy(a).to(DEV) for a in (h, w, b, dtv))
+    hp, wp = ops.split_bf16x3(ht), ops.split_bf16x3(wt)
+    utopv, utopi, rmax, rsum = ops.hpd_stream_fwd(ht, wt, bt, K, h_planes=hp, w_planes=wp)
+    dw0 = rng.standard_normal((T, Kd)).astype(np.float32)          # dw / db are accumulated into
+    db0 = rng.standard_normal(T).astype(np.float32)
+    dw, db = torch.from_numpy(dw0).to(DEV), torch.from_numpy(db0).to(DEV)
+    dh = ops.hpd_stream_bwd(_flat_lattice(U), ht, wt, bt, hp, wp, utopv, utopi, dtvt, None, None, rmax, rsum, dw, db)
+    torch.cuda.synchronize()
+
+    logits = h.astype(np.float64) @ w.astype(np.float64).T + b
+    p = O.softmax_lastdim(logits)
+    ti = utopi.cpu().numpy().astype(np.int64)
+    pk = np.take_along_axis(p, ti, -1)
+    pg = pk * dtv
+    dl = -pg.sum(-1, keepdims=True) * p
+    np.add.at(dl, (np.arange(U)[:, None], ti), pg)
+    dh_ref = (dl @ w.astype(np.float64)) * (h > 0)
+    dw_ref = dl.T @ h.astype(np.float64)
+    db_ref = dl.sum(0)
+    assert rel_err(dh.cpu().numpy(), dh_ref) < 1e-4
+    assert rel_err(dw.cpu().numpy() - dw0, dw_ref) < 1e-4
+    assert rel_err(db.cpu().numpy() - db0, db_ref) < 1e-4

@@ -162,6 +162,24 @@ def test_streaming_tensor_core_path_matches_reference_golden(name):
     _check_grads(out, g)
 
 
+@pytest.mark.parametrize("name", ["cfg2_topk_only", "l8_t4096_topk_only"])
+def test_fused_streaming_backward_equals_chunked_recompute(name):
+    """k2_hpd_tc_bwd.cu (dlogits never materialised) against the chunked recompute through the plain GEMM."""
+    from collision_handling_in_instantngp_b200 import ops
+    g = load(name)
+    net = build_net(g)
+    ops.FORCE_STREAMING = True
+    try:
+        out_f = run_step(net, g)
+        ops.STREAM_BWD_FUSED = False
+        out_c = run_step(net, g)
+    finally:
+        ops.FORCE_STREAMING = None
+        ops.STREAM_BWD_FUSED = True
+    for k in out_c["grads"]:
+        assert rel_err(out_f["grads"][k], out_c["grads"][k]) < 1e-4, k
+
+
 @pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "cfg2_epoch1", "js_only", "kl_only", "l16_t1024"])
 def test_fused_loss_kernel_matches_reference_loss(name):
     """k7_loss.cu (value + adjoints) against the reference's Loss / autograd recorded in the goldens."""
