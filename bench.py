@@ -215,6 +215,10 @@ def algorithmic_cost(name, key, w, lat):
         return "tensor", 6 * 2.0 * U * T * kd
     if name == "gngf_tc_gemm_bf16x3":
         return "tensor", 6 * 2.0 * float(key[0]) * key[1] * key[2]
+    if name == "gngf_hpd_stream_bwd":
+        # two fused passes (dh, dW3), each: logits recomputed (3 split products) + second product (3 split products);
+        # useful work = the two gradient products, 2 * 2*U*T*kd
+        return "tensor", 12 * 2.0 * U * T * kd
     table = {
         # per point: x (8) + per level 4 node-feature gathers (4*F*4) + enc row (F*4) + 4 multiplicity atomics (4*4)
         "gngf_encode_fwd": P * (8 + L * (4 * F * 4 + F * 4 + 16)),
@@ -392,7 +396,8 @@ def run_ours(args, w):
         achieved, peak, unit = per_launch_amount / per_launch_s / 1e12, tc_peak, "TFLOP/s"
     roofline = {"bound": te["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get((args.workload, tname)), "kernel": tname,
-                "useful_tflops": (achieved / 6 if tname in ("gngf_hpd_stream_fwd", "gngf_tc_gemm_bf16x3") else None),
+                "useful_tflops": (achieved / 6 if tname in ("gngf_hpd_stream_fwd", "gngf_tc_gemm_bf16x3", "gngf_hpd_stream_bwd")
+                                  else None),
                 "launches_per_step": te["n"] / args.steps,
                 "share_of_step_kernel_time": te["ms"] / total_kernel_ms, "peak_source": peak_src,
                 "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 5) for k, v in

@@ -111,11 +111,13 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer ----
+    {  // ---- MMA issuer: the whole warp runs the loop, an elected lane issues (see tc_common.cuh) ----
       constexpr uint32_t idesc = umma_idesc(BM, BN);
       // partial products of order <= 2 of (hi + mid + lo)(hi + mid + lo)
-      const int pa[6] = {0, 0, 1, 0, 2, 1};
-      const int pb[6] = {0, 1, 0, 2, 0, 1};
+      constexpr int pa[6] = {0, 0, 1, 0, 2, 1};
+      constexpr int pb[6] = {0, 1, 0, 2, 0, 1};
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t ring_lo = umma_desc_lo(smem_u32(smem));
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -123,28 +125,28 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int kb0 = ks * kb_per, kb1 = min(kblocks_all, kb0 + kb_per);
         mbar_wait(tempty + acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * BN;
+        const uint32_t d = tmem_u + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full + stage, phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_base = a_base + PLANES * PLANE_BYTES;
+          const uint32_t a_lo = ring_lo + stage * (STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + ((PLANES * PLANE_BYTES) >> 4);
 #pragma unroll
           for (int pr = 0; pr < 6; ++pr) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t ad = umma_desc(a_base + pa[pr] * PLANE_BYTES + k * UMMA_K * 2);
-              const uint64_t bd = umma_desc(b_base + pb[pr] * PLANE_BYTES + k * UMMA_K * 2);
-              umma_bf16(d, ad, bd, idesc, ((kb - kb0) | pr | k) != 0);
+              const uint64_t ad = umma_desc_pack(a_lo + ((pa[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
+              const uint64_t bd = umma_desc_pack(b_lo + ((pb[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
+              umma_bf16_lead(d, ad, bd, idesc, ((kb - kb0) | pr | k) != 0);
             }
           }
-          umma_commit(empty + stage);  // the stage may be refilled once these MMAs have read it
+          umma_commit_lead(empty + stage);  // the stage may be refilled once these MMAs have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(tfull + acc);  // accumulator complete -> epilogue
+        umma_commit_lead(tfull + acc);  // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -327,13 +329,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer ----
+    {  // ---- MMA issuer: the whole warp runs the loop, an elected lane issues (see tc_common.cuh) ----
       constexpr uint32_t idesc = umma_idesc(BM, BN);
-      const int pa[6] = {0, 0, 1, 0, 2, 1};
-      const int pb[6] = {0, 1, 0, 2, 0, 1};
+      constexpr int pa[6] = {0, 0, 1, 0, 2, 1};
+      constexpr int pb[6] = {0, 1, 0, 2, 0, 1};
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_buf));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(b_ring));
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-      const uint32_t a_base0 = smem_u32(a_buf);
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int sp = w % n_split;
         const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
@@ -343,34 +347,34 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
         for (int nt = nt0; nt < nt1; ++nt) {
           mbar_wait(tempty + acc, acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d = tmem_base + acc * BN;
+          const uint32_t d = tmem_u + acc * BN;
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(b_full + stage, phase);
             tc_fence_after();
-            const uint32_t a_base = a_base0 + kb * PLANES * PLANE_BYTES;
-            const uint32_t b_base = smem_u32(b_ring + stage * B_STAGE_BYTES);
+            const uint32_t a_lo = a_lo0 + kb * ((PLANES * PLANE_BYTES) >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (B_STAGE_BYTES >> 4);
 #pragma unroll
             for (int pr = 0; pr < 6; ++pr) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
-                const uint64_t ad = umma_desc(a_base + pa[pr] * PLANE_BYTES + k * UMMA_K * 2);
-                const uint64_t bd = umma_desc(b_base + pb[pr] * PLANE_BYTES + k * UMMA_K * 2);
-                umma_bf16(d, ad, bd, idesc, (kb | pr | k) != 0);
+                const uint64_t ad = umma_desc_pack(a_lo + ((pa[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
+                const uint64_t bd = umma_desc_pack(b_lo + ((pb[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
+                umma_bf16_lead(d, ad, bd, idesc, (kb | pr | k) != 0);
               }
             }
-            umma_commit(b_empty + stage);
+            umma_commit_lead(b_empty + stage);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(tfull + acc);
+          umma_commit_lead(tfull + acc);
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
-        umma_commit(a_empty);  // every MMA that reads the resident A tile has completed
+        umma_commit_lead(a_empty);  // every MMA that reads the resident A tile has completed
       }
     }
   } else {  // ---- epilogue warps 2..17: thread = (lattice node, 32-column part of every tile) ----

@@ -139,12 +139,14 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer ----
+    {  // ---- MMA issuer: the whole warp runs the loop, lane 0 issues (see tc_common.cuh) ----
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy
       constexpr uint32_t idesc1 = umma_idesc(BM, SBN);
       const uint32_t idesc2 = umma_idesc(BM, n2) | UMMA_B_MN_MAJOR;
-      const int pa[3] = {0, 0, 1};   // hi.hi, hi.mid, mid.hi
-      const int pb[3] = {0, 1, 0};
-      const uint32_t x_base = smem_u32(x_buf);
+      const uint32_t x_lo = umma_desc_lo(smem_u32(x_buf));
+      const uint32_t y_lo = umma_desc_lo(smem_u32(y_ring));                      // K-major view (first product)
+      const uint32_t y_lo_mn = umma_desc_lo(smem_u32(y_ring), NP * YP_BYTES);    // MN-major view (second product)
+      const uint32_t e_lo = umma_desc_lo(smem_u32(e_bufs));
       int s1_stage = 0, s2_stage = 0;          // Y ring positions of the first / second product
       uint32_t s1_phase = 0;
       uint32_t it1 = 0, it2 = 0;               // running tile counters (S / E buffer = counter & 1)
@@ -158,25 +160,29 @@ __global__ void __launch_bounds__(THREADS, 1)
         x_phase ^= 1;
         tc_fence_after();
         for (int j = 0; j <= nt; ++j) {
-          if (j < nt) {  // S(j) = X Y_j^T
+          if (j < nt) {  // S(j) = X Y_j^T : products hi.hi, hi.mid, mid.hi
             const uint32_t buf = it1 & 1, ph = (it1 >> 1) & 1;
             mbar_wait(y_full + s1_stage, s1_phase);
             mbar_wait(s_empty + buf, ph ^ 1);
             tc_fence_after();
-            const uint32_t y_base = smem_u32(y_ring + s1_stage * Y_STAGE_BYTES);
-            const uint32_t d = tmem_base + buf * SBN;
+            const uint32_t yb = y_lo + s1_stage * (Y_STAGE_BYTES >> 4);
+            const uint32_t d = tmem_u + buf * SBN;
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
-              for (int kb = 0; kb < kblocks; ++kb) {
+              const int pa = pr >> 1, pb = pr & 1;   // (0,0) (0,1) (1,0)
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                  const uint64_t ad = umma_desc(x_base + (kb * NP + pa[pr]) * XP_BYTES + k * UMMA_K * 2);
-                  const uint64_t bd = umma_desc(y_base + (kb * NP + pb[pr]) * YP_BYTES + k * UMMA_K * 2);
-                  umma_bf16(d, ad, bd, idesc1, (pr | kb | k) != 0);
+              for (int kb = 0; kb < 2; ++kb) {
+                if (kb < kblocks) {
+#pragma unroll
+                  for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t ad = umma_desc_pack(x_lo + (((kb * NP + pa) * XP_BYTES + k * UMMA_K * 2) >> 4));
+                    const uint64_t bd = umma_desc_pack(yb + (((kb * NP + pb) * YP_BYTES + k * UMMA_K * 2) >> 4));
+                    umma_bf16_lead(d, ad, bd, idesc1, (pr | kb | k) != 0);
+                  }
                 }
               }
             }
-            umma_commit(s_full + buf);
+            umma_commit_lead(s_full + buf);
             ++it1;
             if (++s1_stage == YSTAGES) {
               s1_stage = 0;
@@ -191,29 +197,30 @@ __global__ void __launch_bounds__(THREADS, 1)
               o_phase ^= 1;
             }
             tc_fence_after();
-            const uint32_t e_base = smem_u32(e_bufs + buf * E_BUF_BYTES);
-            const uint32_t y_base = smem_u32(y_ring + s2_stage * Y_STAGE_BYTES);
-            const uint32_t d = tmem_base + O_COL;
+            const uint32_t eb = e_lo + buf * (E_BUF_BYTES >> 4);
+            const uint32_t yb = y_lo_mn + s2_stage * (Y_STAGE_BYTES >> 4);
+            const uint32_t d = tmem_u + O_COL;
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
+              const int pa = pr >> 1, pb = pr & 1;
 #pragma unroll
               for (int k = 0; k < SBN / UMMA_K; ++k) {
                 // A: E plane, K-major (K = streamed index, 16 columns = 32 bytes per step)
-                const uint64_t ad = umma_desc(e_base + pa[pr] * EP_BYTES + k * UMMA_K * 2);
+                const uint64_t ad = umma_desc_pack(eb + ((pa * EP_BYTES + k * UMMA_K * 2) >> 4));
                 // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*YP_BYTES apart),
                 //    K = streamed index (rows of 128 bytes, 16 rows = 2048 bytes per step)
-                const uint64_t bd = umma_desc_mn(y_base + pb[pr] * YP_BYTES + k * UMMA_K * 128, NP * YP_BYTES, 1024);
-                umma_bf16(d, ad, bd, idesc2, (j != 1) || (pr | k) != 0);
+                const uint64_t bd = umma_desc_pack(yb + ((pb * YP_BYTES + k * UMMA_K * 128) >> 4));
+                umma_bf16_lead(d, ad, bd, idesc2, (j != 1) || (pr | k) != 0);
               }
             }
-            umma_commit(e_empty + buf);
-            umma_commit(y_empty + s2_stage);
+            umma_commit_lead(e_empty + buf);
+            umma_commit_lead(y_empty + s2_stage);
             ++it2;
             if (++s2_stage == YSTAGES) s2_stage = 0;
           }
         }
-        umma_commit(o_full);
-        umma_commit(x_empty);
+        umma_commit_lead(o_full);
+        umma_commit_lead(x_empty);
       }
     }
   } else {  // ---- epilogue warps 2..9 ----

@@ -94,6 +94,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- issue-side helpers for a WARP-UNIFORM MMA loop --------------------------------------------------------------
+// The whole MMA warp runs the loop and only the tcgen05 instructions are predicated on the leader lane: with uniform
+// control flow the descriptor arithmetic stays in the uniform datapath (a loop under `if (lane == 0)` costs ~20 SASS
+// instructions per MMA -- ELECT / R2UR.BROADCAST / 64-bit descriptor assembly -- and made the issuing thread, not the
+// tensor pipe, the bottleneck: 940 instructions per 36-MMA tile at ~4.7 clocks each).
+// Descriptors are (lo, hi) pairs: hi is constant per layout, lo = base_lo + (byte offset >> 4).
+constexpr uint32_t UMMA_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, 128-byte swizzle
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(UMMA_DESC_HI));
+  return d;
+}
+// one lane of a converged warp (elect.sync): the form the compiler turns into ELECT + a uniformly predicated UTCHMMA
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t"
+      "}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_lead(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (elect_one()) umma_bf16(tmem_d, adesc, bdesc, idesc, acc);
+}
+__device__ __forceinline__ void umma_commit_lead(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
