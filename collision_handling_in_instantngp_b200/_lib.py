@@ -84,6 +84,10 @@ SIGNATURES = {
     "gngf_mlp3_bwd_workspace_floats": (c_int64, [c_int32, c_int32]),
     "gngf_mlp3_bwd": (c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gngf_mlp3_tc_supported": (c_int, [c_int32, c_int32, c_int32, c_int32]),
+    "gngf_mlp3_tc_fwd": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gngf_mlp3_tc_bwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
+                                 _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
     "gngf_count_distinct_workspace_words": (c_int64, [c_int32, c_int32, c_int64]),

@@ -265,6 +265,8 @@ class ForwardState:
     cnt: Optional[torch.Tensor] = None                           # (S,) int32
     mlp_acts: List[torch.Tensor] = field(default_factory=list)   # enc, a1, ..., rgb  (enc, rgb when fused)
     mlp_fused: bool = False
+    mlp_tc: bool = False                                         # decoder ran on the tensor cores (k6_mlp_tc.cu)
+    mlp_masks: Optional[torch.Tensor] = None                     # (P,4) int32 ReLU pattern of the hidden layers
     err_flag: Optional[torch.Tensor] = None
 
 
@@ -292,6 +294,8 @@ def _streaming_ok(cfg, U, T, k, kd) -> bool:
         return bool(FORCE_STREAMING)
     return U * T >= STREAM_MIN_ELEMENTS
 
+
+MLP_TENSOR_CORES = True           # decoder through k6_mlp_tc.cu (tcgen05); False: the fp32 CUDA-core kernels of k6_mlp.cu
 
 SMALL_LATTICE_MAX_NODES = 8192    # fused per-node HPD kernels (k2_hpd_small.cu) below this many nodes
 
@@ -402,9 +406,17 @@ class GNGFPath(torch.autograd.Function):
             # K6: one kernel, hidden activations never leave the SM (recomputed in backward)
             C = mlp_w[2].shape[0]
             rgb_out = torch.empty((P, C), dtype=torch.float32, device=dev)
-            call("gngf_mlp3_fwd", enc.data_ptr(), P, L * F, C, int(cfg.leaky), mlp_w[0].data_ptr(), mlp_b[0].data_ptr(),
-                 mlp_w[1].data_ptr(), mlp_b[1].data_ptr(), mlp_w[2].data_ptr(), mlp_b[2].data_ptr(), rgb_out.data_ptr(),
-                 st)
+            state.mlp_tc = bool(MLP_TENSOR_CORES)
+            if state.mlp_tc:
+                # (P,4) words: the ReLU pattern of the two hidden layers, which the backward gates with
+                state.mlp_masks = torch.empty((P, 4), dtype=torch.int32, device=dev)
+                call("gngf_mlp3_tc_fwd", enc.data_ptr(), P, L * F, C, int(cfg.leaky), mlp_w[0].data_ptr(),
+                     mlp_b[0].data_ptr(), mlp_w[1].data_ptr(), mlp_b[1].data_ptr(), mlp_w[2].data_ptr(),
+                     mlp_b[2].data_ptr(), rgb_out.data_ptr(), state.mlp_masks.data_ptr(), st)
+            else:
+                call("gngf_mlp3_fwd", enc.data_ptr(), P, L * F, C, int(cfg.leaky), mlp_w[0].data_ptr(),
+                     mlp_b[0].data_ptr(), mlp_w[1].data_ptr(), mlp_b[1].data_ptr(), mlp_w[2].data_ptr(),
+                     mlp_b[2].data_ptr(), rgb_out.data_ptr(), st)
             acts = [enc, rgb_out]
         else:
             acts = [enc]
@@ -463,12 +475,20 @@ class GNGFPath(torch.autograd.Function):
         if state.mlp_fused:
             C = rgb.shape[1]
             denc = torch.empty((P, L * F), dtype=torch.float32, device=dev)
-            work = torch.empty(_lib.load().gngf_mlp3_bwd_workspace_floats(L * F, C), dtype=torch.float32, device=dev)
-            call("gngf_mlp3_bwd", acts[0].data_ptr(), grad_rgb.data_ptr(), P, L * F, C, int(cfg.leaky),
-                 mlp_w[0].data_ptr(), mlp_b[0].data_ptr(), mlp_w[1].data_ptr(), mlp_b[1].data_ptr(), mlp_w[2].data_ptr(),
-                 mlp_b[2].data_ptr(), denc.data_ptr(), g_mlp_w[0].data_ptr(), g_mlp_b[0].data_ptr(),
-                 g_mlp_w[1].data_ptr(), g_mlp_b[1].data_ptr(), g_mlp_w[2].data_ptr(), g_mlp_b[2].data_ptr(),
-                 work.data_ptr(), st)
+            if state.mlp_tc:
+                call("gngf_mlp3_tc_bwd", acts[0].data_ptr(), rgb.data_ptr(), grad_rgb.data_ptr(), P, L * F, C,
+                     int(cfg.leaky), mlp_w[0].data_ptr(), mlp_b[0].data_ptr(), mlp_w[1].data_ptr(), mlp_b[1].data_ptr(),
+                     mlp_w[2].data_ptr(), state.mlp_masks.data_ptr(), denc.data_ptr(), g_mlp_w[0].data_ptr(),
+                     g_mlp_b[0].data_ptr(), g_mlp_w[1].data_ptr(), g_mlp_b[1].data_ptr(), g_mlp_w[2].data_ptr(),
+                     g_mlp_b[2].data_ptr(), st)
+            else:
+                work = torch.empty(_lib.load().gngf_mlp3_bwd_workspace_floats(L * F, C), dtype=torch.float32,
+                                   device=dev)
+                call("gngf_mlp3_bwd", acts[0].data_ptr(), grad_rgb.data_ptr(), P, L * F, C, int(cfg.leaky),
+                     mlp_w[0].data_ptr(), mlp_b[0].data_ptr(), mlp_w[1].data_ptr(), mlp_b[1].data_ptr(),
+                     mlp_w[2].data_ptr(), mlp_b[2].data_ptr(), denc.data_ptr(), g_mlp_w[0].data_ptr(),
+                     g_mlp_b[0].data_ptr(), g_mlp_w[1].data_ptr(), g_mlp_b[1].data_ptr(), g_mlp_w[2].data_ptr(),
+                     g_mlp_b[2].data_ptr(), work.data_ptr(), st)
         else:
             dz = torch.empty_like(rgb)
             call("gngf_sigmoid_bwd", grad_rgb.data_ptr(), rgb.data_ptr(), rgb.numel(), dz.data_ptr(), st)

@@ -174,6 +174,25 @@ int gngf_mlp3_bwd(const float* enc, const float* drgb, int64_t P, int32_t in_dim
                   float* denc, float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, float* workspace,
                   void* stream);
 
+/* K6 on the tensor cores (k6_mlp_tc.cu): the same decoder (models.py:382-392, 468-470) as chains of tcgen05 products,
+ * 128-point tiles, operands as bf16 planes of the fp32 values kept in shared memory between layers.
+ *   forward : three planes / six partial products per k-step (~1.5e-6 relative);
+ *   backward: two planes / three partial products (~1e-5 relative; gradient bar 1e-4).  It re-reads the forward's
+ *   output `rgb` (P,out_dim) instead of recomputing the last layer and gates with the forward's own ReLU pattern
+ *   `masks` (P,4) uint32 -- words [layer*2 + half], bit j = pre-activation of hidden unit half*32+j was positive;
+ *   the forward writes them when `masks` is non-NULL -- recomputes the hidden activation VALUES, reads every
+ *   shared-memory tile K-major for the dX products and MN-major for the dW products, accumulates dW in TMEM over all
+ *   tiles of a persistent CTA and adds (red.global) into dw0/db0/dw1/db1/dw2/db2 -- which must be valid accumulators
+ *   (zero-initialised or holding earlier contributions); dw1 16-byte aligned.                                     */
+int gngf_mlp3_tc_supported(int32_t in_dim, int32_t h1, int32_t h2, int32_t out_dim);
+int gngf_mlp3_tc_fwd(const float* enc, int64_t P, int32_t in_dim, int32_t out_dim, int32_t leaky, const float* w0,
+                     const float* b0, const float* w1, const float* b1, const float* w2, const float* b2, float* rgb,
+                     uint32_t* masks, void* stream);
+int gngf_mlp3_tc_bwd(const float* enc, const float* rgb, const float* drgb, int64_t P, int32_t in_dim, int32_t out_dim,
+                     int32_t leaky, const float* w0, const float* b0, const float* w1, const float* b1, const float* w2,
+                     const uint32_t* masks, float* denc, float* dw0, float* db0, float* dw1, float* db1, float* dw2,
+                     float* db2, void* stream);
+
 /* ---- loss assembly (utils.py:78-174 Loss + functions.py:243-245) with its adjoints, one kernel ---------------
  * total = l_mse * MSE(rgb, target) + sum_l (l_js_kl * level_l + coll_l), level_l = -(gamma+epsilon) JS_l + epsilon KL_l
  * of pbar_l = colsum_l / rows against the uniform distribution.  out (2+L): [0] total, [1] mse, [2+l] level_l;

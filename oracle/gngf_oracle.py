@@ -291,9 +291,11 @@ def gngf_forward(params: dict, x: np.ndarray, cfg: dict) -> dict:
 # --------------------------------------------------------------------------------------------------------
 # whole path: backward (closed form of what autograd does for a-4 ... a-11 + Loss)   SURVEY.md 8a-14
 # --------------------------------------------------------------------------------------------------------
-def _mlp_backward(acts, weights, dz_last, relu_like=True, leaky=False):
+def _mlp_backward(acts, weights, dz_last, relu_like=True, leaky=False, masks=None):
     """acts[i] is the input of layer i; dz_last is the grad wrt the last layer's pre-activation.
-    Returns (dW list, db list, dX of layer 0)."""
+    Returns (dW list, db list, dX of layer 0).  masks (optional): masks[i] (rows, width_i) booleans replacing
+    `acts[i] > 0` for i >= 1 -- differentiates a GIVEN ReLU pattern (a forward whose pre-activations differ from this
+    one's at rounding level sits on the other side of a kink for a few units; the derivative is discontinuous there)."""
     n = len(weights)
     dws, dbs = [None] * n, [None] * n
     dz = dz_last
@@ -304,11 +306,11 @@ def _mlp_backward(acts, weights, dz_last, relu_like=True, leaky=False):
         dbs[i] = dz2.sum(axis=0)
         dx = dz2 @ weights[i]
         if i > 0:
-            h = a
+            pos = (a > 0) if masks is None or masks[i] is None else masks[i].reshape(a.shape)
             if leaky:
-                dz = np.where(h > 0, dx, dx * dx.dtype.type(0.01))
+                dz = np.where(pos, dx, dx * dx.dtype.type(0.01))
             else:
-                dz = dx * (h > 0)
+                dz = dx * pos
         else:
             dz = dx
     return dws, dbs, dz
@@ -327,7 +329,9 @@ def gngf_backward(params: dict, x: np.ndarray, target: np.ndarray, cfg: dict, fw
     # MSE -> sigmoid
     dout = loss_cfg["l_mse"] * 2 * (rgb - target) / dt.type(rgb.size)
     dz = dout * rgb * (1 - rgb)
-    dws, dbs, denc = _mlp_backward(fwd["mlp_acts"][:-1], params["mlp_w"], dz, leaky=cfg.get("leaky", False))
+    # cfg["force_mlp_masks"]: [None, (P,w1) bool, (P,w2) bool] -- differentiate a given ReLU pattern (see _mlp_backward)
+    dws, dbs, denc = _mlp_backward(fwd["mlp_acts"][:-1], params["mlp_w"], dz, leaky=cfg.get("leaky", False),
+                                   masks=cfg.get("force_mlp_masks"))
     grads["mlp_w"], grads["mlp_b"] = dws, dbs
 
     F = params["tables"][0].shape[1]

@@ -93,3 +93,13 @@ def run_step(net, g, materialize=False):
     st = net.last_state
     out["state"] = st
     return out
+
+
+def decoder_masks(state):
+    """The decoder's ReLU pattern as the tensor-core forward recorded it: [None, (P,64) bool, (P,64) bool]
+    (k6_mlp_tc.cu: words [layer*2 + half], bit j = unit half*32 + j), or None when the fp32 decoder ran."""
+    if getattr(state, "mlp_masks", None) is None or not state.mlp_tc:
+        return None
+    m = state.mlp_masks.cpu().numpy().view(np.uint32)                 # (P,4)
+    bits = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)   # (P,4,32)
+    return [None, bits[:, 0:2].reshape(-1, 64), bits[:, 2:4].reshape(-1, 64)]

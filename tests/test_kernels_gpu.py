@@ -191,6 +191,55 @@ def test_fused_decoder_mlp(P, IN, OUT, leaky):
         assert rel_err(gb[i].cpu().numpy(), dbs[i]) < 2e-5, i
 
 
+@pytest.mark.parametrize("P,IN,OUT,leaky", [(1000, 8, 3, 0), (57404, 8, 3, 0), (333, 32, 3, 1), (129, 6, 1, 0),
+                                             (4097, 64, 3, 0), (1, 8, 3, 0), (40000, 32, 3, 0), (700, 20, 4, 1)])
+def test_tensor_core_decoder_mlp(P, IN, OUT, leaky):
+    """k6_mlp_tc.cu (tcgen05 chains, operands as bf16 planes kept in shared memory) against float64.
+    Forward: three planes, bar 1e-5; backward: two planes, bar 1e-4 (gradients accumulate into the given buffers).
+    The backward gates with the ReLU pattern the forward recorded; the float64 reference differentiates that same
+    pattern (it may differ from float64's own on units whose pre-activation is within the forward's rounding error
+    of zero -- asserted to be a < 1e-5 fraction)."""
+    from collision_handling_in_instantngp_b200 import _lib
+    rng = np.random.default_rng(P + IN)
+    enc = (rng.standard_normal((P, IN)) * 0.5).astype(np.float32)
+    ws = [(rng.standard_normal((o, i)) / np.sqrt(i)).astype(np.float32) for i, o in [(IN, 64), (64, 64), (64, OUT)]]
+    bs = [(rng.standard_normal(o) * 0.1).astype(np.float32) for o in (64, 64, OUT)]
+    drgb = rng.standard_normal((P, OUT)).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    enc_t, ws_t, bs_t, drgb_t = t(enc), [t(w) for w in ws], [t(b) for b in bs], t(drgb)
+    rgb = torch.empty((P, OUT), device=DEV)
+    masks_t = torch.empty((P, 4), dtype=torch.int32, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("gngf_mlp3_tc_fwd", enc_t.data_ptr(), P, IN, OUT, leaky, ws_t[0].data_ptr(), bs_t[0].data_ptr(),
+              ws_t[1].data_ptr(), bs_t[1].data_ptr(), ws_t[2].data_ptr(), bs_t[2].data_ptr(), rgb.data_ptr(),
+              masks_t.data_ptr(), st)
+    w64, b64 = [w.astype(np.float64) for w in ws], [b.astype(np.float64) for b in bs]
+    acts = O.decoder_forward(enc.astype(np.float64), w64, b64, bool(leaky))
+    assert rel_err(rgb.cpu().numpy(), acts[-1]) < 1e-5
+    m = masks_t.cpu().numpy().view(np.uint32)
+    bits = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+    masks = [None, bits[:, 0:2].reshape(P, 64), bits[:, 2:4].reshape(P, 64)]
+    for i in (1, 2):
+        assert (masks[i] != (acts[i] > 0)).mean() < 1e-5
+    denc = torch.empty((P, IN), device=DEV)
+    gw0 = [rng.standard_normal(w.shape).astype(np.float32) for w in ws]      # accumulated into
+    gb0 = [rng.standard_normal(b.shape).astype(np.float32) for b in bs]
+    gw, gb = [t(a) for a in gw0], [t(a) for a in gb0]
+    _lib.call("gngf_mlp3_tc_bwd", enc_t.data_ptr(), rgb.data_ptr(), drgb_t.data_ptr(), P, IN, OUT, leaky,
+              ws_t[0].data_ptr(), bs_t[0].data_ptr(), ws_t[1].data_ptr(), bs_t[1].data_ptr(), ws_t[2].data_ptr(),
+              masks_t.data_ptr(), denc.data_ptr(), gw[0].data_ptr(), gb[0].data_ptr(), gw[1].data_ptr(),
+              gb[1].data_ptr(), gw[2].data_ptr(), gb[2].data_ptr(), st)
+    dz = drgb.astype(np.float64) * acts[-1] * (1 - acts[-1])
+    dws, dbs, dx = O._mlp_backward(acts[:-1], w64, dz, leaky=bool(leaky), masks=masks)
+    assert rel_err(denc.cpu().numpy(), dx) < 1e-4
+    for i in range(3):
+        # the random starting contents limit what float32 accumulation can resolve: compare the increments
+        scale = max(np.abs(dws[i]).max(), 1.0)
+        assert np.abs(gw[i].cpu().numpy().astype(np.float64) - gw0[i] - dws[i]).max() < 1e-4 * scale, i
+        scale = max(np.abs(dbs[i]).max(), 1.0)
+        assert np.abs(gb[i].cpu().numpy().astype(np.float64) - gb0[i] - dbs[i]).max() < 1e-4 * scale, i
+
+
 def test_generic_decoder_shape_uses_linear_layers():
     """A decoder that is not IN-64-64-OUT goes through gngf_linear_fwd/bwd and still matches the oracle."""
     from golden_util import loss_cfg, oracle_cfg, params_of
