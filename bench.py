@@ -247,6 +247,7 @@ def run_ours(args, w):
     from collision_handling_in_instantngp_b200 import _lib, dp, launch_count
     from collision_handling_in_instantngp_b200.loss import fused_total_loss as total_loss
     from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+    from collision_handling_in_instantngp_b200.optim import FusedAdam
     from collision_handling_in_instantngp_b200.trainer import GraphedTrainer
 
     rank = int(os.environ.get("RANK", "0"))
@@ -265,11 +266,11 @@ def run_ours(args, w):
     h, wd = w["lattice_hw"]
     m = max(h, wd) - 1
     net.set_coord_bounds((0.0, 0.0), ((h - 1) / m, (wd - 1) / m))
-    opt = torch.optim.Adam(                                                     # functions.py:96-127
+    opt = FusedAdam(                                                            # functions.py:96-127, one launch
         [{"params": net.encoding.parameters(), "lr": w["lr"]["encoding"], "weight_decay": w["wd"]["encoding"]},
          {"params": net.HPD.parameters(), "lr": w["lr"]["hpd"], "weight_decay": w["wd"]["hpd"]},
          {"params": net.mlp.parameters(), "lr": w["lr"]["mlp"], "weight_decay": w["wd"]["mlp"]}],
-        betas=(0.9, 0.99), eps=1e-15, capturable=True, fused=True)
+        betas=(0.9, 0.99), eps=1e-15)
     dp.enable_gradient_allreduce()          # N > 1: one in-place NCCL all-reduce of the flat gradient buffer
 
     x_np, y_np = make_inputs(w, 65535, rank)

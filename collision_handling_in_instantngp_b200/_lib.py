@@ -51,6 +51,14 @@ class Tables(Structure):
     _fields_ = [("ptr", c_void_p * MAX_LEVELS)]
 
 
+class AdamTensor(Structure):
+    """gngf_adam_tensor (include/gngf.h)."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64), ("lr", c_float),
+                ("weight_decay", c_float)]
+
+
+ADAM_MAX_TENSORS = 64
+
 _P = c_void_p  # device pointers travel as integers (tensor.data_ptr())
 
 # name -> (restype, argtypes); every symbol declared in include/gngf.h appears here
@@ -88,6 +96,8 @@ SIGNATURES = {
     "gngf_mlp3_tc_fwd": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_mlp3_tc_bwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gngf_peer_allreduce": (c_int, [_P, _P, c_int32, c_int32, _P, _P, c_int64, c_int64, c_int32, c_float, _P, _P]),
+    "gngf_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_float, c_float, c_float, _P, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
     "gngf_count_distinct_workspace_words": (c_int64, [c_int32, c_int32, c_int64]),

@@ -1,0 +1,115 @@
+// f-3: the optimizer step that follows every backward (functions.py:96-127, 281: torch.optim.Adam with per-group
+// learning rate / weight decay, betas (0.9, 0.99), eps 1e-15) as ONE launch over all parameter tensors.
+// torch's fused Adam issues one multi-tensor launch per parameter group plus a step-counter launch per group (6
+// launches, ~33 us at the published configuration where the whole step is ~0.25 ms); here the tensor descriptors
+// travel in kernel-parameter space, a block finds its tensor with a search over the chunk prefix sums, and the step
+// counter is a device scalar advanced by the last block to finish (CUDA-graph friendly: no host state).
+//   g' = g + wd p ;  m += (1 - b1)(g' - m) ;  v = b2 v + (1 - b2) g'^2 ;
+//   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)            (torch.optim.Adam, amsgrad = False)
+#include "common.cuh"
+
+namespace gngf {
+
+constexpr int ADAM_THREADS = 256;
+constexpr int ADAM_CHUNK = ADAM_THREADS * 4 * 4;   // elements per block: 4 float4 per thread
+
+struct AdamArgs {
+  gngf_adam_tensor t[GNGF_ADAM_MAX_TENSORS];
+  int64_t chunk_end[GNGF_ADAM_MAX_TENSORS];   // prefix sums of the tensors' chunk counts
+  int count;
+};
+
+__global__ void __launch_bounds__(ADAM_THREADS)
+    adam_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float eps, int* __restrict__ step,
+                unsigned int* __restrict__ ticket) {
+  const int t_now = *step + 1;
+  // which tensor does this block's chunk belong to?
+  const int64_t b = blockIdx.x;
+  int lo = 0, hi = a.count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (b < a.chunk_end[mid]) hi = mid; else lo = mid + 1;
+  }
+  const gngf_adam_tensor& T = a.t[lo];
+  const int64_t chunk = b - (lo ? a.chunk_end[lo - 1] : 0);
+  const float bc1 = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), t_now));
+  const float bc2 = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), t_now));
+  const float step_size = T.lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float wd = T.weight_decay, omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  const int64_t base = chunk * ADAM_CHUNK;
+  const bool vec = ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) | reinterpret_cast<uintptr_t>(T.m) |
+                     reinterpret_cast<uintptr_t>(T.v)) & 15) == 0;
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    g = fmaf(wd, p, g);
+    m = fmaf(omb1, g - m, m);
+    v = fmaf(beta2, v, omb2 * g * g);
+    p -= step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + eps));
+  };
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = base + (static_cast<int64_t>(r) * ADAM_THREADS + threadIdx.x) * 4;
+    if (i >= T.n) break;
+    if (vec && i + 4 <= T.n) {
+      float4 p = *reinterpret_cast<float4*>(T.p + i);
+      const float4 g = *reinterpret_cast<const float4*>(T.g + i);
+      float4 m = *reinterpret_cast<float4*>(T.m + i);
+      float4 v = *reinterpret_cast<float4*>(T.v + i);
+      upd(p.x, g.x, m.x, v.x);
+      upd(p.y, g.y, m.y, v.y);
+      upd(p.z, g.z, m.z, v.z);
+      upd(p.w, g.w, m.w, v.w);
+      *reinterpret_cast<float4*>(T.p + i) = p;
+      *reinterpret_cast<float4*>(T.m + i) = m;
+      *reinterpret_cast<float4*>(T.v + i) = v;
+    } else {
+      for (int64_t j = i; j < min(i + 4, T.n); ++j) {
+        float p = T.p[j], m = T.m[j], v = T.v[j];
+        upd(p, T.g[j], m, v);
+        T.p[j] = p;
+        T.m[j] = m;
+        T.v[j] = v;
+      }
+    }
+  }
+  // the last block to finish advances the step counter (every block has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(ticket, 1u);
+    if (done == gridDim.x - 1) {
+      *step = t_now;
+      *ticket = 0u;
+    }
+  }
+}
+
+}  // namespace gngf
+
+extern "C" {
+
+int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t* step,
+                   uint32_t* ticket, void* stream) {
+  if (count < 0 || count > GNGF_ADAM_MAX_TENSORS || !step || !ticket) return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::AdamArgs a;
+  int64_t chunks = 0;
+  int used = 0;
+  for (int i = 0; i < count; ++i) {
+    if (tensors[i].n < 0) return GNGF_ERR_INVALID_ARGUMENT;
+    if (tensors[i].n == 0) continue;
+    if (!tensors[i].p || !tensors[i].g || !tensors[i].m || !tensors[i].v) return GNGF_ERR_INVALID_ARGUMENT;
+    a.t[used] = tensors[i];
+    chunks += gngf::ceil_div(tensors[i].n, gngf::ADAM_CHUNK);
+    a.chunk_end[used] = chunks;
+    ++used;
+  }
+  a.count = used;
+  if (used == 0) return GNGF_OK;
+  if (chunks >= (1ll << 31)) return GNGF_ERR_UNSUPPORTED;
+  gngf::adam_kernel<<<static_cast<unsigned>(chunks), gngf::ADAM_THREADS, 0, gngf::as_stream(stream)>>>(a, beta1, beta2, eps,
+                                                                                                      step, ticket);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+}  // extern "C"

@@ -9,6 +9,11 @@ on its shard of the coordinates.  Two exchange steps per 
 
 The reference has no distributed code; this is the B200 data-parallel form of functions.py:183-281.
 Works with any torch.distributed backend (NCCL on the GPUs; gloo in the CPU tests of the host logic).
+
+On NVLink-connected GPUs both exchanges go through `PeerAllReduce` when the buffer is small (the published
+configuration: 4 KB of column sums, ~200 KB of gradients): a one-shot all-reduce kernel over symmetric peer memory
+(k10_allreduce.cu) whose cost is one NVLink round trip instead of NCCL's launch + protocol latency; large buffers
+(the 268 MB output-layer gradient at T = 2^19) stay with NCCL, which is bandwidth-optimal.
 """
 from __future__ import annotations
 
@@ -16,13 +21,93 @@ import torch
 import torch.distributed as dist
 
 
+PEER_MAX_BYTES = 512 << 10        # buffers up to this size use the one-shot peer kernel (measured: 14 vs 19 us at 225 KB,
+                                  # 22 vs 18 us at 1 MB on 2 x B200); larger ones NCCL
+_PEER = {}                        # (group name, device) -> PeerAllReduce or None (unavailable)
+
+
+class PeerAllReduce:
+    """One-shot all-reduce over NVLink peer memory (k10_allreduce.cu).  Every rank of `group` must construct it and
+    call it collectively, with the same sizes in the same order; calls are asynchronous on the current stream and
+    can be captured in a CUDA graph."""
+
+    def __init__(self, max_floats: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self._lib = _lib
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.cap = (int(max_floats) + 3) & ~3
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.stage = symm_mem.empty(2 * self.cap, dtype=torch.float32, device=dev)
+        self.stage.zero_()
+        self.handle = symm_mem.rendezvous(self.stage, group)
+        self.stage_ptrs = int(self.handle.buffer_ptrs_dev)
+        self.signal_ptrs = int(self.handle.signal_pad_ptrs_dev)
+        # slots (block, source rank) of 4 bytes each in the signal pad
+        self.max_blocks = max(1, min(64, int(self.handle.signal_pad_size) // 4 // self.world))
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group)             # every pad / staging buffer is zeroed before the first signal arrives
+
+    def __call__(self, inp: torch.Tensor, out: torch.Tensor = None, scale: float = 1.0) -> torch.Tensor:
+        n = inp.numel()
+        if n > self.cap or inp.dtype != torch.float32 or not inp.is_contiguous():
+            raise ValueError(f"PeerAllReduce: {n} floats exceed the staging capacity {self.cap} (or bad dtype/layout)")
+        if out is None:
+            out = torch.empty_like(inp)
+        self._lib.call("gngf_peer_allreduce", self.stage_ptrs, self.signal_ptrs, self.rank, self.world, inp.data_ptr(),
+                       out.data_ptr(), n, self.cap, self.max_blocks, float(scale), self.state.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+        return out
+
+    def timed_out(self) -> bool:
+        return bool(self.state[2].item())
+
+
+def peer_allreduce_for(group=None):
+    """The process-wide PeerAllReduce of `group` (created collectively on first use), or None when symmetric memory
+    is unavailable (not NCCL / no peer access / CPU tensors): callers then use the process group's all_reduce."""
+    if not dist.is_initialized() or not torch.cuda.is_available():
+        return None
+    g = group if group is not None else dist.group.WORLD
+    if dist.get_backend(g) != "nccl":
+        return None
+    key = (id(g), torch.cuda.current_device())
+    if key not in _PEER:
+        ok = torch.zeros(1, device="cuda")
+        try:
+            comm = PeerAllReduce(PEER_MAX_BYTES // 4, g)
+            ok += 1
+        except Exception as e:      # noqa: BLE001 -- any failure on any rank must disable it on every rank
+            comm = None
+            import warnings
+            warnings.warn(f"PeerAllReduce unavailable ({type(e).__name__}: {e}); using NCCL all_reduce")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)
+        _PEER[key] = comm if float(ok.item()) > 0 else None
+    return _PEER[key]
+
+
+def all_reduce_sum_(t: torch.Tensor, scale: float = 1.0, group=None) -> torch.Tensor:
+    """In-place scale * sum over ranks of a float32 CUDA tensor: peer kernel when small, NCCL otherwise."""
+    comm = peer_allreduce_for(group) if t.is_cuda else None
+    if comm is not None and t.dtype == torch.float32 and t.is_contiguous() and t.numel() * 4 <= PEER_MAX_BYTES \
+            and t.data_ptr() % 16 == 0:
+        comm(t, out=t, scale=scale)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if scale != 1.0:
+            t.mul_(scale)
+    return t
+
+
 class _AllReduceSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, group):
         ctx.world = dist.get_world_size(group)
-        out = t.clone()
-        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-        return out
+        return all_reduce_sum_(t.clone(), 1.0, group)
 
     @staticmethod
     def backward(ctx, g):
@@ -83,10 +168,10 @@ def enable_gradient_allreduce(group=None) -> None:
         ops.GRAD_REDUCE_HOOK = None
         return
     world = dist.get_world_size(group)
+    peer_allreduce_for(group)       # collective set-up now, not inside the first (possibly graph-captured) step
 
     def hook(flat: torch.Tensor) -> None:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world)
+        all_reduce_sum_(flat, 1.0 / world, group)
 
     ops.GRAD_REDUCE_HOOK = hook
 

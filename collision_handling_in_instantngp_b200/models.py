@@ -323,7 +323,7 @@ class GeneralNeuralGaugeFields(nn.Module):
             counts = self._calc_counts_per_level(hashed, ops.corners_fwd(x, lat)[1]) if should_calc_counts else []
             return rgb, None, hashed, counts
         rgb, colsum, uvals = ops.GNGFPath.apply(x, state, *params)
-        idx_topk = ops.gather_rows(x, lat, state.utopi)                               # (P,L,4,K) int64
+        idx_topk = state.idx_topk                                                     # (P,L,4,K) int64
         counts = []
         if should_calc_counts:                                                        # models.py:431-439
             counts = self._calc_counts_per_level(idx_topk[..., 0], ops.corners_fwd(x, lat)[1])

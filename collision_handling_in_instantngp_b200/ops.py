@@ -32,6 +32,51 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- intra-step concurrency -------------------------------------------------------------------------------------
+# At the published batch size every kernel of the step is a few tens of microseconds and fills a fraction of the
+# chip, so independent kernels are forked onto side streams (the API-output gather of idx_topk, the column sums the
+# loss needs, the per-layer weight-gradient products of the HPD) and joined before their results are consumed.
+# Under CUDA-graph capture the forks become parallel branches of the graph.  Buffers are always allocated on the
+# main stream (the caching allocator ties a block to the stream it was allocated on); only launches move.
+CONCURRENT = True
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, i: int) -> torch.cuda.Stream:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), i)
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return s
+
+
+class _Fork:
+    """with _Fork(dev, i): ...launches...   -- runs the block on side stream i after everything queued so far on the
+    current stream; `.join()` makes the current stream wait for it.  With CONCURRENT off it is a no-op."""
+
+    def __init__(self, dev, i: int):
+        self.on = CONCURRENT
+        if self.on:
+            self.main = torch.cuda.current_stream(dev)
+            self.side = _side_stream(dev, i)
+            self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.main)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -217,14 +262,16 @@ def count_distinct(indices: torch.Tensor, value_range: int):
     return uniq, outliers
 
 
-def gather_rows(x, lat: Lattice, uvals: torch.Tensor) -> torch.Tensor:
+def gather_rows(x, lat: Lattice, uvals: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(P,L,4,N) rows of a per-node array; int32 input gives the int64 API dtype."""
     P, N = x.shape[0], uvals.shape[1]
     if uvals.dtype == torch.int32:
-        out = torch.empty((P, lat.num_levels, 4, N), dtype=torch.int64, device=x.device)
+        if out is None:
+            out = torch.empty((P, lat.num_levels, 4, N), dtype=torch.int64, device=x.device)
         call("gngf_lattice_gather_rows_i64", x.data_ptr(), P, lat, uvals.data_ptr(), N, out.data_ptr(), _stream())
     else:
-        out = torch.empty((P, lat.num_levels, 4, N), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((P, lat.num_levels, 4, N), dtype=torch.float32, device=x.device)
         call("gngf_lattice_gather_rows", x.data_ptr(), P, lat, uvals.data_ptr(), N, out.data_ptr(), _stream())
     return out
 
@@ -267,6 +314,7 @@ class ForwardState:
     mlp_fused: bool = False
     mlp_tc: bool = False                                         # decoder ran on the tensor cores (k6_mlp_tc.cu)
     mlp_masks: Optional[torch.Tensor] = None                     # (P,4) int32 ReLU pattern of the hidden layers
+    idx_topk: Optional[torch.Tensor] = None                      # (P,L,4,K) int64, the API output (models.py:476-484)
     err_flag: Optional[torch.Tensor] = None
 
 
@@ -387,6 +435,11 @@ class GNGFPath(torch.autograd.Function):
             colsum = uvals = None
         else:
             hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev, cfg, state)
+            # API output idx_topk (P,L,4,K) int64: nothing in the step reads it -> side stream, joined at the end
+            state.idx_topk = torch.empty((P, L, 4, K), dtype=torch.int64, device=dev)
+            fork_idx = _Fork(dev, 0)
+            with fork_idx:
+                gather_rows(x, lat, state.utopi, out=state.idx_topk)
             S = lat.num_level_nodes
             nfeat = torch.empty((S, F), dtype=torch.float32, device=dev)
             call("gngf_node_features_fwd", lat, tab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
@@ -399,7 +452,9 @@ class GNGFPath(torch.autograd.Function):
             call("gngf_encode_fwd", x.data_ptr(), P, lat, F, nfeat.data_ptr(), enc.data_ptr(), state.cnt.data_ptr(),
                  state.err_flag.data_ptr(), st)
             uvals = state.utopv if cfg.topk_only else state.uprobs
-            call("gngf_lattice_colsum", lat, state.cnt.data_ptr(), uvals.data_ptr(), N, colsum.data_ptr(), st)
+            fork_col = _Fork(dev, 1)      # only the loss reads the column sums: overlaps the decoder
+            with fork_col:
+                call("gngf_lattice_colsum", lat, state.cnt.data_ptr(), uvals.data_ptr(), N, colsum.data_ptr(), _stream())
 
         state.mlp_fused = _mlp3_supported(mlp_w)
         if state.mlp_fused:
@@ -425,6 +480,9 @@ class GNGFPath(torch.autograd.Function):
             for i in range(nm):
                 h = linear_fwd(h, mlp_w[i], mlp_b[i], hidden_act if i < nm - 1 else ACT_SIGMOID)
                 acts.append(h)
+        if not cfg.use_hash:
+            fork_idx.join()
+            fork_col.join()
         state.mlp_acts = acts
         state.x = x
         ctx.state = state
@@ -537,9 +595,15 @@ class GNGFPath(torch.autograd.Function):
                  _lib.ptr_array(state.hpd_acts), _lib.ptr_array(gacts), _lib.ptr_array(g_hpd_b), g_hpd_w[0].data_ptr(), K,
                  state.uprobs.data_ptr(), state.utopi.data_ptr(), dtv.data_ptr(), state.cnt.data_ptr(), _ptr(gcol),
                  _ptr(gcol_k), _ptr(gdense), st)
-            for i in range(1, nh):
-                call("gngf_linear_bwd", gacts[i].data_ptr(), state.hpd_acts[i - 1].data_ptr(), hpd_w[i].data_ptr(), U,
-                     hpd_w[i].shape[0], hpd_w[i].shape[1], ACT_NONE, None, g_hpd_w[i].data_ptr(), None, st)
+            forks = []
+            for i in range(1, nh):      # independent products: one stream each
+                f = _Fork(dev, i - 1)
+                with f:
+                    call("gngf_linear_bwd", gacts[i].data_ptr(), state.hpd_acts[i - 1].data_ptr(), hpd_w[i].data_ptr(), U,
+                         hpd_w[i].shape[0], hpd_w[i].shape[1], ACT_NONE, None, g_hpd_w[i].data_ptr(), None, _stream())
+                forks.append(f)
+            for f in forks:
+                f.join()
             if GRAD_REDUCE_HOOK is not None:
                 GRAD_REDUCE_HOOK(flat)
             return (None, None, *grads)

@@ -9,7 +9,7 @@ then: copy the batch into the static buffers, replay, read the loss.
     trainer = GraphedTrainer(net, optimizer, points=P, gamma=-2, epsilon=1)   # after net.set_coord_bounds(...)
     loss = trainer.step(x_host_pinned, y_host_pinned)                          # or CUDA tensors
 
-The optimizer must be capturable (e.g. ``torch.optim.Adam(..., capturable=True, fused=True)``); the lattice bounds
+The optimizer must be capturable (``optim.FusedAdam``, or ``torch.optim.Adam(..., capturable=True, fused=True)``); the lattice bounds
 must be fixed (``net.set_coord_bounds``) because a captured step cannot read the batch's min/max back to the host.
 """
 from __future__ import annotations

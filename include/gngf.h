@@ -272,6 +272,35 @@ int gngf_count_distinct_f32(const float* indices, int64_t P, int32_t L, int32_t 
 int gngf_count_distinct_i64(const int64_t* indices, int64_t P, int32_t L, int32_t V, int32_t C, int64_t range,
                             uint32_t* bitmap, int32_t* uniq, int32_t* outliers, void* stream);
 
+/* ---- f-3: fused Adam over all parameter tensors (functions.py:96-127, 281) ------------------------------------------
+ * One launch: for every tensor  g' = g + weight_decay p;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)   with t = *step + 1  (torch.optim.Adam semantics,
+ * amsgrad off).  `tensors` is a HOST array (copied into kernel-parameter space); p/g/m/v are device pointers.
+ * `step` (device int32) is advanced by the kernel; `ticket` (device uint32, zero-initialised) is scratch.           */
+#define GNGF_ADAM_MAX_TENSORS 64
+typedef struct gngf_adam_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+  float lr;
+  float weight_decay;
+} gngf_adam_tensor;
+int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t* step,
+                   uint32_t* ticket, void* stream);
+
+/* ---- 8e: one-shot all-reduce over NVLink peer memory for small buffers (k10_allreduce.cu) -------------------------
+ * out (n) = scale * sum over ranks of in (n), identical bits on every rank (fixed summation order).
+ * stage_ptrs_dev / signal_ptrs_dev: DEVICE arrays of `world` peer-mapped pointers (symmetric memory): staging buffers
+ *   of 2 * cap_floats floats each, and zero-initialised signal pads of at least max_blocks * world uint32 each.
+ * state: 3 device uint32 (epoch, ticket, error), zero-initialised, owned by this communicator; state[2] != 0 after a
+ *   call means a peer did not arrive within ~3 s.  Every rank must call with the same n and max_blocks, in the same
+ *   order.  in / out 16-byte aligned; out may alias in.  Asynchronous on `stream`, CUDA-graph capturable.          */
+int gngf_peer_allreduce(const void* stage_ptrs_dev, const void* signal_ptrs_dev, int32_t rank, int32_t world,
+                        const float* in, float* out, int64_t n, int64_t cap_floats, int32_t max_blocks, float scale,
+                        uint32_t* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

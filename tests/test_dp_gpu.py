@@ -91,3 +91,19 @@ def test_two_ranks_match_full_batch_golden_gradients():
         ref = v.grad.detach().cpu().numpy()
         # divergence adjoint enters each rank scaled by world (adjoint of the sum-all-reduce) and is then averaged
         assert rel_err(got[0][k], ref) < 1e-4, (k, rel_err(got[0][k], ref))
+
+
+def test_peer_allreduce_matches_nccl():
+    """One-shot all-reduce over NVLink peer memory (k10_allreduce.cu) against NCCL: needs two GPUs."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(HERE, "peer_allreduce_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    print(r.stderr[-3000:])
+    assert r.returncode == 0 and "PEER_ALLREDUCE_OK" in r.stdout

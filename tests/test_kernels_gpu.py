@@ -361,3 +361,33 @@ def test_streaming_hpd_backward_matches_fp64(U, T, Kd, K):
     assert rel_err(dh.cpu().numpy(), dh_ref) < 1e-4
     assert rel_err(dw.cpu().numpy() - dw0, dw_ref) < 1e-4
     assert rel_err(db.cpu().numpy() - db0, db_ref) < 1e-4
+
+
+def test_fused_adam_matches_torch_adam():
+    """k9_adam.cu (one launch for all tensors, device-side step counter) against torch.optim.Adam with the
+    reference's settings (functions.py:96-127): per-group lr / weight decay, betas (0.9, 0.99), eps 1e-15."""
+    from collision_handling_in_instantngp_b200.optim import FusedAdam
+    rng = np.random.default_rng(3)
+    shapes = [(256, 2), (256, 2), (64, 8), (64,), (64, 64), (3, 64), (3,), (1, 1), (1000, 37)]
+    init = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+
+    def make(cls, **kw):
+        ps = [torch.nn.Parameter(torch.from_numpy(a.copy()).to(DEV)) for a in init]
+        opt = cls([{"params": ps[:2], "lr": 1e-4, "weight_decay": 0.0}, {"params": ps[2:5], "lr": 1e-3, "weight_decay": 1e-6},
+                   {"params": ps[5:], "lr": 2e-3, "weight_decay": 1e-2}], betas=(0.9, 0.99), eps=1e-15, **kw)
+        return ps, opt
+
+    pa, oa = make(torch.optim.Adam)
+    pb, ob = make(FusedAdam)
+    for step in range(12):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            g = torch.from_numpy((rng.standard_normal(a.shape) * 10.0 ** rng.integers(-6, 1)).astype(np.float32)).to(DEV)
+            if step == 5 and i == 7:
+                g = None                                   # a parameter without a gradient is skipped
+            a.grad = g
+            b.grad = None if g is None else g.clone()
+        oa.step()
+        ob.step()
+        for a, b in zip(pa, pb):
+            assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
+    assert ob.step_count == 12
