@@ -180,6 +180,8 @@ class CallProfiler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/r01_*_ncu_full.txt); None where no capture exists yet
 NCU_TRAFFIC = {("cfg2", "gngf_mlp3_bwd"): 2606080, ("cfg2", "gngf_mlp3_fwd"): 1892096,
+               ("cfg2", "gngf_mlp3_tc_bwd"): 4259840, ("cfg2", "gngf_mlp3_tc_fwd"): 1924608,
+               ("cfg3_t14", "gngf_hpd_stream_bwd"): 438117632,
                ("cfg3_t14", "gngf_hpd_stream_fwd"): 154538000, ("cfg3_t14", "gngf_tc_gemm_bf16x3"): 2802181000}
 
 
@@ -198,6 +200,13 @@ def algorithmic_cost(name, key, w, lat):
     """(bound, amount per launch, unit): ALGORITHMIC bytes (hbm) or FLOPs (tensor) of one launch."""
     P, L, F, K, T = w["P"], w["L"], w["F"], w["K"], w["T"]
     U, S = lat.num_nodes, lat.num_level_nodes
+    if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
+        # EXECUTED tensor-core FLOPs (DESIGN.md section 4): inputs padded to 16, output layer padded to 16 columns;
+        # forward: 6 split products; backward: 3 split products over recompute (2 layers) + dA2, dA1, dX + dW2, dW1, dW0
+        inp = (L * F + 15) // 16 * 16
+        if name == "gngf_mlp3_tc_fwd":
+            return "tensor", 6 * 2.0 * P * (inp * 64 + 64 * 64 + 64 * 16)
+        return "tensor", 3 * 2.0 * P * ((inp * 64 + 64 * 64) + (16 * 64 + 64 * 64 + 64 * inp) + (64 * 16 + 64 * 64 + 64 * inp))
     if name in ("gngf_mlp3_fwd", "gngf_mlp3_bwd"):
         dims = [L * F, *w["mlp"], 3]
         flops = 2.0 * P * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
@@ -238,6 +247,24 @@ def algorithmic_cost(name, key, w, lat):
         "gngf_split_bf16x3": 0.0,
     }
     return "hbm", float(table.get(name, 0))
+
+
+def useful_tflops(name, achieved, w):
+    """The share of the executed tensor-core FLOPs that the fp32 algorithm asks for (one pass per product)."""
+    if name in ("gngf_hpd_stream_fwd", "gngf_tc_gemm_bf16x3"):
+        return achieved / 6
+    if name == "gngf_hpd_stream_bwd":
+        return achieved / 6                       # 12 executed passes for the 2 gradient products
+    if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
+        dims = [w["L"] * w["F"], *w["mlp"], 3]
+        useful = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * (1 if name == "gngf_mlp3_tc_fwd" else 2)
+        inp = (dims[0] + 15) // 16 * 16
+        if name == "gngf_mlp3_tc_fwd":
+            executed = 6 * 2.0 * (inp * 64 + 64 * 64 + 64 * 16)
+        else:
+            executed = 3 * 2.0 * ((inp * 64 + 64 * 64) + (16 * 64 + 64 * 64 + 64 * inp) + (64 * 16 + 64 * 64 + 64 * inp))
+        return achieved * useful / executed
+    return None
 
 
 def run_ours(args, w):
@@ -397,8 +424,7 @@ def run_ours(args, w):
         achieved, peak, unit = per_launch_amount / per_launch_s / 1e12, tc_peak, "TFLOP/s"
     roofline = {"bound": te["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get((args.workload, tname)), "kernel": tname,
-                "useful_tflops": (achieved / 6 if tname in ("gngf_hpd_stream_fwd", "gngf_tc_gemm_bf16x3", "gngf_hpd_stream_bwd")
-                                  else None),
+                "useful_tflops": useful_tflops(tname, achieved, w),
                 "launches_per_step": te["n"] / args.steps,
                 "share_of_step_kernel_time": te["ms"] / total_kernel_ms, "peak_source": peak_src,
                 "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 5) for k, v in

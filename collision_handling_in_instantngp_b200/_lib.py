@@ -53,8 +53,8 @@ class Tables(Structure):
 
 class AdamTensor(Structure):
     """gngf_adam_tensor (include/gngf.h)."""
-    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64), ("lr", c_float),
-                ("weight_decay", c_float)]
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("step", c_void_p), ("n", c_int64),
+                ("lr", c_float), ("weight_decay", c_float)]
 
 
 ADAM_MAX_TENSORS = 64
@@ -97,7 +97,7 @@ SIGNATURES = {
     "gngf_mlp3_tc_bwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_peer_allreduce": (c_int, [_P, _P, c_int32, c_int32, _P, _P, c_int64, c_int64, c_int32, c_float, _P, _P]),
-    "gngf_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_float, c_float, c_float, _P, _P, _P]),
+    "gngf_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_float, c_float, c_float, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
     "gngf_count_distinct_workspace_words": (c_int64, [c_int32, c_int32, c_int64]),

@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(SM_THREADS)
       if (kk < Kd) {
         const int j0 = hf * (N / halves), j1 = (hf == halves - 1) ? N : j0 + N / halves;
         const float* wcol = net.w[i] + kk;
-#pragma unroll 8
-        for (int j = j0; j < j1; ++j) {
+#pragma unroll 16
+        for (int j = j0; j < j1; ++j) {   // (16 weight loads in flight per thread: the loop is L2-latency bound)
           const float w = __ldg(wcol + static_cast<int64_t>(j) * Kd);
           const float4 a = *reinterpret_cast<const float4*>(gT + j * NB);
           const float4 b = *reinterpret_cast<const float4*>(gT + j * NB + 4);

@@ -3,7 +3,8 @@
 // torch's fused Adam issues one multi-tensor launch per parameter group plus a step-counter launch per group (6
 // launches, ~33 us at the published configuration where the whole step is ~0.25 ms); here the tensor descriptors
 // travel in kernel-parameter space, a block finds its tensor with a search over the chunk prefix sums, and the step
-// counter is a device scalar advanced by the last block to finish (CUDA-graph friendly: no host state).
+// counters (one per tensor, as in torch: a parameter whose gradient is missing in some step does not advance) are
+// device scalars advanced by the last block to finish (CUDA-graph friendly: no host state).
 //   g' = g + wd p ;  m += (1 - b1)(g' - m) ;  v = b2 v + (1 - b2) g'^2 ;
 //   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)            (torch.optim.Adam, amsgrad = False)
 #include "common.cuh"
@@ -20,9 +21,8 @@ struct AdamArgs {
 };
 
 __global__ void __launch_bounds__(ADAM_THREADS)
-    adam_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float eps, int* __restrict__ step,
+    adam_kernel(const __grid_constant__ AdamArgs a, float beta1, float beta2, float eps,
                 unsigned int* __restrict__ ticket) {
-  const int t_now = *step + 1;
   // which tensor does this block's chunk belong to?
   const int64_t b = blockIdx.x;
   int lo = 0, hi = a.count - 1;
@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(ADAM_THREADS)
     if (b < a.chunk_end[mid]) hi = mid; else lo = mid + 1;
   }
   const gngf_adam_tensor& T = a.t[lo];
+  const int t_now = *T.step + 1;
   const int64_t chunk = b - (lo ? a.chunk_end[lo - 1] : 0);
   const float bc1 = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), t_now));
   const float bc2 = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), t_now));
@@ -72,13 +73,13 @@ __global__ void __launch_bounds__(ADAM_THREADS)
       }
     }
   }
-  // the last block to finish advances the step counter (every block has read it by then)
+  // the last block to finish advances the step counters (every block has read its own by then)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int done = atomicAdd(ticket, 1u);
     if (done == gridDim.x - 1) {
-      *step = t_now;
+      for (int i = 0; i < a.count; ++i) *a.t[i].step += 1;
       *ticket = 0u;
     }
   }
@@ -88,16 +89,17 @@ __global__ void __launch_bounds__(ADAM_THREADS)
 
 extern "C" {
 
-int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t* step,
-                   uint32_t* ticket, void* stream) {
-  if (count < 0 || count > GNGF_ADAM_MAX_TENSORS || !step || !ticket) return GNGF_ERR_INVALID_ARGUMENT;
+int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, uint32_t* ticket,
+                   void* stream) {
+  if (count < 0 || count > GNGF_ADAM_MAX_TENSORS || !ticket) return GNGF_ERR_INVALID_ARGUMENT;
   gngf::AdamArgs a;
   int64_t chunks = 0;
   int used = 0;
   for (int i = 0; i < count; ++i) {
     if (tensors[i].n < 0) return GNGF_ERR_INVALID_ARGUMENT;
     if (tensors[i].n == 0) continue;
-    if (!tensors[i].p || !tensors[i].g || !tensors[i].m || !tensors[i].v) return GNGF_ERR_INVALID_ARGUMENT;
+    if (!tensors[i].p || !tensors[i].g || !tensors[i].m || !tensors[i].v || !tensors[i].step)
+      return GNGF_ERR_INVALID_ARGUMENT;
     a.t[used] = tensors[i];
     chunks += gngf::ceil_div(tensors[i].n, gngf::ADAM_CHUNK);
     a.chunk_end[used] = chunks;
@@ -107,7 +109,7 @@ int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, 
   if (used == 0) return GNGF_OK;
   if (chunks >= (1ll << 31)) return GNGF_ERR_UNSUPPORTED;
   gngf::adam_kernel<<<static_cast<unsigned>(chunks), gngf::ADAM_THREADS, 0, gngf::as_stream(stream)>>>(a, beta1, beta2, eps,
-                                                                                                      step, ticket);
+                                                                                                      ticket);
   gngf::note_launch();
   return gngf::check_launch();
 }

@@ -103,6 +103,15 @@ def all_reduce_sum_(t: torch.Tensor, scale: float = 1.0, group=None) -> torch.Te
     return t
 
 
+def all_reduce_sum(t: torch.Tensor, scale: float = 1.0, group=None) -> torch.Tensor:
+    """Out-of-place scale * sum over ranks (no autograd)."""
+    comm = peer_allreduce_for(group) if t.is_cuda else None
+    if comm is not None and t.dtype == torch.float32 and t.is_contiguous() and t.numel() * 4 <= PEER_MAX_BYTES \
+            and t.data_ptr() % 16 == 0:
+        return comm(t, scale=scale)
+    return all_reduce_sum_(t.clone(), scale, group)
+
+
 class _AllReduceSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t, group):

@@ -66,3 +66,21 @@ class _FusedLoss(torch.autograd.Function):
 def fused_total_loss(rgb, target, colsum, rows, gamma, epsilon, l_mse=1.0, l_js_kl=1.0, collisions_term=None):
     """Same value and gradients as :func:`total_loss`, from the single CUDA kernel of k7_loss.cu."""
     return _FusedLoss.apply(rgb, target, colsum, rows, gamma, epsilon, l_mse, l_js_kl, collisions_term)
+
+
+def fused_loss_and_grads(rgb, target, colsum, rows, gamma, epsilon, l_mse=1.0, l_js_kl=1.0, collisions_term=None):
+    """The same kernel without an autograd node: returns (out, d_rgb, d_colsum) with out = [total, mse, level_0..]
+    and the adjoints of `total` w.r.t. rgb and colsum.  A caller whose loss is the root of the backward pass feeds
+    them straight into ``torch.autograd.backward([rgb, colsum], [d_rgb, d_colsum])`` -- no ones_like(), no
+    multiplications by the incoming gradient, no materialised zero gradients (trainer.GraphedTrainer)."""
+    from . import ops
+    rgb_c, tgt_c, cs_c = ops._f32c(rgb.detach()), ops._f32c(target), ops._f32c(colsum.detach())
+    L, N = cs_c.shape
+    out = torch.empty(2 + L, dtype=torch.float32, device=rgb_c.device)
+    d_rgb = torch.empty_like(rgb_c)
+    d_colsum = torch.empty_like(cs_c)
+    ops.call("gngf_loss_fwd_bwd", rgb_c.data_ptr(), tgt_c.data_ptr(), rgb_c.numel(), cs_c.data_ptr(), L, N,
+             float(rows), float(gamma), float(epsilon), float(l_mse), float(l_js_kl),
+             None if collisions_term is None else ops._f32c(collisions_term).data_ptr(), out.data_ptr(),
+             d_rgb.data_ptr(), d_colsum.data_ptr(), ops._stream())
+    return out, d_rgb, d_colsum

@@ -419,6 +419,7 @@ class GNGFPath(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, state: ForwardState, *params):
         cfg, lat = state.cfg, state.lat
+        ctx.set_materialize_grads(False)      # unused outputs (uvals, colsum) arrive as None, not as zero tensors
         dev = x.device
         L, F, K, T = lat.num_levels, cfg.feature_dim, cfg.topk_k, cfg.table_size
         P = x.shape[0]
@@ -529,7 +530,7 @@ class GNGFPath(torch.autograd.Function):
         # decoder MLP (models.py:468-470)
         acts = state.mlp_acts
         rgb = acts[-1]
-        grad_rgb = _f32c(grad_rgb)
+        grad_rgb = torch.zeros_like(rgb) if grad_rgb is None else _f32c(grad_rgb)
         if state.mlp_fused:
             C = rgb.shape[1]
             denc = torch.empty((P, L * F), dtype=torch.float32, device=dev)

@@ -27,12 +27,12 @@ class FusedAdam(torch.optim.Optimizer):
         eps_set = {float(g["eps"]) for g in self.param_groups}
         if len(betas_set) != 1 or len(eps_set) != 1:
             raise GngfError("FusedAdam: betas and eps must be the same for all parameter groups")
-        self._step_dev = None      # int32 device scalar, advanced by the kernel
         self._ticket = None
 
-    @property
-    def step_count(self) -> int:
-        return 0 if self._step_dev is None else int(self._step_dev.item())
+    def step_count(self, p) -> int:
+        """Number of updates parameter `p` has received (device counter; this call synchronises)."""
+        st = self.state.get(p)
+        return 0 if not st else int(st["step"].item())
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -55,28 +55,23 @@ class FusedAdam(torch.optim.Optimizer):
                 if not st:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["step"] = torch.zeros(1, dtype=torch.int32, device=p.device)   # advanced by the kernel
                 dev = p.device
-                entries.append((p, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), float(group["weight_decay"])))
+                entries.append((p, g, st["exp_avg"], st["exp_avg_sq"], st["step"], float(group["lr"]),
+                                float(group["weight_decay"])))
         if not entries:
             return loss
-        if self._step_dev is None:
-            self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self._ticket is None:
             self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         beta1, beta2 = self.param_groups[0]["betas"]
         eps = float(self.param_groups[0]["eps"])
         stream = torch.cuda.current_stream(dev).cuda_stream
         fn = _lib.load().gngf_adam_step
-        # more than ADAM_MAX_TENSORS tensors: several launches; only the last one may advance the step counter, so
-        # the earlier ones run on a scratch copy of it
-        chunks = [entries[i:i + ADAM_MAX_TENSORS] for i in range(0, len(entries), ADAM_MAX_TENSORS)]
-        for ci, chunk in enumerate(chunks):
+        for i0 in range(0, len(entries), ADAM_MAX_TENSORS):     # (more than 64 tensors: several launches)
+            chunk = entries[i0:i0 + ADAM_MAX_TENSORS]
             arr = (AdamTensor * len(chunk))()
-            for i, (p, g, m, v, lr, wd) in enumerate(chunk):
+            for i, (p, g, m, v, t, lr, wd) in enumerate(chunk):
                 arr[i].p, arr[i].g, arr[i].m, arr[i].v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
-                arr[i].n, arr[i].lr, arr[i].weight_decay = p.numel(), lr, wd
-            step_ptr = self._step_dev
-            if ci < len(chunks) - 1:
-                step_ptr = self._step_dev.clone()
-            check(fn(arr, len(chunk), float(beta1), float(beta2), eps, step_ptr.data_ptr(), self._ticket.data_ptr(),
-                     stream), "gngf_adam_step")
+                arr[i].step, arr[i].n, arr[i].lr, arr[i].weight_decay = t.data_ptr(), p.numel(), lr, wd
+            check(fn(arr, len(chunk), float(beta1), float(beta2), eps, self._ticket.data_ptr(), stream), "gngf_adam_step")
         return loss

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 from . import dp
 from ._lib import GngfError
-from .loss import fused_total_loss
+from .loss import fused_loss_and_grads
 
 
 class GraphedTrainer:
@@ -50,11 +50,17 @@ class GraphedTrainer:
     def _eager_step(self):
         self.opt.zero_grad(set_to_none=True)
         rgb, probs, _, _ = self.net(self.x, 1.0)
-        colsum = dp.all_reduce_colsum(probs.colsum) if self.world > 1 else probs.colsum
-        total, _, _ = fused_total_loss(rgb, self.y, colsum, self.rows, *self.loss_args)
-        total.backward()
+        local = probs.colsum
+        # the (L, N) column sums are summed over ranks before the non-linear divergence terms (dp.py); every rank
+        # evaluates the same function of the sum, so the adjoint of the local column sums is world * d_colsum
+        colsum = dp.all_reduce_sum(local.detach()) if self.world > 1 else local.detach()
+        out, d_rgb, d_colsum = fused_loss_and_grads(rgb, self.y, colsum, self.rows, *self.loss_args)
+        if self.world > 1:
+            d_colsum = d_colsum * float(self.world)
+        # the loss kernel emits its own adjoints: they seed the backward directly
+        torch.autograd.backward([rgb, local], [d_rgb, d_colsum])
         self.opt.step()
-        return total.detach()
+        return out[0]
 
     def _capture(self, warmup_steps):
         side = torch.cuda.Stream()

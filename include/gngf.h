@@ -275,20 +275,22 @@ int gngf_count_distinct_i64(const int64_t* indices, int64_t P, int32_t L, int32_
 /* ---- f-3: fused Adam over all parameter tensors (functions.py:96-127, 281) ------------------------------------------
  * One launch: for every tensor  g' = g + weight_decay p;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
  *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)   with t = *step + 1  (torch.optim.Adam semantics,
- * amsgrad off).  `tensors` is a HOST array (copied into kernel-parameter space); p/g/m/v are device pointers.
- * `step` (device int32) is advanced by the kernel; `ticket` (device uint32, zero-initialised) is scratch.           */
+ * amsgrad off).  `tensors` is a HOST array (copied into kernel-parameter space); p/g/m/v/step are device pointers;
+ * every tensor has its own `step` (device int32, distinct addresses), advanced by the kernel; `ticket` (device
+ * uint32, zero-initialised) is scratch.                                                                             */
 #define GNGF_ADAM_MAX_TENSORS 64
 typedef struct gngf_adam_tensor {
   float* p;
   const float* g;
   float* m;
   float* v;
+  int32_t* step;
   int64_t n;
   float lr;
   float weight_decay;
 } gngf_adam_tensor;
-int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t* step,
-                   uint32_t* ticket, void* stream);
+int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, uint32_t* ticket,
+                   void* stream);
 
 /* ---- 8e: one-shot all-reduce over NVLink peer memory for small buffers (k10_allreduce.cu) -------------------------
  * out (n) = scale * sum over ranks of in (n), identical bits on every rank (fixed summation order).
