@@ -83,7 +83,7 @@ def main():
             pt_b = P * (8 + L * (4 * F * 4) + L * F * 4)
             res = {"P": P, "T": T, "L": L, "F": F, "K": K, "lattice_nodes": U, "level_nodes": S, "hbm_peak_gbs": hbm}
             t = timeit(lambda: _lib.call("gngf_encode_fwd", x.data_ptr(), P, lat, F, nfeat.data_ptr(), enc.data_ptr(),
-                                         None, None, st))
+                                         None, None, None, st))
             res["gngf_point_fwd"] = {"ms": t, "gbs": pt_b / t / 1e6, "frac": pt_b / t / 1e6 / hbm}
             res["gngf_node_fwd"] = {"ms": t_node_f, "gbs": node_fwd_b / t_node_f / 1e6}
             t = timeit(lambda: _lib.call("gngf_encode_bwd", x.data_ptr(), P, lat, F, denc.data_ptr(), dnf.data_ptr(), st))

@@ -107,7 +107,8 @@ SIGNATURES = {
     "gngf_topk_fwd": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "gngf_topk_bwd": (c_int, [_P, _P, c_int64, c_int64, c_int32, _P, _P]),
     "gngf_node_features_fwd": (c_int, [Lattice, Tables, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
-    "gngf_encode_fwd": (c_int, [_P, c_int64, Lattice, c_int32, _P, _P, _P, _P, _P]),
+    "gngf_encode_fwd": (c_int, [_P, c_int64, Lattice, c_int32, _P, _P, _P, _P, _P, _P]),
+    "gngf_cell_to_node_counts": (c_int, [Lattice, _P, _P, _P]),
     "gngf_encode_hash_fwd": (c_int, [_P, c_int64, Lattice, Tables, c_int64, c_int32, _P, _P, _P]),
     "gngf_lattice_colsum": (c_int, [Lattice, _P, _P, c_int64, _P, _P]),
     "gngf_lattice_gather_rows": (c_int, [_P, c_int64, Lattice, _P, c_int64, _P, _P]),

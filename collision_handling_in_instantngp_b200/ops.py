@@ -445,16 +445,20 @@ class GNGFPath(torch.autograd.Function):
             nfeat = torch.empty((S, F), dtype=torch.float32, device=dev)
             call("gngf_node_features_fwd", lat, tab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
                  state.utopi.data_ptr(), nfeat.data_ptr(), st)
-            # cnt (S) | err flag (1) | colsum (L*N) share one zero-initialised buffer: one memset
+            # cnt (S) | cell counts (S) | err flag (1) | colsum (L*N) share one zero-initialised buffer: one memset
             N = K if cfg.topk_only else T
-            zbuf = torch.zeros(S + 1 + L * N, dtype=torch.int32, device=dev)
-            state.cnt, state.err_flag = zbuf[:S], zbuf[S:S + 1]
-            colsum = zbuf[S + 1:].view(torch.float32).view(L, N)
+            # (the column sums start on a 16-byte boundary: the peer all-reduce of dp.py moves them as float4)
+            c0 = (2 * S + 1 + 3) & ~3
+            zbuf = torch.zeros(c0 + L * N, dtype=torch.int32, device=dev)
+            state.cnt, cell_cnt, state.err_flag = zbuf[:S], zbuf[S:2 * S], zbuf[2 * S:2 * S + 1]
+            colsum = zbuf[c0:].view(torch.float32).view(L, N)
             call("gngf_encode_fwd", x.data_ptr(), P, lat, F, nfeat.data_ptr(), enc.data_ptr(), state.cnt.data_ptr(),
-                 state.err_flag.data_ptr(), st)
+                 cell_cnt.data_ptr(), state.err_flag.data_ptr(), st)
             uvals = state.utopv if cfg.topk_only else state.uprobs
             fork_col = _Fork(dev, 1)      # only the loss reads the column sums: overlaps the decoder
             with fork_col:
+                # node multiplicities from the per-cell counts of the point pass (one atomic per (point, level))
+                call("gngf_cell_to_node_counts", lat, cell_cnt.data_ptr(), state.cnt.data_ptr(), _stream())
                 call("gngf_lattice_colsum", lat, state.cnt.data_ptr(), uvals.data_ptr(), N, colsum.data_ptr(), _stream())
 
         state.mlp_fused = _mlp3_supported(mlp_w)

@@ -220,9 +220,13 @@ int gngf_node_features_fwd(gngf_lattice lat, gngf_tables tables, int64_t T, int3
                            const float* utopv, const int32_t* utopi, float* nfeat, void* stream);
 /* per point: corners + bilinear weights (models.py:621-655) + gather of 4 node features per level:
  *   enc (P, L*F); optional cnt (S) int32 += multiplicity of every level node; err_flag (int32, optional)
- *   is set to 1 when a coordinate falls outside the lattice box (the access is clamped).               */
+ *   is set to 1 when a coordinate falls outside the lattice box (the access is clamped).
+ *   cell_cnt (S int32, zero-initialised, optional, needs cnt != NULL): count ONE update per (point, level) -- the
+ *   cell, indexed by its floor-corner node -- into cell_cnt instead of four into cnt; the caller then derives
+ *   cnt = gngf_cell_to_node_counts(cell_cnt) (a node's multiplicity is the sum of its four surrounding cells).  */
 int gngf_encode_fwd(const float* x, int64_t P, gngf_lattice lat, int32_t F, const float* nfeat, float* enc,
-                    int32_t* cnt, int32_t* err_flag, void* stream);
+                    int32_t* cnt, int32_t* cell_cnt, int32_t* err_flag, void* stream);
+int gngf_cell_to_node_counts(gngf_lattice lat, const int32_t* cell_cnt, int32_t* cnt, void* stream);
 /* hash-function mode (models.py:181-190 + 504-528): enc straight from table_l[hash(corner)]             */
 int gngf_encode_hash_fwd(const float* x, int64_t P, gngf_lattice lat, gngf_tables tables, int64_t T, int32_t F,
                          float* enc, int64_t* idx_out, void* stream);
