@@ -59,49 +59,106 @@ __device__ __forceinline__ float reduce_scatter8(const float (&acc)[NB], int lan
   return a1;
 }
 
-// One layer for the CTA's NB nodes: dst[n][j] = act(sum_k in[n][k] W[j][k] + b[j]).  A warp takes JB = 4 outputs at
-// a time; the lanes stride k (a weight row is read coalesced) and all JB * CH weight loads of a step are issued
-// before the first use, so one L2 round trip covers four outputs.  CH = ceil(K / 32) <= 8.
-template <int CH>
-__device__ __forceinline__ void small_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int N,
-                                            const float* in /*[NB][SM_MAXW]*/, float* dst, int ldd, bool relu,
-                                            float* gsave, int64_t u0, int64_t U, int warp, int lane) {
-  constexpr int JB = 4;
-  float xin[NB][CH];
-#pragma unroll
-  for (int n = 0; n < NB; ++n)
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int k = lane + 32 * c;
-      xin[n][c] = k < K ? in[n * SM_MAXW + k] : 0.0f;
+// One layer for the CTA's NB nodes: out[j][n] = act(sum_k in[k][n] W[j][k] + b[j]).
+// Thread = output unit j (a pass covers SM_THREADS of them); the weight rows of the pass stream through shared memory
+// in tiles of TK input units (cp.async, double-buffered, rows padded to TK + 4 floats so that the float4 reads of a
+// quarter warp hit distinct banks); activations live unit-major ([unit][NB]) so that the NB values of one input unit
+// are two broadcast 16-byte loads.  No shuffles: the previous version (lanes stride k, tree-reduce 8 partial sums per
+// output) spent its time in the shuffle chains (ncu: short-scoreboard + issue stalls, 24 us for 782 nodes).
+constexpr int TK = 32;
+constexpr int WT_LD = TK + 4;
+constexpr int WT_FLOATS = SM_THREADS * WT_LD;   // one tile buffer
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows [j0, j0 + SM_THREADS) x columns [k0, k0 + TK) of W (N x K) -> tile (zero-filled outside the matrix)
+__device__ __forceinline__ void stage_w_tile(const float* __restrict__ W, int N, int K, int j0, int k0, float* tile,
+                                             bool vec_ok) {
+  if (vec_ok && k0 + TK <= K) {
+    for (int e = threadIdx.x; e < SM_THREADS * (TK / 4); e += SM_THREADS) {
+      const int r = e / (TK / 4), c = e % (TK / 4);
+      float* dst = tile + r * WT_LD + c * 4;
+      if (j0 + r < N) cp_async16(dst, W + static_cast<int64_t>(j0 + r) * K + k0 + c * 4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  for (int j0 = warp * JB; j0 < N; j0 += (SM_THREADS / 32) * JB) {
-    float wv[JB][CH];
+  } else {
+    for (int e = threadIdx.x; e < SM_THREADS * TK; e += SM_THREADS) {
+      const int r = e / TK, c = e % TK;
+      tile[r * WT_LD + c] = (j0 + r < N && k0 + c < K) ? __ldg(W + static_cast<int64_t>(j0 + r) * K + k0 + c) : 0.0f;
+    }
+  }
+}
+
+// in: [K][NB] unit-major.  hidden layers: out_t [N][NB] unit-major (+ gsave (U,N) global); last layer: logits [NB][ldl]
+__device__ __forceinline__ void small_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int N,
+                                            const float* in, float* out_t, float* logits, int ldl, bool relu,
+                                            float* gsave, int64_t u0, int64_t U, float* wt) {
+  const bool vec_ok = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+  const int ktiles = (K + TK - 1) / TK;
+  for (int j0 = 0; j0 < N; j0 += SM_THREADS) {
+    const int j = j0 + threadIdx.x;
+    float acc[NB];
 #pragma unroll
-    for (int jb = 0; jb < JB; ++jb)
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int k = lane + 32 * c;
-        wv[jb][c] = (j0 + jb < N && k < K) ? __ldg(W + static_cast<int64_t>(j0 + jb) * K + k) : 0.0f;
+    for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
+    stage_w_tile(W, N, K, j0, 0, wt, vec_ok);
+    cp_async_commit();
+    for (int t = 0; t < ktiles; ++t) {
+      if (t + 1 < ktiles) {
+        stage_w_tile(W, N, K, j0, (t + 1) * TK, wt + ((t + 1) & 1) * WT_FLOATS, vec_ok);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
+      __syncthreads();
+      const float* wrow = wt + (t & 1) * WT_FLOATS + threadIdx.x * WT_LD;
+      const float* xin = in + t * TK * NB;
+      const int kmax = min(TK, K - t * TK);
+#pragma unroll 2
+      for (int kk = 0; kk < TK; kk += 4) {
+        if (kk >= kmax) break;
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + kk);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-    for (int jb = 0; jb < JB; ++jb) {
-      float acc[NB];
+        for (int i = 0; i < 4; ++i) {
+          if (kk + i < kmax) {
+            const float4 xa = *reinterpret_cast<const float4*>(xin + (kk + i) * NB);
+            const float4 xb = *reinterpret_cast<const float4*>(xin + (kk + i) * NB + 4);
+            acc[0] = fmaf(wv[i], xa.x, acc[0]); acc[1] = fmaf(wv[i], xa.y, acc[1]);
+            acc[2] = fmaf(wv[i], xa.z, acc[2]); acc[3] = fmaf(wv[i], xa.w, acc[3]);
+            acc[4] = fmaf(wv[i], xb.x, acc[4]); acc[5] = fmaf(wv[i], xb.y, acc[5]);
+            acc[6] = fmaf(wv[i], xb.z, acc[6]); acc[7] = fmaf(wv[i], xb.w, acc[7]);
+          }
+        }
+      }
+      __syncthreads();   // the buffer just read is refilled two iterations later
+    }
+    if (j < N) {
+      const float bj = __ldg(bias + j);
 #pragma unroll
       for (int n = 0; n < NB; ++n) {
-        float a = 0.0f;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) a = fmaf(wv[jb][c], xin[n][c], a);
-        acc[n] = a;
-      }
-      int node;
-      const float s = reduce_scatter8(acc, lane, node);
-      const int j = j0 + jb;
-      if ((lane & 3) == 0 && j < N) {
-        float v = s + bias[j];
+        float v = acc[n] + bj;
         if (relu) v = fmaxf(v, 0.0f);
-        dst[node * ldd + j] = v;
-        if (gsave && u0 + node < U) gsave[(u0 + node) * N + j] = v;
+        acc[n] = v;
+      }
+      if (logits) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n) logits[n * ldl + j] = acc[n];
+      } else {
+        *reinterpret_cast<float4*>(out_t + j * NB) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(out_t + j * NB + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      if (gsave) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n)
+          if (u0 + n < U) gsave[(u0 + n) * N + j] = acc[n];
       }
     }
   }
@@ -111,27 +168,28 @@ __global__ void __launch_bounds__(SM_THREADS)
     hpd_small_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net, int K,
                          float* __restrict__ uprobs, float* __restrict__ utopv, int32_t* __restrict__ utopi) {
   extern __shared__ float sm[];
-  float* bufA = sm;                       // [NB][SM_MAXW]
-  float* bufB = sm + NB * SM_MAXW;        // [NB][SM_MAXW]
+  float* bufA = sm;                       // [SM_MAXW][NB] unit-major activations
+  float* bufB = sm + NB * SM_MAXW;        // [SM_MAXW][NB]
   float* logits = sm + 2 * NB * SM_MAXW;  // [NB][T]
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int nl = net.n_layers, T = net.width[nl];
+  float* wt = logits + NB * T;            // [2][SM_THREADS][WT_LD] weight tiles
 
   // layer 0 from the node coordinates (models.py:416: the HPD input is the integer corner)
   {
     const int N0 = net.width[1];
     const float2* w0 = reinterpret_cast<const float2*>(net.w[0]);
     for (int e = tid; e < NB * N0; e += SM_THREADS) {
-      const int n = e / N0, j = e % N0;
+      const int j = e / NB, n = e % NB;
       const int64_t u = min(u0 + n, U - 1);
       const float cx = static_cast<float>(lat.ox + static_cast<int>(u / lat.wy));
       const float cy = static_cast<float>(lat.oy + static_cast<int>(u % lat.wy));
       const float2 w = w0[j];
       float v = fmaf(cy, w.y, fmaf(cx, w.x, net.b[0][j]));
       v = fmaxf(v, 0.0f);
-      bufA[n * SM_MAXW + j] = v;
+      bufA[j * NB + n] = v;
       if (u0 + n < U) net.act[0][(u0 + n) * N0 + j] = v;
     }
   }
@@ -141,14 +199,8 @@ __global__ void __launch_bounds__(SM_THREADS)
   for (int i = 1; i < nl; ++i) {
     const int Kd = net.width[i], N = net.width[i + 1];
     const bool last = i == nl - 1;
-    float* dst = last ? logits : out;
-    const int ldd = last ? T : SM_MAXW;
-    float* gsave = last ? nullptr : net.act[i];
-    const int ch = (Kd + 31) / 32;
-    if (ch <= 1) small_layer<1>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
-    else if (ch <= 2) small_layer<2>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
-    else if (ch <= 4) small_layer<4>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
-    else small_layer<8>(net.w[i], net.b[i], Kd, N, in, dst, ldd, !last, gsave, u0, U, warp, lane);
+    small_layer(net.w[i], net.b[i], Kd, N, in, out, last ? logits : nullptr, T, !last, last ? nullptr : net.act[i], u0, U,
+                wt);
     __syncthreads();
     if (!last) {
       float* t = in;
@@ -197,6 +249,7 @@ __global__ void __launch_bounds__(SM_THREADS)
   float* gT = sm;                         // [max(T, SM_MAXW)][NB] adjoint of the current layer's pre-activation
   float* gN = sm + SM_MAXT * NB;          // [SM_MAXW][NB] next (lower) layer's adjoint
   float* part = gN + SM_MAXW * NB;        // [2][SM_MAXW][NB] partial sums of the two j-halves
+  float* wtile = part + 2 * SM_MAXW * NB; // [2][32][SM_MAXW] weight-row tiles of the dX products
   __shared__ float cl_s[NB][GNGF_MAX_LEVELS];
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
@@ -297,21 +350,60 @@ __global__ void __launch_bounds__(SM_THREADS)
       float acc[NB];
 #pragma unroll
       for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
-      if (kk < Kd) {
-        const int j0 = hf * (N / halves), j1 = (hf == halves - 1) ? N : j0 + N / halves;
-        const float* wcol = net.w[i] + kk;
-#pragma unroll 16
-        for (int j = j0; j < j1; ++j) {   // (16 weight loads in flight per thread: the loop is L2-latency bound)
-          const float w = __ldg(wcol + static_cast<int64_t>(j) * Kd);
-          const float4 a = *reinterpret_cast<const float4*>(gT + j * NB);
-          const float4 b = *reinterpret_cast<const float4*>(gT + j * NB + 4);
-          acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
-          acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
-          acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]);
-          acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+      {
+        // W_i rows stream through shared memory in tiles of TJ output units (cp.async, double-buffered): the loop was
+        // bound by the L2 latency of its weight loads.  Thread (kk, hf) takes rows hf, hf + halves, ... of every tile.
+        constexpr int TJ = 32;
+        const float* Wg = net.w[i];
+        const bool vec_ok = (Kd & 3) == 0 && (reinterpret_cast<uintptr_t>(Wg) & 15) == 0;
+        const int tiles = (N + TJ - 1) / TJ;
+        auto stage = [&](int t, float* buf) {
+          const int jb = t * TJ;
+          if (vec_ok) {
+            const int cpr = Kd / 4;   // 16-byte chunks per row
+            for (int e = tid; e < TJ * cpr; e += SM_THREADS) {
+              const int r = e / cpr, c = e % cpr;
+              if (jb + r < N) cp_async16(buf + r * SM_MAXW + c * 4, Wg + static_cast<int64_t>(jb + r) * Kd + c * 4);
+            }
+          } else {
+            for (int e = tid; e < TJ * Kd; e += SM_THREADS) {
+              const int r = e / Kd, c = e % Kd;
+              if (jb + r < N) buf[r * SM_MAXW + c] = __ldg(Wg + static_cast<int64_t>(jb + r) * Kd + c);
+            }
+          }
+        };
+        stage(0, wtile);
+        cp_async_commit();
+        for (int t = 0; t < tiles; ++t) {
+          if (t + 1 < tiles) {
+            stage(t + 1, wtile + ((t + 1) & 1) * TJ * SM_MAXW);
+            cp_async_commit();
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
+          }
+          __syncthreads();
+          if (kk < Kd) {
+            const float* buf = wtile + (t & 1) * TJ * SM_MAXW;
+            const int rows = min(TJ, N - t * TJ);
+#pragma unroll 4
+            for (int r = hf; r < rows; r += halves) {
+              const float w = buf[r * SM_MAXW + kk];
+              const int j = t * TJ + r;
+              const float4 a = *reinterpret_cast<const float4*>(gT + j * NB);
+              const float4 b = *reinterpret_cast<const float4*>(gT + j * NB + 4);
+              acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+              acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+              acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]);
+              acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+            }
+          }
+          __syncthreads();
         }
+        if (kk < Kd) {
 #pragma unroll
-        for (int n = 0; n < NB; ++n) part[(hf * SM_MAXW + kk) * NB + n] = acc[n];
+          for (int n = 0; n < NB; ++n) part[(hf * SM_MAXW + kk) * NB + n] = acc[n];
+        }
       }
       __syncthreads();
       // combine the halves, apply the ReLU mask of h_{i-1} (saved forward activation), -> gN
@@ -330,8 +422,8 @@ __global__ void __launch_bounds__(SM_THREADS)
   }
 }
 
-static size_t small_fwd_smem(int T) { return sizeof(float) * (2 * NB * SM_MAXW + NB * T); }
-static size_t small_bwd_smem() { return sizeof(float) * (SM_MAXT * NB + SM_MAXW * NB + 2 * SM_MAXW * NB); }
+static size_t small_fwd_smem(int T) { return sizeof(float) * (2 * NB * SM_MAXW + NB * T + 2 * WT_FLOATS); }
+static size_t small_bwd_smem() { return sizeof(float) * (SM_MAXT * NB + SM_MAXW * NB + 2 * SM_MAXW * NB + 2 * 32 * SM_MAXW); }
 
 }  // namespace gngf
 

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * BM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
+  // (row tiles on grid.x: up to 2^31 - 1 of them -- 67 M lattice nodes at the 8192^2 configuration)
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM, n0 = static_cast<int64_t>(blockIdx.y) * BN;
   const int64_t k_begin = static_cast<int64_t>(blockIdx.z) * k_chunk;
   const int64_t k_end = min(K, k_begin + k_chunk);
   const bool a_kfast = (sak == 1), b_kfast = (sbk == 1);
@@ -123,8 +124,8 @@ static int launch_sgemm(const float* A, int64_t sam, int64_t sak, const float* B
   split = static_cast<int>(ceil_div(K, k_chunk));
   if (split > 1 && !ep.atomic) return GNGF_ERR_INVALID_ARGUMENT;
   const int64_t gy = ceil_div(M, bm), gx = ceil_div(N, bm);
-  if (gy > 65535) return GNGF_ERR_UNSUPPORTED;
-  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy), static_cast<unsigned>(split));
+  if (gx > 65535 || gy >= (1ll << 31)) return GNGF_ERR_UNSUPPORTED;
+  dim3 grid(static_cast<unsigned>(gy), static_cast<unsigned>(gx), static_cast<unsigned>(split));
   if (small)
     sgemm_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, k_chunk, ep);
   else
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
                                                      int64_t rows_per_block, float* __restrict__ db) {
   __shared__ float part[8][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-  const int64_t n = static_cast<int64_t>(blockIdx.x) * 32 + tx;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t n = static_cast<int64_t>(blockIdx.y) * 32 + tx;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(M, r0 + rows_per_block);
   float s = 0.0f;
   if (n < N)
@@ -250,8 +251,8 @@ int gngf_linear_bwd(const float* dz, const float* x, const float* w, int64_t M, 
     const int64_t col_blocks = gngf::ceil_div(N, 32);
     const int64_t rows_per_block =
         std::min<int64_t>(256, std::max<int64_t>(32, gngf::ceil_div(M * col_blocks, 4 * gngf::sm_count())));
-    dim3 grid(static_cast<unsigned>(col_blocks), static_cast<unsigned>(gngf::ceil_div(M, rows_per_block)));
-    if (grid.y > 65535) return GNGF_ERR_UNSUPPORTED;
+    if (col_blocks > 65535) return GNGF_ERR_UNSUPPORTED;
+    dim3 grid(static_cast<unsigned>(gngf::ceil_div(M, rows_per_block)), static_cast<unsigned>(col_blocks));
     gngf::colsum_kernel<<<grid, 256, 0, st>>>(dz, M, N, rows_per_block, db);
     gngf::note_launch();
     rc = gngf::check_launch();

@@ -238,6 +238,45 @@ __global__ void __launch_bounds__(128)
   atomicAdd(out + l * N + n, acc);
 }
 
+// the same for a narrow value row (top-k-only mode: N = K <= 8): thread per level node, N register accumulators,
+// block reduction, one atomic per (block, column).  The column-per-thread kernel above leaves all but N threads idle
+// (315 ms at the 8192^2 lattice, 119 M level nodes).  grid (node blocks, L)
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+    lattice_colsum_narrow_kernel(const __grid_constant__ gngf_lattice lat, const int32_t* __restrict__ cnt,
+                                 const float* __restrict__ uvals, int N, float* __restrict__ out) {
+  const int l = blockIdx.y;
+  const int wy = lat.lwy[l];
+  const int64_t box = static_cast<int64_t>(lat.lwx[l]) * wy;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.0f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < box;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = cnt[lat.loff[l] + i];
+    if (c == 0) continue;
+    const int64_t u = global_node(lat, lat.lox[l] + static_cast<int>(i / wy), lat.loy[l] + static_cast<int>(i % wy));
+    const float cf = static_cast<float>(c);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc[n] = fmaf(cf, uvals[u * N + n], acc[n]);
+  }
+  __shared__ float red[8][NMAX];
+  const int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    const float s = warp_sum(acc[n]);
+    if (lane == 0) red[w][n] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    if (s != 0.0f) atomicAdd(out + l * N + threadIdx.x, s);
+  }
+}
+
 // out (P,L,4,N) = uvals[u(p,l,v), :]; thread per output element
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256)
@@ -354,6 +393,13 @@ int gngf_encode_hash_fwd(const float* x, int64_t P, gngf_lattice lat, gngf_table
 int gngf_lattice_colsum(gngf_lattice lat, const int32_t* cnt, const float* uvals, int64_t N, float* out, void* stream) {
   if (!gngf::valid_lat(lat) || N <= 0) return GNGF_ERR_INVALID_ARGUMENT;
   const int64_t box = gngf::max_level_box(lat);
+  if (N <= 8) {
+    dim3 grid(static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(box, 256), 8 * gngf::sm_count())), lat.num_levels);
+    gngf::lattice_colsum_narrow_kernel<8><<<grid, 256, 0, gngf::as_stream(stream)>>>(lat, cnt, uvals, static_cast<int>(N),
+                                                                                    out);
+    gngf::note_launch();
+    return gngf::check_launch();
+  }
   const int64_t nodes_per_block = std::max<int64_t>(32, gngf::ceil_div(box, 64));
   dim3 grid(static_cast<unsigned>(gngf::ceil_div(N, 128)), static_cast<unsigned>(gngf::ceil_div(box, nodes_per_block)),
             lat.num_levels);
