@@ -37,8 +37,9 @@ constexpr uint32_t YP_BYTES = SBN * 128;                  // one (k-block, plane
 constexpr uint32_t Y_STAGE_BYTES = 2 * NP * YP_BYTES;     // 32 KB
 constexpr uint32_t EP_BYTES = 128 * 128;                  // one plane of E: 128 rows x 64 bf16
 constexpr uint32_t E_BUF_BYTES = NP * EP_BYTES;           // 32 KB
-constexpr uint32_t TMEM_COLS = 256;                       // S: 2 x 64 columns, O: 128 columns
+constexpr uint32_t TMEM_COLS = 512;                       // S: 2 x 64 columns, O: 128, resident X planes: 2 x 64
 constexpr uint32_t O_COL = 128;
+constexpr uint32_t X_COL = 256;                           // plane p of X: columns [X_COL + 64 p, +64) (bf16 pairs)
 constexpr size_t SMEM_BYTES = X_BYTES + YSTAGES * Y_STAGE_BYTES + 2 * E_BUF_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* e_empty = e_full + 2;
   uint64_t* o_full = e_empty + 2;
   uint64_t* o_empty = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* xt_full = o_empty + 1;          // the epilogue warps have copied the X tile into tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, EPI_WARPS);
+    mbar_init(xt_full, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -143,7 +146,6 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy
       constexpr uint32_t idesc1 = umma_idesc(BM, SBN);
       const uint32_t idesc2 = umma_idesc(BM, n2) | UMMA_B_MN_MAJOR;
-      const uint32_t x_lo = umma_desc_lo(smem_u32(x_buf));
       const uint32_t y_lo = umma_desc_lo(smem_u32(y_ring));                      // K-major view (first product)
       const uint32_t y_lo_mn = umma_desc_lo(smem_u32(y_ring), NP * YP_BYTES);    // MN-major view (second product)
       const uint32_t e_lo = umma_desc_lo(smem_u32(e_bufs));
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
         const int nt = t1 - t0;
         if (nt <= 0) continue;
-        mbar_wait(x_full, x_phase);
+        mbar_wait(xt_full, x_phase);   // X tile resident in tensor memory (A operand of the first product)
         x_phase ^= 1;
         tc_fence_after();
         for (int j = 0; j <= nt; ++j) {
@@ -175,9 +177,11 @@ __global__ void __launch_bounds__(THREADS, 1)
                 if (kb < kblocks) {
 #pragma unroll
                   for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t ad = umma_desc_pack(x_lo + (((kb * NP + pa) * XP_BYTES + k * UMMA_K * 2) >> 4));
+                    // A from tensor memory (no shared-memory traffic: with N = 64 the product was bound by the 6 KB of
+                    // operand reads per MMA); 8 columns per K = 16 step, 32 per k-block, 64 per plane
+                    const uint32_t at = tmem_u + X_COL + pa * 64 + kb * 32 + k * 8;
                     const uint64_t bd = umma_desc_pack(yb + (((kb * NP + pb) * YP_BYTES + k * UMMA_K * 2) >> 4));
-                    umma_bf16_lead(d, ad, bd, idesc1, (pr | kb | k) != 0);
+                    umma_bf16_ts_lead(d, at, bd, idesc1, (pr | kb | k) != 0);
                   }
                 }
               }
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;       // which 32 of the 64 S columns
     const int row_l = q * 32 + lane;        // row of the X tile / of E / of O
-    uint32_t it = 0, o_phase = 0;
+    uint32_t it = 0, o_phase = 0, x_par = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int m0 = (w / n_split) * BM, sp = w % n_split;
       const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
@@ -241,6 +245,30 @@ __global__ void __launch_bounds__(THREADS, 1)
       } else {
         r_off = row_ok ? __ldg(m2neg + row) : 0.0f;
         r_scale = row_ok ? __ldg(ascale + row) : 0.0f;
+      }
+      {  // X tile: shared memory (TMA, 128-byte swizzle) -> tensor memory; warp (q, half) copies plane `half` of rows 32q..
+        mbar_wait(x_full, x_par);
+        x_par ^= 1;
+        const uint8_t* xrow = x_buf + (row_l >> 3) * 1024 + (row_l & 7) * 128;
+#pragma unroll 1
+        for (int kb = 0; kb < 2; ++kb) {
+          uint32_t v[32];
+          if (kb < kblocks) {
+            const uint8_t* src = xrow + (kb * NP + half) * XP_BYTES;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 c = *reinterpret_cast<const uint4*>(src + ((ch ^ (row_l & 7)) << 4));
+              v[ch * 4 + 0] = c.x; v[ch * 4 + 1] = c.y; v[ch * 4 + 2] = c.z; v[ch * 4 + 3] = c.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          tmem_st32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + X_COL + half * 64 + kb * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xt_full);
       }
       float rsum = 0.0f;   // DW: db3[row] = sum of E over all streamed nodes
       for (int t = t0; t < t1; ++t, ++it) {
