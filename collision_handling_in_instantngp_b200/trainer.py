@@ -23,38 +23,73 @@ from .loss import fused_loss_and_grads
 
 
 class GraphedTrainer:
+    """Whole training step (forward + loss + backward + optimizer, and under data parallelism the two exchanges) captured
+    in CUDA graphs over static input buffers.
+
+    Two buffer sets / two graphs alternate so that the host-to-device copy of batch t+1 (on a copy stream) overlaps the
+    replay of step t: `step_pipelined` never blocks the host, returns the loss of the PREVIOUS step as a host float
+    (None on the first call) and `flush()` returns the last one.  `step` is the blocking form (copy, replay; the
+    caller reads the returned device tensor)."""
+
     def __init__(self, net, optimizer, points: int, gamma: float, epsilon: float, l_mse: float = 1.0,
-                 l_js_kl: float = 1.0, channels: int = 3, warmup_steps: int = 3, sample_x=None, sample_y=None):
+                 l_js_kl: float = 1.0, channels: int = 3, warmup_steps: int = 3, sample_x=None, sample_y=None,
+                 pipelined: bool = True):
         if net._coord_bounds is None:
             raise GngfError("GraphedTrainer needs fixed lattice bounds: call net.set_coord_bounds(lo, hi) first")
         self.net, self.opt = net, optimizer
         dev = next(net.parameters()).device
+        self.dev = dev
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.loss_args = (float(gamma), float(epsilon), float(l_mse), float(l_js_kl))
         self.rows = 4 * points * self.world
-        self.x = torch.zeros((points, 2), dtype=torch.float32, device=dev)
-        self.y = torch.zeros((points, channels), dtype=torch.float32, device=dev)
-        if sample_x is not None:
-            self.x.copy_(sample_x)
-            self.y.copy_(sample_y)
-        else:       # any in-bounds coordinates will do for the warm-up steps
-            lo, hi = net._coord_bounds
-            self.x.copy_(torch.rand((points, 2), device=dev) * (torch.tensor(hi, device=dev) - torch.tensor(lo, device=dev))
-                         + torch.tensor(lo, device=dev))
+        n_sets = 2 if pipelined else 1
+        self.xs = [torch.zeros((points, 2), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+        self.ys = [torch.zeros((points, channels), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+        for x, y in zip(self.xs, self.ys):
+            if sample_x is not None:
+                x.copy_(sample_x)
+                y.copy_(sample_y)
+            else:       # any in-bounds coordinates will do for the warm-up steps
+                lo, hi = net._coord_bounds
+                x.copy_(torch.rand((points, 2), device=dev) * (torch.tensor(hi, device=dev) - torch.tensor(lo, device=dev))
+                        + torch.tensor(lo, device=dev))
         if self.world > 1:
             dp.enable_gradient_allreduce()
-        self.loss = None
-        self.graph = None
+        self.losses = [None] * n_sets          # device loss tensor of each graph
+        self.graphs = [None] * n_sets
+        self.cur = 0                           # buffer set of the next step
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.done = [None] * n_sets            # event: the last replay that read buffer set i has finished
+        self.loss_host = [torch.zeros(1).pin_memory() for _ in range(n_sets)]
+        self.loss_ready = [None] * n_sets      # event: loss_host[i] holds the loss of the last replay of set i
+        self._pending = None                   # buffer set whose loss has not been returned yet
         self._capture(warmup_steps)
 
-    def _eager_step(self):
+    # the first buffer set under the names the single-buffer version used
+    @property
+    def x(self):
+        return self.xs[0]
+
+    @property
+    def y(self):
+        return self.ys[0]
+
+    @property
+    def loss(self):
+        return self.losses[0]
+
+    @property
+    def graph(self):
+        return self.graphs[0]
+
+    def _eager_step(self, i: int = 0):
         self.opt.zero_grad(set_to_none=True)
-        rgb, probs, _, _ = self.net(self.x, 1.0)
+        rgb, probs, _, _ = self.net(self.xs[i], 1.0)
         local = probs.colsum
         # the (L, N) column sums are summed over ranks before the non-linear divergence terms (dp.py); every rank
         # evaluates the same function of the sum, so the adjoint of the local column sums is world * d_colsum
         colsum = dp.all_reduce_sum(local.detach()) if self.world > 1 else local.detach()
-        out, d_rgb, d_colsum = fused_loss_and_grads(rgb, self.y, colsum, self.rows, *self.loss_args)
+        out, d_rgb, d_colsum = fused_loss_and_grads(rgb, self.ys[i], colsum, self.rows, *self.loss_args)
         if self.world > 1:
             d_colsum = d_colsum * float(self.world)
         # the loss kernel emits its own adjoints: they seed the backward directly
@@ -67,28 +102,67 @@ class GraphedTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup_steps)):
-                self._eager_step()
+                self._eager_step(0)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if self.world > 1:
-            dist.barrier()
-        self.opt.zero_grad(set_to_none=True)
-        self.net.last_state = None
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            self.loss = self._eager_step()
-        self.graph = graph
+        for i in range(len(self.graphs)):
+            if self.world > 1:
+                dist.barrier()
+            self.opt.zero_grad(set_to_none=True)
+            self.net.last_state = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.losses[i] = self._eager_step(i)
+            self.graphs[i] = graph
+        torch.cuda.synchronize()
 
     def load_batch(self, x, y) -> None:
-        """Copies a batch (host-pinned or device tensors) into the static input buffers (asynchronous)."""
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y, non_blocking=True)
+        """Copies a batch (host-pinned or device tensors) into the first static buffer set (asynchronous)."""
+        self.xs[0].copy_(x, non_blocking=True)
+        self.ys[0].copy_(y, non_blocking=True)
 
     def replay(self) -> torch.Tensor:
-        """One training step on the batch currently in the static buffers; returns the (device) loss tensor."""
-        self.graph.replay()
-        return self.loss
+        """One training step on the batch currently in the first buffer set; returns the (device) loss tensor."""
+        self.graphs[0].replay()
+        return self.losses[0]
 
     def step(self, x, y) -> torch.Tensor:
         self.load_batch(x, y)
         return self.replay()
+
+    def step_pipelined(self, x, y):
+        """Non-blocking step: the batch is copied on the copy stream into the idle buffer set while the previous step
+        may still be running, the step is queued behind it, and its loss is copied to pinned host memory.  Returns the
+        loss of the previous step (host float; None on the first call)."""
+        i = self.cur
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            if self.done[i] is not None:
+                self.copy_stream.wait_event(self.done[i])        # the last replay reading set i is over
+            self.xs[i].copy_(x, non_blocking=True)
+            self.ys[i].copy_(y, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.copy_stream)
+        main.wait_event(copied)
+        self.graphs[i].replay()
+        self.done[i] = torch.cuda.Event()
+        self.done[i].record(main)
+        self.loss_host[i].copy_(self.losses[i].reshape(1), non_blocking=True)
+        self.loss_ready[i] = torch.cuda.Event()
+        self.loss_ready[i].record(main)
+        prev = self._take_pending()
+        self._pending = i
+        self.cur = (i + 1) % len(self.graphs)
+        return prev
+
+    def _take_pending(self):
+        if self._pending is None:
+            return None
+        j = self._pending
+        self.loss_ready[j].synchronize()
+        self._pending = None
+        return float(self.loss_host[j])
+
+    def flush(self):
+        """Waits for the last pipelined step; returns its loss (host float) or None."""
+        return self._take_pending()
