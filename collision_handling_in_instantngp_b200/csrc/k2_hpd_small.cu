@@ -164,9 +164,67 @@ __device__ __forceinline__ void small_layer(const float* __restrict__ W, const f
   }
 }
 
+// Resident-weights variant: when every layer's weight matrix fits in shared memory next to the activations (the
+// published HPD: 2-32-64-128-256 = 179 KB padded), ALL of them are requested with cp.async at kernel start -- one
+// commit group per layer -- and a layer only waits for its own group.  The weight stream (L2 -> SM) then overlaps
+// layer 0 and the earlier layers instead of being paid tile by tile inside every layer.
+// Layout: layer i at wres + woff[i], N_i rows of K_i + 4 floats.
+__device__ __forceinline__ void stage_w_resident(const float* __restrict__ W, int N, int K, float* dst) {
+  const int ld = K + 4, cpr = K / 4;
+  for (int e = threadIdx.x; e < N * cpr; e += SM_THREADS) {
+    const int r = e / cpr, c = e % cpr;
+    cp_async16(dst + r * ld + c * 4, W + static_cast<int64_t>(r) * K + c * 4);
+  }
+}
+
+__device__ __forceinline__ void small_layer_resident(const float* wsm, const float* __restrict__ bias, int K, int N,
+                                                     const float* in, float* out_t, float* logits, int ldl, bool relu,
+                                                     float* gsave, int64_t u0, int64_t U) {
+  const int j = threadIdx.x;   // N <= SM_THREADS
+  if (j >= N) return;
+  float acc[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
+  const float* wrow = wsm + j * (K + 4);
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 xa = *reinterpret_cast<const float4*>(in + (k + i) * NB);
+      const float4 xb = *reinterpret_cast<const float4*>(in + (k + i) * NB + 4);
+      acc[0] = fmaf(wv[i], xa.x, acc[0]); acc[1] = fmaf(wv[i], xa.y, acc[1]);
+      acc[2] = fmaf(wv[i], xa.z, acc[2]); acc[3] = fmaf(wv[i], xa.w, acc[3]);
+      acc[4] = fmaf(wv[i], xb.x, acc[4]); acc[5] = fmaf(wv[i], xb.y, acc[5]);
+      acc[6] = fmaf(wv[i], xb.z, acc[6]); acc[7] = fmaf(wv[i], xb.w, acc[7]);
+    }
+  }
+  const float bj = __ldg(bias + j);
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    float v = acc[n] + bj;
+    if (relu) v = fmaxf(v, 0.0f);
+    acc[n] = v;
+  }
+  if (logits) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) logits[n * ldl + j] = acc[n];
+  } else {
+    *reinterpret_cast<float4*>(out_t + j * NB) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(out_t + j * NB + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  if (gsave) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+      if (u0 + n < U) gsave[(u0 + n) * N + j] = acc[n];
+  }
+}
+
 __global__ void __launch_bounds__(SM_THREADS)
     hpd_small_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net, int K,
-                         float* __restrict__ uprobs, float* __restrict__ utopv, int32_t* __restrict__ utopi) {
+                         float* __restrict__ uprobs, float* __restrict__ utopv, int32_t* __restrict__ utopi,
+                         int resident) {
   extern __shared__ float sm[];
   float* bufA = sm;                       // [SM_MAXW][NB] unit-major activations
   float* bufB = sm + NB * SM_MAXW;        // [SM_MAXW][NB]
@@ -175,7 +233,15 @@ __global__ void __launch_bounds__(SM_THREADS)
   const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int nl = net.n_layers, T = net.width[nl];
-  float* wt = logits + NB * T;            // [2][SM_THREADS][WT_LD] weight tiles
+  float* wt = logits + NB * T;            // [2][SM_THREADS][WT_LD] weight tiles, or all layers' weights (resident)
+  if (resident) {   // request every layer's weights now; group i-1 <-> layer i
+    float* dst = wt;
+    for (int i = 1; i < nl; ++i) {
+      stage_w_resident(net.w[i], net.width[i + 1], net.width[i], dst);
+      cp_async_commit();
+      dst += net.width[i + 1] * (net.width[i] + 4);
+    }
+  }
 
   // layer 0 from the node coordinates (models.py:416: the HPD input is the integer corner)
   {
@@ -196,11 +262,27 @@ __global__ void __launch_bounds__(SM_THREADS)
   __syncthreads();
   float* in = bufA;
   float* out = bufB;
+  const float* wres = wt;
   for (int i = 1; i < nl; ++i) {
     const int Kd = net.width[i], N = net.width[i + 1];
     const bool last = i == nl - 1;
-    small_layer(net.w[i], net.b[i], Kd, N, in, out, last ? logits : nullptr, T, !last, last ? nullptr : net.act[i], u0, U,
-                wt);
+    if (resident) {
+      // groups are committed in layer order: layer i may proceed once at most (nl - 1 - i) newer groups are pending
+      switch (nl - 1 - i) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        default: cp_async_wait<4>(); break;
+      }
+      __syncthreads();
+      small_layer_resident(wres, net.b[i], Kd, N, in, out, last ? logits : nullptr, T, !last,
+                           last ? nullptr : net.act[i], u0, U);
+      wres += N * (Kd + 4);
+    } else {
+      small_layer(net.w[i], net.b[i], Kd, N, in, out, last ? logits : nullptr, T, !last, last ? nullptr : net.act[i],
+                  u0, U, wt);
+    }
     __syncthreads();
     if (!last) {
       float* t = in;
@@ -243,18 +325,32 @@ __global__ void __launch_bounds__(SM_THREADS)
                          const float* __restrict__ uprobs, const int32_t* __restrict__ utopi,
                          const float* __restrict__ dtv, const int32_t* __restrict__ cnt,
                          const float* __restrict__ gcol, const float* __restrict__ gcol_k,
-                         const float* __restrict__ gdense) {
+                         const float* __restrict__ gdense, int gt_rows, int resident) {
   extern __shared__ float sm[];
   const int nl = net.n_layers, T = net.width[nl];
-  float* gT = sm;                         // [max(T, SM_MAXW)][NB] adjoint of the current layer's pre-activation
-  float* gN = sm + SM_MAXT * NB;          // [SM_MAXW][NB] next (lower) layer's adjoint
+  float* gT = sm;                         // [gt_rows = max width][NB] adjoint of the current layer's pre-activation
+  float* gN = sm + gt_rows * NB;          // [SM_MAXW][NB] next (lower) layer's adjoint
   float* part = gN + SM_MAXW * NB;        // [2][SM_MAXW][NB] partial sums of the two j-halves
-  float* wtile = part + 2 * SM_MAXW * NB; // [2][32][SM_MAXW] weight-row tiles of the dX products
+  float* wtile = part + 2 * SM_MAXW * NB; // [2][32][SM_MAXW] weight-row tiles of the dX products, or -- resident -- every
+                                          // layer's (N_i, K_i) matrix, top layer first, requested at kernel start
   __shared__ float cl_s[NB][GNGF_MAX_LEVELS];
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int L = lat.num_levels;
+  if (resident) {   // one cp.async group per layer, in the order the backward walks them: they land during the dlogits phase
+    float* dst = wtile;
+    for (int i = nl - 1; i >= 1; --i) {
+      const int N = net.width[i + 1], Kd = net.width[i], cpr = Kd / 4;
+      for (int e = tid; e < N * cpr; e += SM_THREADS) {
+        const int r = e / cpr, c = e % cpr;
+        cp_async16(dst + r * Kd + c * 4, net.w[i] + static_cast<int64_t>(r) * Kd + c * 4);
+      }
+      cp_async_commit();
+      dst += N * Kd;
+    }
+  }
+  const float* wres = wtile;
 
   // ---- dlogits of node (u0 + warp): same arithmetic as hpd_dlogits_kernel ----
   {
@@ -350,6 +446,32 @@ __global__ void __launch_bounds__(SM_THREADS)
       float acc[NB];
 #pragma unroll
       for (int n = 0; n < NB; ++n) acc[n] = 0.0f;
+      if (resident) {
+        // layer i's matrix is group (nl - 1 - i): wait until at most (i - 1) newer groups are pending
+        switch (i - 1) {
+          case 0: cp_async_wait<0>(); break;
+          case 1: cp_async_wait<1>(); break;
+          case 2: cp_async_wait<2>(); break;
+          case 3: cp_async_wait<3>(); break;
+          default: cp_async_wait<4>(); break;
+        }
+        __syncthreads();
+        if (kk < Kd) {
+#pragma unroll 4
+          for (int j = hf; j < N; j += halves) {
+            const float w = wres[j * Kd + kk];
+            const float4 a = *reinterpret_cast<const float4*>(gT + j * NB);
+            const float4 b = *reinterpret_cast<const float4*>(gT + j * NB + 4);
+            acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+            acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+            acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]);
+            acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+          }
+#pragma unroll
+          for (int n = 0; n < NB; ++n) part[(hf * SM_MAXW + kk) * NB + n] = acc[n];
+        }
+        wres += N * Kd;
+      } else
       {
         // W_i rows stream through shared memory in tiles of TJ output units (cp.async, double-buffered): the loop was
         // bound by the L2 latency of its weight loads.  Thread (kk, hf) takes rows hf, hf + halves, ... of every tile.
@@ -423,7 +545,34 @@ __global__ void __launch_bounds__(SM_THREADS)
 }
 
 static size_t small_fwd_smem(int T) { return sizeof(float) * (2 * NB * SM_MAXW + NB * T + 2 * WT_FLOATS); }
-static size_t small_bwd_smem() { return sizeof(float) * (SM_MAXT * NB + SM_MAXW * NB + 2 * SM_MAXW * NB + 2 * 32 * SM_MAXW); }
+// resident-weights forward: every hidden/output width <= SM_THREADS, K % 4 == 0, and everything fits in 227 KB
+static size_t small_fwd_resident_smem(int n_layers, const int32_t* widths, const float* const* w) {
+  size_t wfl = 0;
+  for (int i = 1; i < n_layers; ++i) {
+    if (widths[i + 1] > SM_THREADS || (widths[i] & 3) || (reinterpret_cast<uintptr_t>(w[i]) & 15)) return 0;
+    wfl += static_cast<size_t>(widths[i + 1]) * (widths[i] + 4);
+  }
+  const size_t bytes = sizeof(float) * (2 * NB * SM_MAXW + NB * widths[n_layers] + wfl);
+  return (n_layers <= 6 && bytes <= 227 * 1024 - 1024) ? bytes : 0;
+}
+static int small_bwd_gt_rows(int n_layers, const int32_t* widths) {
+  int m = SM_MAXW;
+  for (int i = 1; i <= n_layers; ++i) m = std::max(m, widths[i]);
+  return m;
+}
+static size_t small_bwd_smem(int gt_rows) {
+  return sizeof(float) * (static_cast<size_t>(gt_rows) * NB + SM_MAXW * NB + 2 * SM_MAXW * NB + 2 * 32 * SM_MAXW);
+}
+// resident-weights backward: all (N_i, K_i) matrices of layers >= 1 in shared memory (K_i % 4 == 0)
+static size_t small_bwd_resident_smem(int n_layers, const int32_t* widths, const float* const* w, int gt_rows) {
+  size_t wfl = 0;
+  for (int i = 1; i < n_layers; ++i) {
+    if ((widths[i] & 3) || (reinterpret_cast<uintptr_t>(w[i]) & 15)) return 0;
+    wfl += static_cast<size_t>(widths[i + 1]) * widths[i];
+  }
+  const size_t bytes = sizeof(float) * (static_cast<size_t>(gt_rows) * NB + SM_MAXW * NB + 2 * SM_MAXW * NB + wfl);
+  return (n_layers <= 6 && bytes <= 227 * 1024 - 2048) ? bytes : 0;
+}
 
 }  // namespace gngf
 
@@ -451,12 +600,13 @@ int gngf_hpd_small_fwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths
     net.b[i] = b[i];
     net.act[i] = i < n_layers - 1 ? act[i] : nullptr;
   }
-  const size_t smem = gngf::small_fwd_smem(widths[n_layers]);
+  const size_t res = gngf::small_fwd_resident_smem(n_layers, widths, w);
+  const size_t smem = res ? res : gngf::small_fwd_smem(widths[n_layers]);
   if (cudaFuncSetAttribute(gngf::hpd_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(smem)) != cudaSuccess)
     return gngf::check_launch();
   gngf::hpd_small_fwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::NB)), gngf::SM_THREADS, smem,
-                               gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopv, utopi);
+                               gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopv, utopi, res ? 1 : 0);
   gngf::note_launch();
   return gngf::check_launch();
 }
@@ -481,13 +631,15 @@ int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths
     net.dbias[i] = dbias[i];
   }
   net.dw0 = dw0;
-  const size_t smem = gngf::small_bwd_smem();
+  const int gt_rows = gngf::small_bwd_gt_rows(n_layers, widths);
+  const size_t res = gngf::small_bwd_resident_smem(n_layers, widths, w, gt_rows);
+  const size_t smem = res ? res : gngf::small_bwd_smem(gt_rows);
   if (cudaFuncSetAttribute(gngf::hpd_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(smem)) != cudaSuccess)
     return gngf::check_launch();
   gngf::hpd_small_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::NB)), gngf::SM_THREADS, smem,
                                gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopi, dtv, cnt, gcol, gcol_k,
-                                                          gdense);
+                                                          gdense, gt_rows, res ? 1 : 0);
   gngf::note_launch();
   return gngf::check_launch();
 }
