@@ -51,3 +51,27 @@ def test_lattice_boxes():
     # negative coordinates (BatchNorm'd inputs): boxes follow the data
     lat = build_lattice(n_ls, (-1.5, -0.25), (2.0, 0.5))
     assert lat.lox[0] == -12 and lat.loy[0] == -2 and lat.lwx[0] == 16 - (-12) + 2
+
+
+def test_host_side_argument_validation_needs_no_gpu():
+    """Entry points reject bad arguments before touching the device; FusedAdam refuses CPU parameters (no CPU path)."""
+    import ctypes
+
+    import pytest
+    import torch
+
+    from collision_handling_in_instantngp_b200.optim import FusedAdam
+    lib = pkg.load()
+    assert lib.gngf_mlp3_tc_supported(8, 64, 64, 3) == 1 and lib.gngf_mlp3_tc_supported(65, 64, 64, 3) == 0
+    assert lib.gngf_mlp3_tc_supported(8, 32, 64, 3) == 0
+    arr = (_lib.AdamTensor * 1)()
+    assert lib.gngf_adam_step(arr, 65, 0.9, 0.99, 1e-15, None, None) == -1          # too many tensors / no ticket
+    assert lib.gngf_peer_allreduce(None, None, 0, 2, None, None, 4, 4, 1, 1.0, None, None) == -1
+    assert ctypes.sizeof(_lib.AdamTensor) == 56
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    opt = FusedAdam([p], lr=1e-3)
+    with pytest.raises(_lib.GngfError):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)

@@ -37,6 +37,13 @@ def _worker(rank, world, port, out):
     red = dp.GradientAllReducer([theta, extra])
     assert red.nbytes() == (D + 3) * 4
     red()
+    # the peer (NVLink) all-reduce is a CUDA + NCCL feature: under gloo the helpers fall back to the process group
+    assert dp.peer_allreduce_for() is None
+    t = torch.full((5,), float(rank + 1))
+    s2 = dp.all_reduce_sum(t, scale=0.5)
+    assert torch.equal(t, torch.full((5,), float(rank + 1))) and torch.equal(s2, torch.full((5,), 1.5))
+    dp.all_reduce_sum_(t, 1.0 / world)
+    assert torch.equal(t, torch.full((5,), 1.5))
     out.put((rank, theta.grad.numpy().copy(), extra.grad.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
