@@ -8,12 +8,19 @@
 // attention-shaped pair of products with E[r, t] = a_r exp(z[r, t] - max_r), a_r = -<G,p>_r / sum_r:
 //     dh  (U, Kd) = E   W3           dW3 (T, Kd) += E^T h           db3 (T) += E^T 1
 // Both are instances of ONE kernel (hpd_stream_bwd_kernel<DW>):
-//     X (128 x Kd) resident, Y tiles (64 x Kd) streamed by TMA;   S = X Y^T  (tcgen05, TMEM, double-buffered)
-//     E = rowscale_i colscale_j exp2(S log2e + rowoff_i + coloff_j)   (8 epilogue warps; E -> bf16 planes -> smem)
-//     O (128 x Kd) += E Y   (second tcgen05 product: A = E K-major from shared memory, B = the SAME Y tile read
-//                            MN-major -- no transposed copy of anything), accumulated in TMEM over all Y tiles
+//     X (128 x Kd) resident, Y tiles (128 x Kd) streamed by TMA through a 3-slot ring (X travels through it once per item)
+//     S = X Y^T   : A = the X tile, copied once per item into TENSOR MEMORY (bf16 pairs per column), B = Y from shared
+//                   memory (K-major); accumulator in TMEM, double-buffered
+//     E = rowscale_i colscale_j exp2(S log2e + rowoff_i + coloff_j)  : 8 epilogue warps read S with tcgen05.ld and write
+//                   the two bf16 planes of E back IN PLACE over S with tcgen05.st
+//     O (128 x Kd) += E Y : A = E from tensor memory, B = the SAME Y tile read MN-major (no transposed copy of anything),
+//                   accumulated in TMEM over all Y tiles
 //   DW = false:  X = h tile,  Y = W3 tiles:  O = dh tile          (rows carry (a_r, -max_r log2e), columns the bias)
 //   DW = true :  X = W3 tile, Y = h tiles :  O = dW3 tile, db3    (rows carry the bias, columns (a_r, -max_r log2e))
+// Neither product reads its A operand from shared memory: the only shared-memory operand traffic is the Y tile (4 KB
+// per 128x128x16 MMA = 64 B/clk).  History: E through shared memory with 64-row Y tiles reached 67 % of the measured
+// bf16 peak (the N = 64 first product was bound by 6 KB of operand reads per MMA), X as a TMEM operand 71 %, E in TMEM
+// with 128-row tiles 85 %.  TMEM: S/E 2 x 128 columns, O 128, X 128 = all 512.
 // Operands are two bf16 planes (hi, mid) of the fp32 values and each product is hi.hi + hi.mid + mid.hi (relative
 // error ~1e-5: the gradient tolerance is 1e-4; the forward, which must reproduce top-k selections exactly, uses three
 // planes and six products).  MMA issue order S(j+1), O(j) keeps the tensor pipe busy while the epilogue turns S(j)
@@ -26,21 +33,18 @@ namespace gngf {
 namespace tc {
 namespace sb {
 
-constexpr int SBN = 64;                                   // rows of a streamed Y tile (= columns of S and E)
+constexpr int SBN = 128;                                  // rows of a streamed Y tile (= columns of S and E)
 constexpr int NP = 2;                                     // planes used: hi, mid
-constexpr int YSTAGES = 3;
-constexpr int EPI_WARPS = 8;                              // (TMEM lane quarter) x (32-column half of the S tile)
+constexpr int RING = 3;                                   // shared-memory ring of (X | Y) tiles
+constexpr int EPI_WARPS = 8;                              // (TMEM lane quarter) x (64-column half of the S tile)
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr uint32_t XP_BYTES = 128 * 128;                  // one (k-block, plane) of X: 128 rows x 64 bf16
-constexpr uint32_t X_BYTES = 2 * NP * XP_BYTES;           // 64 KB
-constexpr uint32_t YP_BYTES = SBN * 128;                  // one (k-block, plane) of a Y tile: 64 rows x 64 bf16
-constexpr uint32_t Y_STAGE_BYTES = 2 * NP * YP_BYTES;     // 32 KB
-constexpr uint32_t EP_BYTES = 128 * 128;                  // one plane of E: 128 rows x 64 bf16
-constexpr uint32_t E_BUF_BYTES = NP * EP_BYTES;           // 32 KB
-constexpr uint32_t TMEM_COLS = 512;                       // S: 2 x 64 columns, O: 128, resident X planes: 2 x 64
-constexpr uint32_t O_COL = 128;
-constexpr uint32_t X_COL = 256;                           // plane p of X: columns [X_COL + 64 p, +64) (bf16 pairs)
-constexpr size_t SMEM_BYTES = X_BYTES + YSTAGES * Y_STAGE_BYTES + 2 * E_BUF_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TP_BYTES = 128 * 128;                  // one (k-block, plane) of a tile: 128 rows x 64 bf16
+constexpr uint32_t TILE_BYTES = 2 * NP * TP_BYTES;        // 64 KB: [k-block][plane]
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t SE_COL = 0;                            // two S / E buffers of 128 columns
+constexpr uint32_t O_COL = 256;                           // O accumulator, 128 columns
+constexpr uint32_t X_COL = 384;                           // resident X tile: plane p at [X_COL + 64 p, +64) (bf16 pairs)
+constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -49,8 +53,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // x_rows / y_rows: number of valid rows of X / Y (U or T); Kdim <= 128.
-// row_off / row_scale: per X row; col_off / col_scale: per Y row.  DW = false: row_off = -max log2e, row_scale = a,
-// col vectors come from `bias`; DW = true: the other way round.
+// DW = false: X = h tile, rows carry (a, -max log2e), columns the bias;  DW = true: X = W3 tile, the other way round.
+//
+// Data flow per (X tile, Y tile):  S = X Y^T (A = X from tensor memory, B = Y from shared memory, K-major)
+//   -> epilogue: E = scale * exp2(S log2e + offsets), two bf16 planes written IN PLACE over S in tensor memory
+//   -> O += E Y (A = E from tensor memory, B = the same Y tile read MN-major).
+// Neither product reads its A operand from shared memory, so the only shared-memory operand traffic is the Y tile
+// (4 KB per 128x128x16 MMA = 64 B/clk), and the ring holds 128-row tiles (X travels through it once per item).
 template <bool DW>
 __global__ void __launch_bounds__(THREADS, 1)
     hpd_stream_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
@@ -59,36 +68,28 @@ __global__ void __launch_bounds__(THREADS, 1)
                           float* __restrict__ dbias) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* x_buf = smem;
-  uint8_t* y_ring = smem + X_BYTES;
-  uint8_t* e_bufs = y_ring + YSTAGES * Y_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(e_bufs + 2 * E_BUF_BYTES);
-  uint64_t* x_full = bars;
-  uint64_t* x_empty = bars + 1;
-  uint64_t* y_full = bars + 2;
-  uint64_t* y_empty = y_full + YSTAGES;
-  uint64_t* s_full = y_empty + YSTAGES;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* e_full = s_empty + 2;
-  uint64_t* e_empty = e_full + 2;
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING * TILE_BYTES);
+  uint64_t* r_full = bars;                 // [RING] TMA landed
+  uint64_t* r_empty = r_full + RING;       // [RING] slot may be refilled
+  uint64_t* s_full = r_empty + RING;       // [2] S complete in tensor memory
+  uint64_t* e_full = s_full + 2;           // [2] E written over S
+  uint64_t* e_empty = e_full + 2;          // [2] second product done: the S / E buffer is free
   uint64_t* o_full = e_empty + 2;
   uint64_t* o_empty = o_full + 1;
-  uint64_t* xt_full = o_empty + 1;          // the epilogue warps have copied the X tile into tensor memory
+  uint64_t* xt_full = o_empty + 1;         // X tile copied into tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_y)) : "memory");
-    mbar_init(x_full, 1);
-    mbar_init(x_empty, 1);
-    for (int s = 0; s < YSTAGES; ++s) {
-      mbar_init(y_full + s, 1);
-      mbar_init(y_empty + s, 1);
+    for (int s = 0; s < RING; ++s) {
+      mbar_init(r_full + s, 1);
+      mbar_init(r_empty + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full + s, 1);
-      mbar_init(s_empty + s, EPI_WARPS);
       mbar_init(e_full + s, EPI_WARPS);
       mbar_init(e_empty + s, 1);
     }
@@ -115,42 +116,33 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int n2 = kblocks * BK;                // N of the second product (columns of O)
 
   if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer ----
-      int stage = 0;
-      uint32_t phase = 0, x_phase = 0;
+    if (lane == 0) {  // ---- TMA producer: per item the X tile, then its Y tiles, all through one ring ----
+      uint32_t n = 0;   // ring entries produced
+      auto load_tile = [&](const CUtensorMap* map, int row0) {
+        const uint32_t slot = n % RING, ph = (n / RING) & 1;
+        mbar_wait(r_empty + slot, ph ^ 1);
+        mbar_expect_tx(r_full + slot, kblocks * NP * TP_BYTES);
+        uint8_t* dst = ring + slot * TILE_BYTES;
+        for (int kb = 0; kb < kblocks; ++kb)
+          for (int pl = 0; pl < NP; ++pl) tma_load_3d(dst + (kb * NP + pl) * TP_BYTES, map, kb * BK, row0, pl, r_full + slot);
+        ++n;
+      };
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int m0 = (w / n_split) * BM, sp = w % n_split;
         const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
         if (t0 >= t1) continue;   // empty split (every role skips it)
-        mbar_wait(x_empty, x_phase ^ 1);
-        x_phase ^= 1;
-        mbar_expect_tx(x_full, kblocks * NP * XP_BYTES);
-        for (int kb = 0; kb < kblocks; ++kb)
-          for (int pl = 0; pl < NP; ++pl) tma_load_3d(x_buf + (kb * NP + pl) * XP_BYTES, &map_x, kb * BK, m0, pl, x_full);
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(y_empty + stage, phase ^ 1);
-          mbar_expect_tx(y_full + stage, kblocks * NP * YP_BYTES);
-          uint8_t* yb = y_ring + stage * Y_STAGE_BYTES;
-          for (int kb = 0; kb < kblocks; ++kb)
-            for (int pl = 0; pl < NP; ++pl)
-              tma_load_3d(yb + (kb * NP + pl) * YP_BYTES, &map_y, kb * BK, t * SBN, pl, y_full + stage);
-          if (++stage == YSTAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
+        load_tile(&map_x, m0);
+        for (int t = t0; t < t1; ++t) load_tile(&map_y, t * SBN);
       }
     }
   } else if (warp == 1) {
-    {  // ---- MMA issuer: the whole warp runs the loop, lane 0 issues (see tc_common.cuh) ----
+    {  // ---- MMA issuer: the whole warp runs the loop, an elected lane issues (see tc_common.cuh) ----
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy
       constexpr uint32_t idesc1 = umma_idesc(BM, SBN);
       const uint32_t idesc2 = umma_idesc(BM, n2) | UMMA_B_MN_MAJOR;
-      const uint32_t y_lo = umma_desc_lo(smem_u32(y_ring));                      // K-major view (first product)
-      const uint32_t y_lo_mn = umma_desc_lo(smem_u32(y_ring), NP * YP_BYTES);    // MN-major view (second product)
-      const uint32_t e_lo = umma_desc_lo(smem_u32(e_bufs));
-      int s1_stage = 0, s2_stage = 0;          // Y ring positions of the first / second product
-      uint32_t s1_phase = 0;
+      const uint32_t y_lo = umma_desc_lo(smem_u32(ring));                      // K-major view (first product)
+      const uint32_t y_lo_mn = umma_desc_lo(smem_u32(ring), NP * TP_BYTES);    // MN-major view (second product)
+      uint32_t nent = 0;                       // ring entries consumed before this item
       uint32_t it1 = 0, it2 = 0;               // running tile counters (S / E buffer = counter & 1)
       uint32_t x_phase = 0, o_phase = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
@@ -158,17 +150,21 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
         const int nt = t1 - t0;
         if (nt <= 0) continue;
-        mbar_wait(xt_full, x_phase);   // X tile resident in tensor memory (A operand of the first product)
+        // the epilogue warps copy the X tile (ring entry nent) into tensor memory; its slot is free afterwards
+        mbar_wait(xt_full, x_phase);
         x_phase ^= 1;
         tc_fence_after();
+        if (elect_one()) mbar_arrive(r_empty + nent % RING);
+        const uint32_t y0 = nent + 1;          // ring entry of this item's first Y tile
         for (int j = 0; j <= nt; ++j) {
           if (j < nt) {  // S(j) = X Y_j^T : products hi.hi, hi.mid, mid.hi
             const uint32_t buf = it1 & 1, ph = (it1 >> 1) & 1;
-            mbar_wait(y_full + s1_stage, s1_phase);
-            mbar_wait(s_empty + buf, ph ^ 1);
+            const uint32_t ent = y0 + j, slot = ent % RING;
+            mbar_wait(r_full + slot, (ent / RING) & 1);
+            mbar_wait(e_empty + buf, ph ^ 1);    // the second product of tile it1 - 2 has finished reading this buffer
             tc_fence_after();
-            const uint32_t yb = y_lo + s1_stage * (Y_STAGE_BYTES >> 4);
-            const uint32_t d = tmem_u + buf * SBN;
+            const uint32_t yb = y_lo + slot * (TILE_BYTES >> 4);
+            const uint32_t d = tmem_u + SE_COL + buf * SBN;
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
               const int pa = pr >> 1, pb = pr & 1;   // (0,0) (0,1) (1,0)
@@ -177,10 +173,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                 if (kb < kblocks) {
 #pragma unroll
                   for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // A from tensor memory (no shared-memory traffic: with N = 64 the product was bound by the 6 KB of
-                    // operand reads per MMA); 8 columns per K = 16 step, 32 per k-block, 64 per plane
+                    // A: resident X tile in tensor memory, 8 columns per K = 16 step, 32 per k-block, 64 per plane
                     const uint32_t at = tmem_u + X_COL + pa * 64 + kb * 32 + k * 8;
-                    const uint64_t bd = umma_desc_pack(yb + (((kb * NP + pb) * YP_BYTES + k * UMMA_K * 2) >> 4));
+                    const uint64_t bd = umma_desc_pack(yb + (((kb * NP + pb) * TP_BYTES + k * UMMA_K * 2) >> 4));
                     umma_bf16_ts_lead(d, at, bd, idesc1, (pr | kb | k) != 0);
                   }
                 }
@@ -188,50 +183,47 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
             umma_commit_lead(s_full + buf);
             ++it1;
-            if (++s1_stage == YSTAGES) {
-              s1_stage = 0;
-              s1_phase ^= 1;
-            }
           }
           if (j >= 1) {  // O += E(j-1) Y_{j-1}
             const uint32_t buf = it2 & 1, ph = (it2 >> 1) & 1;
+            const uint32_t slot = (y0 + j - 1) % RING;
             mbar_wait(e_full + buf, ph);
             if (j == 1) {
               mbar_wait(o_empty, o_phase ^ 1);   // the previous item's O has been read out
               o_phase ^= 1;
             }
             tc_fence_after();
-            const uint32_t eb = e_lo + buf * (E_BUF_BYTES >> 4);
-            const uint32_t yb = y_lo_mn + s2_stage * (Y_STAGE_BYTES >> 4);
+            const uint32_t eb = tmem_u + SE_COL + buf * SBN;
+            const uint32_t yb = y_lo_mn + slot * (TILE_BYTES >> 4);
             const uint32_t d = tmem_u + O_COL;
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr) {
               const int pa = pr >> 1, pb = pr & 1;
 #pragma unroll
               for (int k = 0; k < SBN / UMMA_K; ++k) {
-                // A: E plane, K-major (K = streamed index, 16 columns = 32 bytes per step)
-                const uint64_t ad = umma_desc_pack(eb + ((pa * EP_BYTES + k * UMMA_K * 2) >> 4));
-                // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*YP_BYTES apart),
+                // A: E plane pa in tensor memory: S columns 16k.. live at packed columns 64 (k / 4) + 32 pa + 8 (k % 4)
+                const uint32_t at = eb + 64 * (k >> 2) + 32 * pa + 8 * (k & 3);
+                // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*TP_BYTES apart),
                 //    K = streamed index (rows of 128 bytes, 16 rows = 2048 bytes per step)
-                const uint64_t bd = umma_desc_pack(yb + ((pb * YP_BYTES + k * UMMA_K * 128) >> 4));
-                umma_bf16_lead(d, ad, bd, idesc2, (j != 1) || (pr | k) != 0);
+                const uint64_t bd = umma_desc_pack(yb + ((pb * TP_BYTES + k * UMMA_K * 128) >> 4));
+                umma_bf16_ts_lead(d, at, bd, idesc2, (j != 1) || (pr | k) != 0);
               }
             }
             umma_commit_lead(e_empty + buf);
-            umma_commit_lead(y_empty + s2_stage);
+            umma_commit_lead(r_empty + slot);
             ++it2;
-            if (++s2_stage == YSTAGES) s2_stage = 0;
           }
         }
         umma_commit_lead(o_full);
-        umma_commit_lead(x_empty);
+        nent += 1 + nt;
       }
     }
   } else {  // ---- epilogue warps 2..9 ----
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which 32 of the 64 S columns
+    const int half = (warp - 2) >> 2;       // which 64 of the 128 S columns
     const int row_l = q * 32 + lane;        // row of the X tile / of E / of O
-    uint32_t it = 0, o_phase = 0, x_par = 0;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t it = 0, o_phase = 0, nent = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int m0 = (w / n_split) * BM, sp = w % n_split;
       const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
@@ -246,15 +238,15 @@ __global__ void __launch_bounds__(THREADS, 1)
         r_off = row_ok ? __ldg(m2neg + row) : 0.0f;
         r_scale = row_ok ? __ldg(ascale + row) : 0.0f;
       }
-      {  // X tile: shared memory (TMA, 128-byte swizzle) -> tensor memory; warp (q, half) copies plane `half` of rows 32q..
-        mbar_wait(x_full, x_par);
-        x_par ^= 1;
-        const uint8_t* xrow = x_buf + (row_l >> 3) * 1024 + (row_l & 7) * 128;
+      {  // X tile: ring slot (TMA, 128-byte swizzle) -> tensor memory; warp (q, half) copies plane `half` of rows 32q..
+        const uint32_t slot = nent % RING;
+        mbar_wait(r_full + slot, (nent / RING) & 1);
+        const uint8_t* xrow = ring + slot * TILE_BYTES + (row_l >> 3) * 1024 + (row_l & 7) * 128;
 #pragma unroll 1
         for (int kb = 0; kb < 2; ++kb) {
           uint32_t v[32];
           if (kb < kblocks) {
-            const uint8_t* src = xrow + (kb * NP + half) * XP_BYTES;
+            const uint8_t* src = xrow + (kb * NP + half) * TP_BYTES;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
               const uint4 c = *reinterpret_cast<const uint4*>(src + ((ch ^ (row_l & 7)) << 4));
@@ -264,87 +256,81 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
-          tmem_st32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + X_COL + half * 64 + kb * 32, v);
+          tmem_st32(tmem_base + lane_off + X_COL + half * 64 + kb * 32, v);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(xt_full);
+        nent += 1 + (t1 - t0);
       }
       float rsum = 0.0f;   // DW: db3[row] = sum of E over all streamed nodes
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        const int c0 = t * SBN + half * 32;
+        const uint32_t se = tmem_base + lane_off + SE_COL + buf * SBN + half * 64;
         mbar_wait(s_full + buf, ph);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * SBN + half * 32, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty + buf);     // S(buf) may be overwritten by the next-but-one product
-
-        float e[32];
-        if (c0 + 32 <= y_rows) {
+        uint32_t hi[32], mid[32];   // this thread's 64 columns of E as bf16 pairs: hi plane, mid plane
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 off, sc;
-            if (DW) {
-              off = __ldg(reinterpret_cast<const float4*>(m2neg + c0 + j));
-              sc = __ldg(reinterpret_cast<const float4*>(ascale + c0 + j));
-            } else {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-              off = make_float4(b.x * LOG2E, b.y * LOG2E, b.z * LOG2E, b.w * LOG2E);
-              sc = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-            }
-            e[j + 0] = exp2f(fmaf(__uint_as_float(v[j + 0]), LOG2E, r_off + off.x)) * (r_scale * sc.x);
-            e[j + 1] = exp2f(fmaf(__uint_as_float(v[j + 1]), LOG2E, r_off + off.y)) * (r_scale * sc.y);
-            e[j + 2] = exp2f(fmaf(__uint_as_float(v[j + 2]), LOG2E, r_off + off.z)) * (r_scale * sc.z);
-            e[j + 3] = exp2f(fmaf(__uint_as_float(v[j + 3]), LOG2E, r_off + off.w)) * (r_scale * sc.w);
-          }
-        } else {
+        for (int cb = 0; cb < 2; ++cb) {
+          const int c0 = t * SBN + half * 64 + cb * 32;
+          uint32_t v[32];
+          tmem_ld32(se + cb * 32, v);
+          float e[32];
+          if (c0 + 32 <= y_rows) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            float off = 0.0f, sc = 0.0f;
-            if (c < y_rows) {
+            for (int j = 0; j < 32; j += 4) {
+              float4 off, sc;
               if (DW) {
-                off = __ldg(m2neg + c);
-                sc = __ldg(ascale + c);
+                off = __ldg(reinterpret_cast<const float4*>(m2neg + c0 + j));
+                sc = __ldg(reinterpret_cast<const float4*>(ascale + c0 + j));
               } else {
-                off = __ldg(bias + c) * LOG2E;
-                sc = 1.0f;
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                off = make_float4(b.x * LOG2E, b.y * LOG2E, b.z * LOG2E, b.w * LOG2E);
+                sc = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
               }
+              e[j + 0] = exp2f(fmaf(__uint_as_float(v[j + 0]), LOG2E, r_off + off.x)) * (r_scale * sc.x);
+              e[j + 1] = exp2f(fmaf(__uint_as_float(v[j + 1]), LOG2E, r_off + off.y)) * (r_scale * sc.y);
+              e[j + 2] = exp2f(fmaf(__uint_as_float(v[j + 2]), LOG2E, r_off + off.z)) * (r_scale * sc.z);
+              e[j + 3] = exp2f(fmaf(__uint_as_float(v[j + 3]), LOG2E, r_off + off.w)) * (r_scale * sc.w);
             }
-            const float ev = exp2f(fmaf(__uint_as_float(v[j]), LOG2E, r_off + off)) * (r_scale * sc);
-            e[j] = c < y_rows ? ev : 0.0f;   // (zero-filled Y rows give S = 0, not a logit: exp2 may overflow there)
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = c0 + j;
+              float off = 0.0f, sc = 0.0f;
+              if (c < y_rows) {
+                if (DW) {
+                  off = __ldg(m2neg + c);
+                  sc = __ldg(ascale + c);
+                } else {
+                  off = __ldg(bias + c) * LOG2E;
+                  sc = 1.0f;
+                }
+              }
+              const float ev = exp2f(fmaf(__uint_as_float(v[j]), LOG2E, r_off + off)) * (r_scale * sc);
+              e[j] = c < y_rows ? ev : 0.0f;   // (zero-filled Y rows give S = 0, not a logit: exp2 may overflow there)
+            }
+          }
+          if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) e[j] = 0.0f;
+          }
+          if (DW) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rsum += e[j];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = e[2 * i], b = e[2 * i + 1];
+            const uint32_t h2 = pack_bf16x2(a, b);
+            hi[cb * 16 + i] = h2;
+            mid[cb * 16 + i] = pack_bf16x2(a - __uint_as_float(h2 << 16), b - __uint_as_float(h2 & 0xffff0000u));
           }
         }
-        if (!row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) e[j] = 0.0f;
-        }
-        if (DW) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rsum += e[j];
-        }
-
-        // E -> two bf16 planes, K-major with the 128-byte swizzle: 16-byte chunk ch of row r lives at chunk ch ^ (r & 7)
-        mbar_wait(e_empty + buf, ph ^ 1);
-        uint8_t* eb = e_bufs + buf * E_BUF_BYTES + (row_l >> 3) * 1024 + (row_l & 7) * 128;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t hi[4], mid[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float a = e[ch * 8 + 2 * i], b = e[ch * 8 + 2 * i + 1];
-            hi[i] = pack_bf16x2(a, b);
-            const float ah = __uint_as_float(hi[i] << 16), bh = __uint_as_float(hi[i] & 0xffff0000u);
-            mid[i] = pack_bf16x2(a - ah, b - bh);
-          }
-          const int pch = ((half * 4 + ch) ^ (row_l & 7)) * 16;
-          *reinterpret_cast<uint4*>(eb + pch) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(eb + EP_BYTES + pch) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-        }
-        fence_proxy_async();
+        // E over S, in place: this thread's 64 fp32 columns become 32 columns of hi pairs + 32 columns of mid pairs
+        tmem_st32(se, hi);
+        tmem_st32(se + 32, mid);
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(e_full + buf);
       }
@@ -359,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int col0 = half * 64 + cc;
         if (col0 >= n2) continue;   // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + O_COL + col0, v);
+        tmem_ld32(tmem_base + lane_off + O_COL + col0, v);
         if (row_ok) {
           float* o = out + static_cast<int64_t>(row) * Kdim + col0;
           if ((Kdim & 3) == 0 && col0 + 32 <= Kdim) {
@@ -511,11 +497,9 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16
   int rc = gngf::check_launch();
   if (rc) return rc;
 
-  CUtensorMap map_h128, map_h64, map_w128, map_w64;
-  if ((rc = make_plane_map(&map_h128, h_planes, U, Kdim, BM))) return rc;
-  if ((rc = make_plane_map(&map_h64, h_planes, U, Kdim, SBN))) return rc;
-  if ((rc = make_plane_map(&map_w128, w_planes, T, Kdim, BM))) return rc;
-  if ((rc = make_plane_map(&map_w64, w_planes, T, Kdim, SBN))) return rc;
+  CUtensorMap map_h, map_w;   // 128-row boxes serve both roles (resident X tile, streamed Y tiles)
+  if ((rc = make_plane_map(&map_h, h_planes, U, Kdim, BM))) return rc;
+  if ((rc = make_plane_map(&map_w, w_planes, T, Kdim, BM))) return rc;
   if (cudaFuncSetAttribute(hpd_stream_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(SMEM_BYTES)) != cudaSuccess ||
       cudaFuncSetAttribute(hpd_stream_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -526,7 +510,7 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16
     const int64_t xt = gngf::ceil_div(U, BM), yt = gngf::ceil_div(T, SBN);
     const int ns = split_count(xt, yt);
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
-    hpd_stream_bwd_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(map_h128, map_w64, static_cast<int>(U),
+    hpd_stream_bwd_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(map_h, map_w, static_cast<int>(U),
                                                                    static_cast<int>(T), static_cast<int>(Kdim), ns, bias,
                                                                    m2neg, ascale, dh, nullptr);
     gngf::note_launch();
@@ -536,7 +520,7 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16
     const int64_t xt = gngf::ceil_div(T, BM), yt = gngf::ceil_div(U, SBN);
     const int ns = split_count(xt, yt);
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
-    hpd_stream_bwd_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(map_w128, map_h64, static_cast<int>(T),
+    hpd_stream_bwd_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(map_w, map_h, static_cast<int>(T),
                                                                   static_cast<int>(U), static_cast<int>(Kdim), ns, bias,
                                                                   m2neg, ascale, dw, db);
     gngf::note_launch();
