@@ -33,8 +33,14 @@ __global__ void __launch_bounds__(ADAM_THREADS)
   const gngf_adam_tensor& T = a.t[lo];
   const int t_now = *T.step + 1;
   const int64_t chunk = b - (lo ? a.chunk_end[lo - 1] : 0);
-  const float bc1 = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), t_now));
-  const float bc2 = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), t_now));
+  // bias corrections: one double-precision evaluation per block (a per-thread pow() dominated this small kernel)
+  __shared__ float bc_s[2];
+  if (threadIdx.x == 0) {
+    bc_s[0] = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), t_now));
+    bc_s[1] = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), t_now));
+  }
+  __syncthreads();
+  const float bc1 = bc_s[0], bc2 = bc_s[1];
   const float step_size = T.lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const float wd = T.weight_decay, omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
