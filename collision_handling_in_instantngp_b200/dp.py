@@ -125,8 +125,10 @@ class _AllReduceSum(torch.autograd.Function):
 
 
 def all_reduce_colsum(colsum: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum of the per-rank column sums, differentiable (see module docstring)."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    """Sum of the per-rank column sums, differentiable (see module docstring).  A no-op once
+    `enable_gradient_allreduce` has installed the in-forward exchange (the module then returns the summed tensor)."""
+    from . import ops
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or ops.COLSUM_REDUCE_HOOK is not None:
         return colsum
     return _AllReduceSum.apply(colsum, group)
 
@@ -168,13 +170,16 @@ class GradientAllReducer:
 
 
 def enable_gradient_allreduce(group=None) -> None:
-    """Averages the parameter gradients over ranks inside GNGFPath.backward: all of them are views of one flat
-    buffer there, so it is a single in-place all-reduce and no flatten / unflatten copies (vs. GradientAllReducer,
-    which works on arbitrary parameter lists)."""
+    """Installs both data-parallel exchanges inside GNGFPath: (1) the parameter gradients are averaged over ranks at
+    the end of the backward -- all of them are views of one flat buffer there, so it is a single in-place all-reduce
+    and no flatten / unflatten copies (vs. GradientAllReducer, which works on arbitrary parameter lists); (2) the
+    (L, N) column sums are summed over ranks inside the forward, on the side stream that produces them, so that the
+    exchange overlaps the decoder; `probs.colsum` is then the global sum and `all_reduce_colsum` a no-op."""
     from . import ops
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         ops.GRAD_REDUCE_HOOK = None
+        ops.COLSUM_REDUCE_HOOK = None
         return
     world = dist.get_world_size(group)
     peer_allreduce_for(group)       # collective set-up now, not inside the first (possibly graph-captured) step
@@ -182,7 +187,12 @@ def enable_gradient_allreduce(group=None) -> None:
     def hook(flat: torch.Tensor) -> None:
         all_reduce_sum_(flat, 1.0 / world, group)
 
+    def colsum_hook(colsum: torch.Tensor) -> int:
+        all_reduce_sum_(colsum, 1.0, group)
+        return world
+
     ops.GRAD_REDUCE_HOOK = hook
+    ops.COLSUM_REDUCE_HOOK = colsum_hook
 
 
 def shard_bounds(total: int, rank: int, world: int):

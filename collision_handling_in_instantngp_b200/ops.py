@@ -24,8 +24,14 @@ from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, MIX_RAW, MIX
 
 MAX_DENSE_LOGIT_BYTES = 96 << 30   # (U, T) fp32 logits are materialised by this path
 
-# data parallelism: called on the flat gradient buffer at the end of GNGFPath.backward (dp.enable_gradient_allreduce)
+# data parallelism (dp.enable_gradient_allreduce):
+#   GRAD_REDUCE_HOOK(flat)      in-place mean over ranks of the flat gradient buffer, at the end of GNGFPath.backward
+#   COLSUM_REDUCE_HOOK(colsum)  in-place sum over ranks of the (L, N) column sums, right behind the kernel that produces
+#                               them -- on the side stream, so the exchange overlaps the decoder forward; returns the
+#                               world size (the adjoint of the local column sums is world * the adjoint of the sum,
+#                               because every rank evaluates the same function of it)
 GRAD_REDUCE_HOOK = None
+COLSUM_REDUCE_HOOK = None
 
 
 def _stream() -> int:
@@ -315,6 +321,7 @@ class ForwardState:
     mlp_tc: bool = False                                         # decoder ran on the tensor cores (k6_mlp_tc.cu)
     mlp_masks: Optional[torch.Tensor] = None                     # (P,4) int32 ReLU pattern of the hidden layers
     idx_topk: Optional[torch.Tensor] = None                      # (P,L,4,K) int64, the API output (models.py:476-484)
+    colsum_world: int = 1                                        # > 1: the column sums were summed over that many ranks
     err_flag: Optional[torch.Tensor] = None
 
 
@@ -460,6 +467,8 @@ class GNGFPath(torch.autograd.Function):
                 # node multiplicities from the per-cell counts of the point pass (one atomic per (point, level))
                 call("gngf_cell_to_node_counts", lat, cell_cnt.data_ptr(), state.cnt.data_ptr(), _stream())
                 call("gngf_lattice_colsum", lat, state.cnt.data_ptr(), uvals.data_ptr(), N, colsum.data_ptr(), _stream())
+                if COLSUM_REDUCE_HOOK is not None:
+                    state.colsum_world = int(COLSUM_REDUCE_HOOK(colsum))
 
         state.mlp_fused = _mlp3_supported(mlp_w)
         if state.mlp_fused:
@@ -581,6 +590,8 @@ class GNGFPath(torch.autograd.Function):
         gcol = gcol_k = gdense = None
         if grad_colsum is not None:
             grad_colsum = _f32c(grad_colsum)
+            if state.colsum_world > 1:
+                grad_colsum = grad_colsum * float(state.colsum_world)
             if cfg.topk_only:
                 gcol_k = grad_colsum
             else:

@@ -85,15 +85,13 @@ class GraphedTrainer:
     def _eager_step(self, i: int = 0):
         self.opt.zero_grad(set_to_none=True)
         rgb, probs, _, _ = self.net(self.xs[i], 1.0)
-        local = probs.colsum
-        # the (L, N) column sums are summed over ranks before the non-linear divergence terms (dp.py); every rank
-        # evaluates the same function of the sum, so the adjoint of the local column sums is world * d_colsum
-        colsum = dp.all_reduce_sum(local.detach()) if self.world > 1 else local.detach()
+        # under data parallelism `probs.colsum` already is the sum over ranks: the exchange happens inside the forward,
+        # on the side stream that produces the column sums (dp.enable_gradient_allreduce), and the backward scales the
+        # adjoint by the world size
+        colsum = probs.colsum
         out, d_rgb, d_colsum = fused_loss_and_grads(rgb, self.ys[i], colsum, self.rows, *self.loss_args)
-        if self.world > 1:
-            d_colsum = d_colsum * float(self.world)
         # the loss kernel emits its own adjoints: they seed the backward directly
-        torch.autograd.backward([rgb, local], [d_rgb, d_colsum])
+        torch.autograd.backward([rgb, colsum], [d_rgb, d_colsum])
         self.opt.step()
         return out[0]
 
