@@ -180,8 +180,8 @@ class CallProfiler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/r01_*_ncu_full.txt); None where no capture exists yet
 NCU_TRAFFIC = {("cfg2", "gngf_mlp3_bwd"): 2606080, ("cfg2", "gngf_mlp3_fwd"): 1892096,
-               ("cfg2", "gngf_mlp3_tc_bwd"): 4259840, ("cfg2", "gngf_mlp3_tc_fwd"): 1924608,
-               ("cfg3_t14", "gngf_hpd_stream_bwd"): 438117632,
+               ("cfg2", "gngf_mlp3_tc_bwd"): 4264960, ("cfg2", "gngf_mlp3_tc_fwd"): 1924608,
+               ("cfg3_t14", "gngf_hpd_stream_bwd"): 441328128,
                ("cfg3_t14", "gngf_hpd_stream_fwd"): 154538000, ("cfg3_t14", "gngf_tc_gemm_bf16x3"): 2802181000}
 
 
