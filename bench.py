@@ -222,6 +222,8 @@ def algorithmic_cost(name, key, w, lat):
     # the useful figure is reported next to it (roofline.useful_tflops)
     if name == "gngf_hpd_stream_fwd":
         return "tensor", 6 * 2.0 * U * T * kd
+    if name == "gngf_hpd_stream_fwd_refined":      # two planes, three split products (+ an fp32 refinement of 8 candidates)
+        return "tensor", 3 * 2.0 * U * T * kd
     if name == "gngf_tc_gemm_bf16x3":
         return "tensor", 6 * 2.0 * float(key[0]) * key[1] * key[2]
     if name == "gngf_hpd_stream_bwd":
@@ -253,6 +255,8 @@ def useful_tflops(name, achieved, w):
     """The share of the executed tensor-core FLOPs that the fp32 algorithm asks for (one pass per product)."""
     if name in ("gngf_hpd_stream_fwd", "gngf_tc_gemm_bf16x3"):
         return achieved / 6
+    if name == "gngf_hpd_stream_fwd_refined":
+        return achieved / 3
     if name == "gngf_hpd_stream_bwd":
         return achieved / 6                       # 12 executed passes for the 2 gradient products
     if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):

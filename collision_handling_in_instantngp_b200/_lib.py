@@ -79,6 +79,9 @@ SIGNATURES = {
     "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "gngf_hpd_stream_workspace_floats": (c_int64, [c_int64, c_int64, c_int32]),
     "gngf_hpd_stream_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
+    "gngf_hpd_stream_refined_workspace_floats": (c_int64, [c_int64, c_int64]),
+    "gngf_hpd_stream_fwd_refined": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P,
+                                            _P]),
     "gngf_hpd_stream_bwd_workspace_floats": (c_int64, [c_int64, c_int32]),
     "gngf_hpd_stream_bwd": (c_int, [Lattice, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P,
                                     _P, _P, c_int32, _P, _P, _P, _P, _P]),

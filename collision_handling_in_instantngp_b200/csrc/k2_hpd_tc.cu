@@ -252,6 +252,11 @@ __device__ __forceinline__ void top_insert(RowTop& t, int K, float z, int n) {
   }
 }
 
+// NPROD = 6: three planes, all products of order <= 2 (1.5e-6: selections exact on their own);
+// NPROD = 3: two planes, hi.hi + hi.mid + mid.hi (1e-5) -- half the tensor-core work; the caller then keeps KTOP = 8
+// candidates per row and re-evaluates them in fp32 (hpd_stream_refine_kernel), which restores exact selections and
+// 1e-6 probabilities as long as the true top-K lie within the approximate top-8.
+template <int NPROD>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
     hpd_stream_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const float* __restrict__ bias, int U, int T, int Kdim, int topk, int n_split,
@@ -308,17 +313,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int m0 = (w / n_split) * BM, sp = w % n_split;
         const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
+        constexpr int NPL = NPROD == 3 ? 2 : PLANES;   // planes actually loaded (the layout keeps room for three)
         mbar_wait(a_empty, a_phase ^ 1);
-        mbar_expect_tx(a_full, kblocks * PLANES * PLANE_BYTES);
+        mbar_expect_tx(a_full, kblocks * NPL * PLANE_BYTES);
         for (int kb = 0; kb < kblocks; ++kb)
-          for (int pl = 0; pl < PLANES; ++pl)
+          for (int pl = 0; pl < NPL; ++pl)
             tma_load_3d(a_buf + (kb * PLANES + pl) * PLANE_BYTES, &map_a, kb * BK, m0, pl, a_full);
         a_phase ^= 1;
         for (int nt = nt0; nt < nt1; ++nt) {
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(b_empty + stage, phase ^ 1);
-            mbar_expect_tx(b_full + stage, B_STAGE_BYTES);
-            for (int pl = 0; pl < PLANES; ++pl)
+            mbar_expect_tx(b_full + stage, NPL * PLANE_BYTES);
+            for (int pl = 0; pl < NPL; ++pl)
               tma_load_3d(b_ring + stage * B_STAGE_BYTES + pl * PLANE_BYTES, &map_b, kb * BK, nt * BN, pl, b_full + stage);
             if (++stage == STAGES) {
               stage = 0;
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
             const uint32_t a_lo = a_lo0 + kb * ((PLANES * PLANE_BYTES) >> 4);
             const uint32_t b_lo = b_lo0 + stage * (B_STAGE_BYTES >> 4);
 #pragma unroll
-            for (int pr = 0; pr < 6; ++pr) {
+            for (int pr = 0; pr < NPROD; ++pr) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint64_t ad = umma_desc_pack(a_lo + ((pa[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
@@ -503,7 +509,10 @@ __global__ void __launch_bounds__(128)
     hpd_stream_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                             const float* __restrict__ part_topv, const int* __restrict__ part_topi, int U, int n_parts,
                             int topk, float* __restrict__ row_max, float* __restrict__ row_sum,
-                            float* __restrict__ utopv, int* __restrict__ utopi) {
+                            float* __restrict__ utopv, int* __restrict__ utopi, float* __restrict__ cand_v,
+                            int* __restrict__ cand_i) {
+  // cand_v / cand_i (U, KTOP), optional: the merged top-KTOP (approximate logits, indices) for hpd_stream_refine_kernel;
+  // utopv / utopi are then not written (topk = number of entries stored per part)
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= U) return;
   float M2 = -INFINITY;
@@ -529,6 +538,14 @@ __global__ void __launch_bounds__(128)
   S *= exp2f(M2 - M * LOG2E);
   if (row_max) row_max[row] = M;
   if (row_sum) row_sum[row] = S;
+  if (cand_v) {
+#pragma unroll
+    for (int k = 0; k < KTOP; ++k) {
+      cand_v[static_cast<int64_t>(row) * KTOP + k] = top.v[k];
+      cand_i[static_cast<int64_t>(row) * KTOP + k] = top.i[k];
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < KTOP; ++k) {
     if (k < topk) {
@@ -537,6 +554,84 @@ __global__ void __launch_bounds__(128)
       utopv[static_cast<int64_t>(row) * topk + k] = p;
       utopi[static_cast<int64_t>(row) * topk + k] = top.i[k];
     }
+  }
+}
+
+// Refinement of the two-plane (1e-5) streaming pass: warp per node.  The KTOP = 8 candidates' logits are re-evaluated
+// in fp32 (z = <h[u,:], W[t,:]> + b[t]), re-ranked (value desc, index asc), and the softmax statistics are corrected for
+// the exact maximum and the exact candidate terms: everything the caller sees about the selected slots is then as
+// accurate as an fp32 evaluation of those logits; only the sum of the remaining (individually tiny) terms carries the
+// 1e-5 of the approximate pass.  row_max / row_sum hold the approximate statistics on entry, the corrected ones on exit.
+__global__ void __launch_bounds__(256)
+    hpd_stream_refine_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias, int U,
+                             int T, int Kdim, int topk, const float* __restrict__ cand_v, const int* __restrict__ cand_i,
+                             float* __restrict__ row_max, float* __restrict__ row_sum, float* __restrict__ utopv,
+                             int* __restrict__ utopi) {
+  const int64_t u = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (u >= U) return;
+  const int c0 = lane * 4;   // Kdim <= 128, Kdim % 4 == 0
+  float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c0 < Kdim) hv = *reinterpret_cast<const float4*>(h + u * Kdim + c0);
+  float z[KTOP], za[KTOP];
+  int idx[KTOP];
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    idx[k] = cand_i[u * KTOP + k];
+    za[k] = cand_v[u * KTOP + k];
+    float acc = 0.0f;
+    if (idx[k] >= 0 && idx[k] < T && c0 < Kdim) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<int64_t>(idx[k]) * Kdim + c0));
+      acc = fmaf(hv.w, wv.w, fmaf(hv.z, wv.z, fmaf(hv.y, wv.y, hv.x * wv.x)));
+    }
+    acc = warp_sum(acc);
+    z[k] = (idx[k] >= 0 && idx[k] < T) ? acc + __ldg(bias + idx[k]) : -INFINITY;   // (fewer than KTOP slots: T < 8)
+  }
+  // re-rank (insertion sort of 8, every lane redundantly)
+  float zs[KTOP];
+  int is[KTOP];
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    zs[k] = -INFINITY;
+    is[k] = 0x7fffffff;
+  }
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k) {
+    float cz = z[k];
+    int ci = idx[k];
+#pragma unroll
+    for (int j = 0; j < KTOP; ++j) {
+      const bool sw = (cz > zs[j]) || (cz == zs[j] && ci < is[j]);
+      const float tz = zs[j];
+      const int tn = is[j];
+      zs[j] = sw ? cz : tz;
+      is[j] = sw ? ci : tn;
+      cz = sw ? tz : cz;
+      ci = sw ? tn : ci;
+    }
+  }
+  const float Ma = row_max[u], M = zs[0];
+  float S = row_sum[u] * expf(Ma - M);
+#pragma unroll
+  for (int k = 0; k < KTOP; ++k)
+    if (z[k] > -INFINITY) S += expf(z[k] - M) - expf(za[k] - M);
+  if (lane == 0) {
+    row_max[u] = M;
+    row_sum[u] = S;
+  }
+  if (lane < topk) {
+    float zk = zs[0];
+    int ik = is[0];
+#pragma unroll
+    for (int k = 1; k < KTOP; ++k)
+      if (lane == k) {
+        zk = zs[k];
+        ik = is[k];
+      }
+    float p = expf(zk - M) / S;
+    if (p != p) p = 0.0f;
+    utopv[u * topk + lane] = p;
+    utopi[u * topk + lane] = ik;
   }
 }
 
@@ -666,18 +761,69 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
   float* part_topv = part_sum + U * n_parts;
   int* part_topi = reinterpret_cast<int*>(part_topv + U * n_parts * topk);
   cudaStream_t st = gngf::as_stream(stream);
-  if (cudaFuncSetAttribute(hpd_stream_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(hpd_stream_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(STREAM_SMEM_BYTES)) != cudaSuccess)
     return gngf::check_launch();
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
-  hpd_stream_fwd_kernel<<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
-                                                                  static_cast<int>(T), static_cast<int>(Kdim), topk,
-                                                                  n_split, part_max, part_sum, part_topv, part_topi);
+  hpd_stream_fwd_kernel<6><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
+                                                                     static_cast<int>(T), static_cast<int>(Kdim), topk,
+                                                                     n_split, part_max, part_sum, part_topv, part_topi);
   gngf::note_launch();
   rc = gngf::check_launch();
   if (rc) return rc;
   hpd_stream_merge_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 128)), 128, 0, st>>>(
       part_max, part_sum, part_topv, part_topi, static_cast<int>(U), static_cast<int>(n_parts), topk, row_max, row_sum,
+      utopv, utopi, nullptr, nullptr);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int64_t gngf_hpd_stream_refined_workspace_floats(int64_t U, int64_t T) {
+  using namespace gngf::tc;
+  // partial records with KTOP candidates each + the merged candidates (U, KTOP) x (value, index)
+  return gngf_hpd_stream_workspace_floats(U, T, KTOP) + 2 * U * KTOP + 4;
+}
+
+int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const uint16_t* b_planes, const float* h, const float* w,
+                                const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk, float* utopv,
+                                int32_t* utopi, float* row_max, float* row_sum, float* workspace, void* stream) {
+  using namespace gngf::tc;
+  if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > A_KBLOCKS * BK || topk <= 0 || 2 * topk > KTOP ||
+      topk > T || U >= (1ll << 31) || T >= (1ll << 31) || !h || !w || !row_max || !row_sum)
+    return GNGF_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w)) & 15) return GNGF_ERR_INVALID_ARGUMENT;
+  CUtensorMap map_a, map_b;
+  int rc = make_plane_map(&map_a, a_planes, U, Kdim);
+  if (rc) return rc;
+  rc = make_plane_map(&map_b, b_planes, T, Kdim);
+  if (rc) return rc;
+  const int64_t row_tiles = gngf::ceil_div(U, BM), col_tiles = gngf::ceil_div(T, BN);
+  const int n_split =
+      static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(col_tiles, (2 * gngf::sm_count()) / row_tiles)));
+  const int64_t n_parts = static_cast<int64_t>(STREAM_COL_PARTS) * n_split;
+  float* part_max = workspace;
+  float* part_sum = part_max + U * n_parts;
+  float* part_topv = part_sum + U * n_parts;
+  int* part_topi = reinterpret_cast<int*>(part_topv + U * n_parts * KTOP);
+  float* cand_v = reinterpret_cast<float*>(part_topi + U * n_parts * KTOP);
+  int* cand_i = reinterpret_cast<int*>(cand_v + U * KTOP);
+  cudaStream_t st = gngf::as_stream(stream);
+  if (cudaFuncSetAttribute(hpd_stream_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(STREAM_SMEM_BYTES)) != cudaSuccess)
+    return gngf::check_launch();
+  const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
+  hpd_stream_fwd_kernel<3><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
+                                                                     static_cast<int>(T), static_cast<int>(Kdim), KTOP,
+                                                                     n_split, part_max, part_sum, part_topv, part_topi);
+  gngf::note_launch();
+  if ((rc = gngf::check_launch())) return rc;
+  hpd_stream_merge_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 128)), 128, 0, st>>>(
+      part_max, part_sum, part_topv, part_topi, static_cast<int>(U), static_cast<int>(n_parts), KTOP, row_max, row_sum,
+      nullptr, nullptr, cand_v, cand_i);
+  gngf::note_launch();
+  if ((rc = gngf::check_launch())) return rc;
+  hpd_stream_refine_kernel<<<static_cast<unsigned>(gngf::ceil_div(U * 32, 256)), 256, 0, st>>>(
+      h, w, bias, static_cast<int>(U), static_cast<int>(T), static_cast<int>(Kdim), topk, cand_v, cand_i, row_max, row_sum,
       utopv, utopi);
   gngf::note_launch();
   return gngf::check_launch();

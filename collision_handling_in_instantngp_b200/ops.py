@@ -183,8 +183,13 @@ def tc_gemm_planes(a_planes, b_planes, out, accumulate=False, k_splits=1) -> Non
          int(k_splits), out.data_ptr(), _stream())
 
 
+STREAM_FWD_REFINED = True         # streaming forward as a two-plane pass + fp32 refinement of 8 candidates (K <= 4)
+
+
 def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
-    """Fused K2+K3: (utopv, utopi int32, row_max, row_sum) of softmax(h w^T + b) without the (U,T) logits."""
+    """Fused K2+K3: (utopv, utopi int32, row_max, row_sum) of softmax(h w^T + b) without the (U,T) logits.
+    K <= 4: half the tensor-core work -- a two-plane (1e-5) streaming pass keeps 8 candidates per row, whose logits are
+    then re-evaluated in fp32 and re-ranked (gngf_hpd_stream_fwd_refined); otherwise three planes / six products."""
     U, Kd = h.shape
     T = w.shape[0]
     hp = split_bf16x3(h) if h_planes is None else h_planes
@@ -194,6 +199,13 @@ def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
     utopi = torch.empty((U, k), dtype=torch.int32, device=dev)
     row_max = torch.empty(U, dtype=torch.float32, device=dev)
     row_sum = torch.empty(U, dtype=torch.float32, device=dev)
+    if STREAM_FWD_REFINED and k <= 4:
+        h, w = _f32c(h), _f32c(w)
+        work = torch.empty(_lib.load().gngf_hpd_stream_refined_workspace_floats(U, T), dtype=torch.float32, device=dev)
+        call("gngf_hpd_stream_fwd_refined", hp.data_ptr(), wp.data_ptr(), h.data_ptr(), w.data_ptr(), b.data_ptr(), U, T,
+             Kd, k, utopv.data_ptr(), utopi.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), work.data_ptr(),
+             _stream())
+        return utopv, utopi, row_max, row_sum
     work = torch.empty(_lib.load().gngf_hpd_stream_workspace_floats(U, T, k), dtype=torch.float32, device=dev)
     call("gngf_hpd_stream_fwd", hp.data_ptr(), wp.data_ptr(), b.data_ptr(), U, T, Kd, k, utopv.data_ptr(),
          utopi.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), work.data_ptr(), _stream())

@@ -127,6 +127,16 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
                         int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max, float* row_sum,
                         float* workspace, void* stream);
 
+/* The same result from HALF the tensor-core work (topk <= 4): a two-plane / three-product pass (1e-5) keeps the 8
+ *   best candidates per row, then the candidates' logits are re-evaluated in fp32 from h (U,Kdim) and w (T,Kdim),
+ *   re-ranked, and row_max / row_sum corrected for the exact maximum and the exact candidate terms.  Selections are
+ *   those of an fp32 evaluation as long as the true top-k lie within the approximate top-8 (a violation needs five
+ *   logits within 2e-5 of the k-th largest).  workspace: gngf_hpd_stream_refined_workspace_floats(U, T) floats.   */
+int64_t gngf_hpd_stream_refined_workspace_floats(int64_t U, int64_t T);
+int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const uint16_t* b_planes, const float* h, const float* w,
+                                const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk, float* utopv,
+                                int32_t* utopi, float* row_max, float* row_sum, float* workspace, void* stream);
+
 /* K5c fused, streaming (top-k-only mode): backward of gngf_hpd_stream_fwd's layer + softmax + top-k
  *   (models.py:80-88, 105-123; DifferentiableTopk.backward, models.py:21-42; column-sum adjoint of utils.py:138)
  *   without materialising logits, probabilities or dlogits.  Per node u
