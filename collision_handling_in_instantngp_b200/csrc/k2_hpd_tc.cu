@@ -405,26 +405,35 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       }
       for (int nt = nt0; nt < nt1; ++nt) {
         const int n0 = nt * BN + part * 32;
+        // this thread's 32 bias values are requested BEFORE the wait for the accumulator: their L1/L2 latency was the
+        // largest single stall of the epilogue (ncu source page: 14 % of all samples on the first add after the load)
+        float4 bb[8];
+        const bool full32 = n0 + 32 <= T;
+        if (full32) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0);   // n0 is a multiple of 32
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = __ldg(b4 + j);
+        }
         mbar_wait(tfull + acc, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + part * 32;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 32; c0 += 16) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int c0 = ch * 16;
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           const int nb = n0 + c0;
           if (nb >= T) continue;
           float z[16];
           float cmax = -INFINITY;
-          if (nb + 16 <= T) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + nb);   // nb is a multiple of 16
+          if (full32) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 bb = __ldg(b4 + j / 4);
-              z[j + 0] = __uint_as_float(v[j + 0]) + bb.x;
-              z[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
-              z[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
-              z[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+              const float4 b = bb[ch * 4 + j / 4];
+              z[j + 0] = __uint_as_float(v[j + 0]) + b.x;
+              z[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+              z[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+              z[j + 3] = __uint_as_float(v[j + 3]) + b.w;
             }
           } else {
 #pragma unroll
