@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
           }
           float csum = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) csum += exp2f(fmaf(z[j], LOG2E, -m2));   // one FFMA + MUFU.EX2 per element
+          for (int j = 0; j < 16; ++j) csum += fast_exp2(fmaf(z[j], LOG2E, -m2));   // one FFMA + MUFU.EX2 per element
           {  // compensated accumulation of the chunk sums (rows are up to 2^22 columns long)
             const float y = csum - comp;
             const float tsum = ssum + y;

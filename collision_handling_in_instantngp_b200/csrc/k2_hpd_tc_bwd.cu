@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                 off = make_float4(b.x * LOG2E, b.y * LOG2E, b.z * LOG2E, b.w * LOG2E);
                 sc = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
               }
-              e[j + 0] = exp2f(fmaf(__uint_as_float(v[j + 0]), LOG2E, r_off + off.x)) * (r_scale * sc.x);
-              e[j + 1] = exp2f(fmaf(__uint_as_float(v[j + 1]), LOG2E, r_off + off.y)) * (r_scale * sc.y);
-              e[j + 2] = exp2f(fmaf(__uint_as_float(v[j + 2]), LOG2E, r_off + off.z)) * (r_scale * sc.z);
-              e[j + 3] = exp2f(fmaf(__uint_as_float(v[j + 3]), LOG2E, r_off + off.w)) * (r_scale * sc.w);
+              e[j + 0] = fast_exp2(fmaf(__uint_as_float(v[j + 0]), LOG2E, r_off + off.x)) * (r_scale * sc.x);
+              e[j + 1] = fast_exp2(fmaf(__uint_as_float(v[j + 1]), LOG2E, r_off + off.y)) * (r_scale * sc.y);
+              e[j + 2] = fast_exp2(fmaf(__uint_as_float(v[j + 2]), LOG2E, r_off + off.z)) * (r_scale * sc.z);
+              e[j + 3] = fast_exp2(fmaf(__uint_as_float(v[j + 3]), LOG2E, r_off + off.w)) * (r_scale * sc.w);
             }
           } else {
 #pragma unroll
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                   sc = 1.0f;
                 }
               }
-              const float ev = exp2f(fmaf(__uint_as_float(v[j]), LOG2E, r_off + off)) * (r_scale * sc);
+              const float ev = fast_exp2(fmaf(__uint_as_float(v[j]), LOG2E, r_off + off)) * (r_scale * sc);
               e[j] = c < y_rows ? ev : 0.0f;   // (zero-filled Y rows give S = 0, not a logit: exp2 may overflow there)
             }
           }

@@ -161,6 +161,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 2^x as the bare MUFU.EX2 (denormal results flush to zero): exp2f() wraps it in a range fix-up (FSETP + 2 FMUL per
+// element) that the softmax epilogues do not need -- their arguments are <= 0 and sums of flushed terms are unaffected
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
