@@ -391,3 +391,16 @@ def test_fused_adam_matches_torch_adam():
         for a, b in zip(pa, pb):
             assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
     assert ob.step_count(pb[0]) == 12 and ob.step_count(pb[7]) == 11
+    # more tensors than one launch carries (64): several launches, same result
+    many_a = [torch.nn.Parameter(torch.full((5,), float(i), device=DEV)) for i in range(70)]
+    many_b = [torch.nn.Parameter(p.detach().clone()) for p in many_a]
+    oa2, ob2 = torch.optim.Adam(many_a, lr=1e-2, betas=(0.9, 0.99), eps=1e-15), FusedAdam(many_b, lr=1e-2, betas=(0.9, 0.99),
+                                                                                       eps=1e-15)
+    for _ in range(3):
+        for a, b in zip(many_a, many_b):
+            a.grad = torch.ones_like(a) * 0.5
+            b.grad = torch.ones_like(b) * 0.5
+        oa2.step()
+        ob2.step()
+    for a, b in zip(many_a, many_b):
+        assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
