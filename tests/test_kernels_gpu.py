@@ -150,6 +150,25 @@ def test_linear_forward_backward(M, N, K, act):
     assert rel_err(dx.cpu().numpy(), (dz.astype(np.float64) @ w) * (xin > 0)) < 1e-5
 
 
+def test_linear_layers_with_more_than_65535_row_tiles():
+    """67 M lattice nodes (the 8192^2 configuration) are > 65 535 row tiles of 64: the row tiles sit on grid.x."""
+    M, N, K = 64 * 70000 + 7, 8, 4
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn((M, K), device=DEV, generator=g)
+    w = torch.randn((N, K), device=DEV, generator=g)
+    b = torch.randn(N, device=DEV, generator=g)
+    y = ops.linear_fwd(x, w, b, 1)
+    ref = torch.relu(x.double() @ w.double().T + b.double())
+    assert float((y.double() - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    dz = torch.randn((M, N), device=DEV, generator=g)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    xin = torch.relu(x)
+    dx = ops.linear_bwd(dz, xin, w, 1, True, dw, db)
+    assert float((dw.double() - dz.double().T @ xin.double()).abs().max()) < 1e-4 * float(dw.abs().max())
+    assert float((db.double() - dz.double().sum(0)).abs().max()) < 1e-4 * float(db.abs().max())
+    assert float((dx.double() - (dz.double() @ w.double()) * (xin > 0)).abs().max()) < 1e-5 * float(dx.abs().max())
+
+
 def test_missing_gpu_tensor_is_rejected():
     from collision_handling_in_instantngp_b200 import GngfError
     with pytest.raises(GngfError):
