@@ -200,6 +200,7 @@ def algorithmic_cost(name, key, w, lat):
     """(bound, amount per launch, unit): ALGORITHMIC bytes (hbm) or FLOPs (tensor) of one launch."""
     P, L, F, K, T = w["P"], w["L"], w["F"], w["K"], w["T"]
     U, S = lat.num_nodes, lat.num_level_nodes
+    Ua = w.get("_active_nodes") or U      # rows of the HPD chain (ops.active_nodes: the nodes the batch touches)
     if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
         # EXECUTED tensor-core FLOPs (DESIGN.md section 4): inputs padded to 16, output layer padded to 16 columns;
         # forward: 6 split products; backward: 3 split products over recompute (2 layers) + dA2, dA1, dX + dW2, dW1, dW0
@@ -221,15 +222,15 @@ def algorithmic_cost(name, key, w, lat):
     # tensor-core kernels: EXECUTED FLOPs = 6 split-precision passes over the useful 2*M*N*K;
     # the useful figure is reported next to it (roofline.useful_tflops)
     if name == "gngf_hpd_stream_fwd":
-        return "tensor", 6 * 2.0 * U * T * kd
+        return "tensor", 6 * 2.0 * Ua * T * kd
     if name == "gngf_hpd_stream_fwd_refined":      # two planes, three split products (+ an fp32 refinement of 8 candidates)
-        return "tensor", 3 * 2.0 * U * T * kd
+        return "tensor", 3 * 2.0 * Ua * T * kd
     if name == "gngf_tc_gemm_bf16x3":
         return "tensor", 6 * 2.0 * float(key[0]) * key[1] * key[2]
-    if name == "gngf_hpd_stream_bwd":
+    if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
         # two fused passes (dh, dW3), each: logits recomputed (3 split products) + second product (3 split products);
         # useful work = the two gradient products, 2 * 2*U*T*kd
-        return "tensor", 12 * 2.0 * U * T * kd
+        return "tensor", 12 * 2.0 * Ua * T * kd
     table = {
         # per point: x (8) + per level 4 node-feature gathers (4*F*4) + enc row (F*4) + 4 multiplicity atomics (4*4)
         "gngf_encode_fwd": P * (8 + L * (4 * F * 4 + F * 4 + 16)),
@@ -244,8 +245,12 @@ def algorithmic_cost(name, key, w, lat):
         "gngf_hpd_dlogits": U * (2 * T * 4 + K * 12) + L * T * 4,
         "gngf_lattice_colsum": S * 4 + U * T * 4 + L * T * 4,
         "gngf_sigmoid_bwd": P * 3 * 4 * 3,
-        "gngf_hpd_first_layer_fwd": U * w["hpd"][0] * 4,
-        "gngf_hpd_first_layer_bwd": U * w["hpd"][0] * 4,
+        "gngf_hpd_first_layer_fwd_nodes": Ua * w["hpd"][0] * 4,
+        "gngf_hpd_first_layer_bwd_nodes": Ua * w["hpd"][0] * 4,
+        # P*L*4 bit sets on a U-bit map; the compaction reads the map three times and writes the ids
+        "gngf_lattice_mark_nodes": P * 8 + U / 8,
+        "gngf_compact_nodes": 2 * U / 8 + Ua * 4,
+        "gngf_scatter_node_rows": Ua * (4 + K * 8),
         "gngf_split_bf16x3": 0.0,
     }
     return "hbm", float(table.get(name, 0))
@@ -257,7 +262,7 @@ def useful_tflops(name, achieved, w):
         return achieved / 6
     if name == "gngf_hpd_stream_fwd_refined":
         return achieved / 3
-    if name == "gngf_hpd_stream_bwd":
+    if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
         return achieved / 6                       # 12 executed passes for the 2 gradient products
     if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
         dims = [w["L"] * w["F"], *w["mlp"], 3]
@@ -363,6 +368,8 @@ def run_ours(args, w):
     _lib.PROFILER = None
     agg = prof.summary()
     lat = net.last_state.lat
+    ids = net.last_state.node_ids
+    w = dict(w, _active_nodes=None if ids is None else int(ids.shape[0]))
     barrier()
 
     # ---- the public fast path: the whole step (our kernels, fused Adam, for N > 1 the two NCCL all-reduces)
@@ -467,7 +474,8 @@ def run_ours(args, w):
                        "decoder": [w["L"] * w["F"], *w["mlp"], 3], "step": "forward+loss+backward+Adam",
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"dp{world}",
                        "launch_mode": launch_mode,
-                       "lattice_nodes": lat.num_nodes, "level_nodes": lat.num_level_nodes},
+                       "lattice_nodes": lat.num_nodes, "level_nodes": lat.num_level_nodes,
+                       "active_nodes": w["_active_nodes"] or lat.num_nodes},
             "e2e": {"value": total / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
                     "path": ("trainer.GraphedTrainer.step_pipelined(x_host, y_host): pinned host batch copied into the idle "

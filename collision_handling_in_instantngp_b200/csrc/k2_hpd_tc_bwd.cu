@@ -377,8 +377,11 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 // per node u: g_k = dtv[u,k] + sum_l cnt[s(l,u)] gcol_k[l,k];  spk[u,k] = p_k g_k;  a_u = -sum_k spk / row_sum;
 // m2neg_u = -row_max log2e.  (The dense-adjoint inputs of gngf_hpd_dlogits do not exist in top-k-only mode.)
+// With node_ids the rows are the active nodes (k11_active_nodes.cu): row r <-> lattice node node_ids[r]; dtv and cnt are
+// indexed by the lattice node, everything else by the row.
 __global__ void __launch_bounds__(256)
-    hpd_stream_bwd_prep_kernel(gngf_lattice lat, int64_t U, int K, const float* __restrict__ utopv,
+    hpd_stream_bwd_prep_kernel(gngf_lattice lat, const int* __restrict__ node_ids, int64_t U, int K,
+                               const float* __restrict__ utopv,
                                const float* __restrict__ dtv, const int* __restrict__ cnt,
                                const float* __restrict__ gcol_k, const float* __restrict__ row_max,
                                const float* __restrict__ row_sum, float* __restrict__ ascale,
@@ -386,10 +389,11 @@ __global__ void __launch_bounds__(256)
   const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (u >= U) return;
   const int L = lat.num_levels;
-  const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
+  const int64_t un = node_ids ? node_ids[u] : u;
+  const int cx = lat.ox + static_cast<int>(un / lat.wy), cy = lat.oy + static_cast<int>(un % lat.wy);
   float dot = 0.0f;
   for (int k = 0; k < K; ++k) {
-    float g = dtv[u * K + k];
+    float g = dtv[un * K + k];
     if (gcol_k) {
       for (int l = 0; l < L; ++l) {
         const int i = cx - lat.lox[l], j = cy - lat.loy[l];
@@ -468,15 +472,17 @@ extern "C" {
 
 int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk) { return U * (2 + static_cast<int64_t>(topk)) + 4; }
 
-int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16_t* w_planes, const float* h,
-                        const float* w, const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk,
-                        const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
-                        const float* gcol_k, const float* row_max, const float* row_sum, int32_t act_prev, float* dh,
-                        float* dw, float* db, float* workspace, void* stream) {
+int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes,
+                              const uint16_t* w_planes, const float* h, const float* w, const float* bias, int64_t U,
+                              int64_t T, int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi,
+                              const float* dtv, const int32_t* cnt, const float* gcol_k, const float* row_max,
+                              const float* row_sum, int32_t act_prev, float* dh, float* dw, float* db, float* workspace,
+                              void* stream) {
   using namespace gngf::tc;
   using namespace gngf::tc::sb;
+  const int64_t box = static_cast<int64_t>(lat.wx) * lat.wy;
   if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > 2 * BK || topk <= 0 || topk > GNGF_MAX_TOPK ||
-      U >= (1ll << 31) || T >= (1ll << 31) || U != static_cast<int64_t>(lat.wx) * lat.wy)
+      U >= (1ll << 31) || T >= (1ll << 31) || (node_ids ? U > box : U != box))
     return GNGF_ERR_UNSUPPORTED;
   if (gcol_k && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
   if (!h_planes || !w_planes || !h || !w || !bias || !utopv || !utopi || !dtv || !row_max || !row_sum || !dh || !dw ||
@@ -492,7 +498,7 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16
   float* m2neg = workspace + U4;
   float* spk = workspace + 2 * U4;
   hpd_stream_bwd_prep_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 256)), 256, 0, st>>>(
-      lat, U, topk, utopv, dtv, cnt, gcol_k, row_max, row_sum, ascale, m2neg, spk);
+      lat, node_ids, U, topk, utopv, dtv, cnt, gcol_k, row_max, row_sum, ascale, m2neg, spk);
   gngf::note_launch();
   int rc = gngf::check_launch();
   if (rc) return rc;
@@ -530,6 +536,15 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16
       U, topk, static_cast<int>(Kdim), utopi, spk, h, w, act_prev, dh, dw, db);
   gngf::note_launch();
   return gngf::check_launch();
+}
+
+int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16_t* w_planes, const float* h,
+                        const float* w, const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk,
+                        const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                        const float* gcol_k, const float* row_max, const float* row_sum, int32_t act_prev, float* dh,
+                        float* dw, float* db, float* workspace, void* stream) {
+  return gngf_hpd_stream_bwd_nodes(lat, nullptr, h_planes, w_planes, h, w, bias, U, T, Kdim, topk, utopv, utopi, dtv, cnt,
+                                   gcol_k, row_max, row_sum, act_prev, dh, dw, db, workspace, stream);
 }
 
 }  // extern "C"

@@ -154,34 +154,37 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   }
 }
 
-// h[u, j] = act(cx * w0[j,0] + cy * w0[j,1] + b0[j]);  node u <-> (cx, cy) = (ox + u / wy, oy + u % wy)
+// h[r, j] = act(cx * w0[j,0] + cy * w0[j,1] + b0[j]);  row r <-> node u = node_ids ? node_ids[r] : r,
+// (cx, cy) = (ox + u / wy, oy + u % wy)
 __global__ void __launch_bounds__(256) first_layer_fwd_kernel(const __grid_constant__ gngf_lattice lat,
+                                                              const int* __restrict__ node_ids, int64_t rows,
                                                               const float2* __restrict__ w0,
                                                               const float* __restrict__ b0, int n_out, int act,
                                                               float* __restrict__ h) {
-  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= U * n_out) return;
-  const int64_t u = i / n_out;
-  const int j = static_cast<int>(i - u * n_out);
+  if (i >= rows * n_out) return;
+  const int64_t r = i / n_out;
+  const int j = static_cast<int>(i - r * n_out);
+  const int64_t u = node_ids ? node_ids[r] : r;
   const float cx = static_cast<float>(lat.ox + static_cast<int>(u / lat.wy));
   const float cy = static_cast<float>(lat.oy + static_cast<int>(u % lat.wy));
   const float2 w = w0[j];
   h[i] = apply_act(fmaf(cy, w.y, fmaf(cx, w.x, b0[j])), act);
 }
 
-// dw0[j, :] += sum_u dz[u, j] * (cx, cy);  db0[j] += sum_u dz[u, j]
+// dw0[j, :] += sum_r dz[r, j] * (cx, cy);  db0[j] += sum_r dz[r, j]
 __global__ void __launch_bounds__(256) first_layer_bwd_kernel(const __grid_constant__ gngf_lattice lat,
+                                                              const int* __restrict__ node_ids, int64_t rows,
                                                               const float* __restrict__ dz, int n_out,
                                                               int64_t rows_per_block, float* __restrict__ dw0,
                                                               float* __restrict__ db0) {
-  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
-  const int64_t r1 = min(U, r0 + rows_per_block);
+  const int64_t r1 = min(rows, r0 + rows_per_block);
   for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
     float sx = 0.0f, sy = 0.0f, sb = 0.0f;
-    for (int64_t u = r0; u < r1; ++u) {
-      const float g = dz[u * n_out + j];
+    for (int64_t r = r0; r < r1; ++r) {
+      const float g = dz[r * n_out + j];
+      const int64_t u = node_ids ? node_ids[r] : r;
       sx = fmaf(g, static_cast<float>(lat.ox + static_cast<int>(u / lat.wy)), sx);
       sy = fmaf(g, static_cast<float>(lat.oy + static_cast<int>(u % lat.wy)), sy);
       sb += g;
@@ -205,26 +208,40 @@ __global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restric
 
 extern "C" {
 
+int gngf_hpd_first_layer_fwd_nodes(gngf_lattice lat, const int32_t* node_ids, int64_t n_nodes, const float* w0,
+                                   const float* b0, int32_t n_out, int32_t act, float* h, void* stream) {
+  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
+  const int64_t rows = node_ids ? n_nodes : U;
+  if (U <= 0 || n_out <= 0 || rows < 0 || rows > U) return GNGF_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return GNGF_OK;
+  gngf::first_layer_fwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(rows * n_out, 256)), 256, 0,
+                                 gngf::as_stream(stream)>>>(lat, node_ids, rows, reinterpret_cast<const float2*>(w0), b0,
+                                                            n_out, act, h);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
 int gngf_hpd_first_layer_fwd(gngf_lattice lat, const float* w0, const float* b0, int32_t n_out, int32_t act, float* h,
                              void* stream) {
+  return gngf_hpd_first_layer_fwd_nodes(lat, nullptr, 0, w0, b0, n_out, act, h, stream);
+}
+
+int gngf_hpd_first_layer_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, int64_t n_nodes, const float* dz,
+                                   int32_t n_out, float* dw0, float* db0, void* stream) {
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
-  if (U <= 0 || n_out <= 0) return GNGF_ERR_INVALID_ARGUMENT;
-  gngf::first_layer_fwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U * n_out, 256)), 256, 0,
-                                 gngf::as_stream(stream)>>>(lat, reinterpret_cast<const float2*>(w0), b0, n_out, act,
-                                                            h);
+  const int64_t rows = node_ids ? n_nodes : U;
+  if (U <= 0 || n_out <= 0 || rows < 0 || rows > U) return GNGF_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return GNGF_OK;
+  // enough blocks to cover the chip even for a few hundred nodes
+  const int64_t rows_per_block = std::max<int64_t>(4, gngf::ceil_div(rows, 4 * gngf::sm_count()));
+  gngf::first_layer_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(rows, rows_per_block)), 128, 0,
+                                 gngf::as_stream(stream)>>>(lat, node_ids, rows, dz, n_out, rows_per_block, dw0, db0);
   gngf::note_launch();
   return gngf::check_launch();
 }
 
 int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, float* dw0, float* db0, void* stream) {
-  const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
-  if (U <= 0 || n_out <= 0) return GNGF_ERR_INVALID_ARGUMENT;
-  // enough blocks to cover the chip even for a few hundred nodes
-  const int64_t rows_per_block = std::max<int64_t>(4, gngf::ceil_div(U, 4 * gngf::sm_count()));
-  gngf::first_layer_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, rows_per_block)), 128, 0,
-                                 gngf::as_stream(stream)>>>(lat, dz, n_out, rows_per_block, dw0, db0);
-  gngf::note_launch();
-  return gngf::check_launch();
+  return gngf_hpd_first_layer_bwd_nodes(lat, nullptr, 0, dz, n_out, dw0, db0, stream);
 }
 
 int gngf_linear_fwd(const float* x, const float* w, const float* b, int64_t M, int32_t N, int32_t K, int32_t act,

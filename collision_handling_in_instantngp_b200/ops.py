@@ -25,7 +25,7 @@ from ._lib import (ACT_LEAKY_RELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, MIX_RAW, MIX
 MAX_DENSE_LOGIT_BYTES = 96 << 30   # (U, T) fp32 logits are materialised by this path
 
 # data parallelism (dp.enable_gradient_allreduce):
-#   GRAD_REDUCE_HOOK(flat)      in-place mean over ranks of the flat gradient buffer, at the end of GNGFPath.backward
+#   GRAD_REDUCE_HOOK(flat_params)      in-place mean over ranks of the flat gradient buffer, at the end of GNGFPath.backward
 #   COLSUM_REDUCE_HOOK(colsum)  in-place sum over ranks of the (L, N) column sums, right behind the kernel that produces
 #                               them -- on the side stream, so the exchange overlaps the decoder forward; returns the
 #                               world size (the adjoint of the local column sums is world * the adjoint of the sum,
@@ -213,17 +213,23 @@ def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
 
 
 def hpd_stream_bwd(lat: Lattice, h, w, b, h_planes, w_planes, utopv, utopi, dtv, cnt, gcol_k, row_max, row_sum,
-                   dw, db, act_prev=ACT_RELU) -> torch.Tensor:
+                   dw, db, act_prev=ACT_RELU, node_ids=None) -> torch.Tensor:
     """Fused K5c (k2_hpd_tc_bwd.cu): returns dh (U,Kd) = (dlogits w) .* act'(h); accumulates dlogits^T h into dw and
     colsum(dlogits) into db, with dlogits = -<g,p_top> p + scatter(p_k g_k) never materialised."""
     U, kd = h.shape
     T, K = w.shape[0], utopv.shape[1]
     dh = torch.zeros((U, kd), dtype=torch.float32, device=h.device)
     work = torch.empty(_lib.load().gngf_hpd_stream_bwd_workspace_floats(U, K), dtype=torch.float32, device=h.device)
-    call("gngf_hpd_stream_bwd", lat, h_planes.data_ptr(), w_planes.data_ptr(), h.data_ptr(), w.data_ptr(),
-         b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(), _ptr(cnt), _ptr(gcol_k),
-         row_max.data_ptr(), row_sum.data_ptr(), act_prev, dh.data_ptr(), dw.data_ptr(), db.data_ptr(),
-         work.data_ptr(), _stream())
+    if node_ids is None:
+        call("gngf_hpd_stream_bwd", lat, h_planes.data_ptr(), w_planes.data_ptr(), h.data_ptr(), w.data_ptr(),
+             b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(), _ptr(cnt), _ptr(gcol_k),
+             row_max.data_ptr(), row_sum.data_ptr(), act_prev, dh.data_ptr(), dw.data_ptr(), db.data_ptr(),
+             work.data_ptr(), _stream())
+    else:   # rows = active nodes; dtv and cnt stay indexed by the lattice node
+        call("gngf_hpd_stream_bwd_nodes", lat, node_ids.data_ptr(), h_planes.data_ptr(), w_planes.data_ptr(),
+             h.data_ptr(), w.data_ptr(), b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(),
+             _ptr(cnt), _ptr(gcol_k), row_max.data_ptr(), row_sum.data_ptr(), act_prev, dh.data_ptr(), dw.data_ptr(),
+             db.data_ptr(), work.data_ptr(), _stream())
     return dh
 
 
@@ -294,6 +300,33 @@ def gather_rows(x, lat: Lattice, uvals: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
+def active_nodes(x: torch.Tensor, lat: Lattice) -> torch.Tensor:
+    """Ascending int32 ids of the lattice nodes that the corners of x touch (k11_active_nodes.cu).  One
+    device->host read of the count (the list sizes every launch of the HPD chain)."""
+    _require_cuda(x, "x")
+    x = _f32c(x)
+    lib = _lib.load()
+    U, P = lat.num_nodes, x.shape[0]
+    dev = x.device
+    words = int(lib.gngf_active_nodes_bitmap_words(U))
+    bitmap = torch.zeros((words + 3) & ~3, dtype=torch.int32, device=dev)
+    call("gngf_lattice_mark_nodes", x.data_ptr(), P, lat, bitmap.data_ptr(), _stream())
+    chunk_offsets = torch.empty(int(lib.gngf_active_nodes_chunks(U)), dtype=torch.int32, device=dev)
+    capacity = max(1, min(U, P * lat.num_levels * 4))
+    ids = torch.empty(capacity, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    call("gngf_compact_nodes", bitmap.data_ptr(), U, chunk_offsets.data_ptr(), ids.data_ptr(), capacity,
+         count.data_ptr(), _stream())
+    return ids[:int(count.item())]
+
+
+def scatter_node_rows(node_ids: torch.Tensor, src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[node_ids[r], :] = src[r, :] for 32-bit element types."""
+    assert src.element_size() == 4 and dst.dtype == src.dtype and src.is_contiguous() and dst.is_contiguous()
+    call("gngf_scatter_node_rows", node_ids.data_ptr(), node_ids.shape[0], src.data_ptr(), src.shape[1], dst.data_ptr(),
+         _stream())
+
+
 # ----------------------------------------------------------------------------------------------------------
 # the fused forward / backward
 # ----------------------------------------------------------------------------------------------------------
@@ -327,6 +360,9 @@ class ForwardState:
     hpd_small: bool = False                                      # fused small-lattice HPD kernels were used
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
+    node_ids: Optional[torch.Tensor] = None                      # (Ua,) int32 active nodes: the HPD chain (hpd_acts,
+    utopv_rows: Optional[torch.Tensor] = None                    #   h_planes, row_max / row_sum, utopv_rows / utopi_rows)
+    utopi_rows: Optional[torch.Tensor] = None                    #   has one row per ACTIVE node; utopv / utopi stay (U,K)
     cnt: Optional[torch.Tensor] = None                           # (S,) int32
     mlp_acts: List[torch.Tensor] = field(default_factory=list)   # enc, a1, ..., rgb  (enc, rgb when fused)
     mlp_fused: bool = False
@@ -352,6 +388,22 @@ TC_MIN_ELEMENTS = 1 << 22         # dense logits come from the tensor-core GEMM 
 BWD_CHUNK_BYTES = 4 << 30         # logits recomputed per chunk of rows in the (un-fused) streaming backward
 STREAM_BWD_FUSED = True           # streaming backward as the fused tcgen05 kernels of k2_hpd_tc_bwd.cu (False: the
                                   # chunked recompute through the plain GEMM, kept as a cross-check for the tests)
+
+
+# active nodes (k11_active_nodes.cu): on large lattices the streaming HPD path is evaluated only on the nodes the batch
+# touches (BASELINE.json configs[3]: 2^22 points touch ~40 % of the 67 M nodes of the 8192^2 box; a data-parallel rank
+# with 1/8 of the batch ~12 %).  Costs one device->host read of the node count per forward.
+ACTIVE_NODES_MIN = 1 << 20        # lattices with fewer nodes are evaluated densely
+ACTIVE_NODES_MAX_FRACTION = 0.75  # ... and so are batches that touch more than this share of the box
+FORCE_ACTIVE_NODES = None         # None: by size; True / False: override (tests)
+
+
+def _active_nodes_wanted(U: int) -> bool:
+    if not STREAM_BWD_FUSED:
+        return False
+    if FORCE_ACTIVE_NODES is not None:
+        return bool(FORCE_ACTIVE_NODES)
+    return U >= ACTIVE_NODES_MIN
 
 
 def _streaming_ok(cfg, U, T, k, kd) -> bool:
@@ -396,9 +448,16 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
              state.utopi.data_ptr(), _stream())
         return
     acts = []
-    h = torch.empty((U, hpd_w[0].shape[0]), dtype=torch.float32, device=device)
-    call("gngf_hpd_first_layer_fwd", lat, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(), hpd_w[0].shape[0],
-         ACT_RELU if n > 1 else ACT_NONE, h.data_ptr(), _stream())
+    ids = None
+    if n > 1 and _streaming_ok(cfg, U, T, k, hpd_w[-1].shape[1]) and _active_nodes_wanted(U):
+        ids = active_nodes(state.x, lat)
+        if ids.shape[0] == 0 or (FORCE_ACTIVE_NODES is None and ids.shape[0] > ACTIVE_NODES_MAX_FRACTION * U):
+            ids = None
+    state.node_ids = ids
+    rows = U if ids is None else ids.shape[0]
+    h = torch.empty((rows, hpd_w[0].shape[0]), dtype=torch.float32, device=device)
+    call("gngf_hpd_first_layer_fwd_nodes", lat, _ptr(ids), rows, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(),
+         hpd_w[0].shape[0], ACT_RELU if n > 1 else ACT_NONE, h.data_ptr(), _stream())
     for i in range(1, n - 1):
         acts.append(h)
         h = linear_fwd(h, hpd_w[i], hpd_b[i], ACT_RELU)
@@ -414,6 +473,14 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
         state.utopv, state.utopi, state.row_max, state.row_sum = hpd_stream_fwd(
             h, hpd_w[-1], hpd_b[-1], k, h_planes=state.h_planes, w_planes=state.w_planes)
         state.uprobs = None
+        if ids is not None:
+            # per-node results back into (U,K) arrays for the gather / scatter kernels.  Untouched nodes: slot 0 with
+            # probability 1 -- finite under every mix mode; their multiplicities and feature adjoints are zero
+            state.utopv_rows, state.utopi_rows = state.utopv, state.utopi
+            state.utopv = torch.ones((U, k), dtype=torch.float32, device=device)
+            state.utopi = torch.zeros((U, k), dtype=torch.int32, device=device)
+            scatter_node_rows(ids, state.utopv_rows, state.utopv)
+            scatter_node_rows(ids, state.utopi_rows, state.utopi)
         return
     if U * T * 4 > MAX_DENSE_LOGIT_BYTES:
         raise GngfError(f"dense logits for U={U} nodes x T={T} slots need {U * T * 4 / 2**30:.0f} GiB; the streaming "
@@ -548,6 +615,8 @@ class GNGFPath(torch.autograd.Function):
             off += npad
         grads = [v.view(p.shape) for v, p in zip(views[:len(params)], params)]
         dnf, dtv = views[-2], views[-1]
+        # what the data-parallel exchange moves: the parameter gradients, not the per-node scratch behind them
+        flat_params = flat[:sum(padded[:len(params)])]
         g_hpd_w, g_hpd_b = grads[0:2 * nh:2], grads[1:2 * nh:2]
         g_tables = grads[2 * nh:2 * nh + L]
         g_mlp_w, g_mlp_b = grads[2 * nh + L::2], grads[2 * nh + L + 1::2]
@@ -585,7 +654,7 @@ class GNGFPath(torch.autograd.Function):
         if cfg.use_hash:
             call("gngf_encode_hash_bwd", x.data_ptr(), P, lat, gtab, T, F, denc.data_ptr(), st)
             if GRAD_REDUCE_HOOK is not None:
-                GRAD_REDUCE_HOOK(flat)
+                GRAD_REDUCE_HOOK(flat_params)
             return (None, None, *grads)
 
         call("gngf_encode_bwd", x.data_ptr(), P, lat, F, denc.data_ptr(), dnf.data_ptr(), st)
@@ -596,7 +665,7 @@ class GNGFPath(torch.autograd.Function):
             for i in range(2 * nh):
                 grads[i] = None
             if GRAD_REDUCE_HOOK is not None:
-                GRAD_REDUCE_HOOK(flat)
+                GRAD_REDUCE_HOOK(flat_params)
             return (None, None, *grads)
 
         gcol = gcol_k = gdense = None
@@ -633,7 +702,7 @@ class GNGFPath(torch.autograd.Function):
             for f in forks:
                 f.join()
             if GRAD_REDUCE_HOOK is not None:
-                GRAD_REDUCE_HOOK(flat)
+                GRAD_REDUCE_HOOK(flat_params)
             return (None, None, *grads)
         if nh == 1:
             dlogits = torch.empty((U, T), dtype=torch.float32, device=dev)
@@ -651,9 +720,11 @@ class GNGFPath(torch.autograd.Function):
             # warps and contracted again (dlogits W3, dlogits^T h) without leaving the SM (k2_hpd_tc_bwd.cu)
             h_last = state.hpd_acts[nh - 2]
             kd = h_last.shape[1]
+            ids = state.node_ids
             dz = hpd_stream_bwd(lat, h_last, hpd_w[nh - 1], params[2 * (nh - 1) + 1], state.h_planes, state.w_planes,
-                                state.utopv, state.utopi, dtv, state.cnt, gcol_k, state.row_max, state.row_sum,
-                                g_hpd_w[nh - 1], g_hpd_b[nh - 1])
+                                state.utopv if ids is None else state.utopv_rows,
+                                state.utopi if ids is None else state.utopi_rows, dtv, state.cnt, gcol_k,
+                                state.row_max, state.row_sum, g_hpd_w[nh - 1], g_hpd_b[nh - 1], node_ids=ids)
         else:
             # streaming path: recompute the logits chunk by chunk on the tensor cores, turn them into dlogits in
             # place from the saved softmax statistics, and feed the output layer's backward
@@ -685,10 +756,10 @@ class GNGFPath(torch.autograd.Function):
                 del buf, dlt_planes, ht_planes
         for i in range(nh - 2, 0, -1):
             dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
-        call("gngf_hpd_first_layer_bwd", lat, dz.data_ptr(), hpd_w[0].shape[0], g_hpd_w[0].data_ptr(),
-             g_hpd_b[0].data_ptr(), st)
+        call("gngf_hpd_first_layer_bwd_nodes", lat, _ptr(state.node_ids), dz.shape[0], dz.data_ptr(), hpd_w[0].shape[0],
+             g_hpd_w[0].data_ptr(), g_hpd_b[0].data_ptr(), st)
         if GRAD_REDUCE_HOOK is not None:
-            GRAD_REDUCE_HOOK(flat)      # every parameter gradient is a view of `flat`: one collective for all
+            GRAD_REDUCE_HOOK(flat_params)      # every parameter gradient is a view of it: one collective for all
         return (None, None, *grads)
 
 

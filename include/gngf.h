@@ -101,6 +101,28 @@ int gngf_linear_bwd(const float* dz, const float* x, const float* w, int64_t M, 
 int gngf_sigmoid_bwd(const float* dy, const float* y, int64_t n, float* dz, void* stream);
 /* backward of the first HPD layer: dw0 (N,2) += dz^T c(u), db0 (N) += colsum(dz)                        */
 int gngf_hpd_first_layer_bwd(gngf_lattice lat, const float* dz, int32_t n_out, float* dw0, float* db0, void* stream);
+/* the same two on a list of lattice nodes (gngf_compact_nodes): row r of h / dz <-> node node_ids[r];
+ * node_ids == NULL: all U nodes of the box (n_nodes ignored)                                            */
+int gngf_hpd_first_layer_fwd_nodes(gngf_lattice lat, const int32_t* node_ids, int64_t n_nodes, const float* w0,
+                                   const float* b0, int32_t n_out, int32_t act, float* h, void* stream);
+int gngf_hpd_first_layer_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, int64_t n_nodes, const float* dz,
+                                   int32_t n_out, float* dw0, float* db0, void* stream);
+
+/* ---- active nodes: the lattice nodes a batch touches ------------------------------------------------
+ * models.py:416-418 evaluates the HPD on one row per (point, level, corner); only the distinct corner
+ * coordinates matter, and on large lattices (BASELINE.json configs[3]: 8192^2) a batch touches a fraction
+ * of the bounding box.  gngf_lattice_mark_nodes sets bit u of `bitmap` (gngf_active_nodes_bitmap_words(U)
+ * ZERO-INITIALISED 32-bit words, 16-byte aligned) for every corner node u of every (point, level);
+ * gngf_compact_nodes writes the set bits as an ascending list node_ids (at most `capacity` entries are
+ * written) and their number to count[0]; chunk_offsets: gngf_active_nodes_chunks(U) int32 of scratch.
+ * gngf_scatter_node_rows: dst[node_ids[r], :] = src[r, :] for rows of `row_words` 32-bit elements.       */
+int64_t gngf_active_nodes_bitmap_words(int64_t U);
+int64_t gngf_active_nodes_chunks(int64_t U);
+int gngf_lattice_mark_nodes(const float* x, int64_t P, gngf_lattice lat, uint32_t* bitmap, void* stream);
+int gngf_compact_nodes(const uint32_t* bitmap, int64_t U, int32_t* chunk_offsets, int32_t* node_ids, int64_t capacity,
+                       int32_t* count, void* stream);
+int gngf_scatter_node_rows(const int32_t* node_ids, int64_t n_nodes, const void* src, int64_t row_words, void* dst,
+                           void* stream);
 
 /* ---- K2 (tensor cores): split-precision GEMM on tcgen05 ------------------------------------------------------
  * gngf_split_bf16x3: x = hi + mid + lo in bf16; planes (3, n) row-major after src's own layout.
@@ -153,6 +175,14 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16
                         const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
                         const float* gcol_k, const float* row_max, const float* row_sum, int32_t act_prev, float* dh,
                         float* dw, float* db, float* workspace, void* stream);
+/* the same on the active nodes: rows of h_planes / h / utopv / utopi / row_max / row_sum / dh are the nodes
+ * node_ids[0..U), while dtv (box, topk) and cnt stay indexed by the lattice node; node_ids == NULL: U = box     */
+int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes,
+                              const uint16_t* w_planes, const float* h, const float* w, const float* bias, int64_t U,
+                              int64_t T, int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi,
+                              const float* dtv, const int32_t* cnt, const float* gcol_k, const float* row_max,
+                              const float* row_sum, int32_t act_prev, float* dh, float* dw, float* db, float* workspace,
+                              void* stream);
 
 /* ---- K2/K3/K5 fused for small lattices (a few hundred to a few thousand nodes, T <= 1024, hidden widths <= 256) ----
  * One CTA per 8 nodes walks the whole HPD (models.py:80-123): layer 0 from the node coordinates, hidden layers,

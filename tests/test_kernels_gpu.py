@@ -48,6 +48,56 @@ def test_corners_match_reference_goldens(name):
     assert np.array_equal(grid.cpu().numpy(), g["grid"])
 
 
+@pytest.mark.parametrize("levels,P", [((8, 32, 4), 57), ((16, 508, 16), 4096), ((16, 8192, 16), 4096), ((2, 1024, 10), 1)])
+def test_active_nodes_are_the_distinct_corner_nodes(levels, P):
+    """mark + compact (k11_active_nodes.cu): ascending ids of exactly the lattice nodes the oracle's corners touch."""
+    n_ls = level_resolutions(*levels)
+    x = _edge_coords()[:P]
+    lat = build_lattice(n_ls)
+    ids = ops.active_nodes(torch.from_numpy(x).to(DEV), lat)
+    _, g_ref = O.scale_to_grid(x, n_ls)                              # (P,2,L,4) integer-valued fp32
+    u = (g_ref[:, 0].astype(np.int64) - lat.ox) * lat.wy + (g_ref[:, 1].astype(np.int64) - lat.oy)
+    assert ids.dtype == torch.int32
+    assert np.array_equal(ids.cpu().numpy().astype(np.int64), np.unique(u))
+
+
+def test_scatter_node_rows_and_first_layer_on_node_lists():
+    lat = build_lattice(level_resolutions(16, 508, 16))
+    U = lat.num_nodes
+    g = torch.Generator(device=DEV).manual_seed(3)
+    ids = torch.sort(torch.randperm(U, device=DEV, generator=g)[:1000])[0].int()
+    src = torch.randn((1000, 4), device=DEV, generator=g)
+    dst = torch.ones((U, 4), device=DEV)
+    ops.scatter_node_rows(ids, src, dst)
+    ref = torch.ones((U, 4), device=DEV)
+    ref[ids.long()] = src
+    assert torch.equal(dst, ref)
+    isrc = torch.randint(0, 1 << 19, (1000, 4), device=DEV, generator=g, dtype=torch.int32)
+    idst = torch.zeros((U, 4), device=DEV, dtype=torch.int32)
+    ops.scatter_node_rows(ids, isrc, idst)
+    assert torch.equal(idst[ids.long()], isrc) and int((idst != 0).sum()) == int((isrc != 0).sum())
+    # first HPD layer on the list == the rows of the full evaluation; its backward == the full one on scattered adjoints
+    w0 = torch.randn((32, 2), device=DEV, generator=g)
+    b0 = torch.randn(32, device=DEV, generator=g)
+    h_all = torch.empty((U, 32), device=DEV)
+    h_ids = torch.empty((1000, 32), device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    ops.call("gngf_hpd_first_layer_fwd", lat, w0.data_ptr(), b0.data_ptr(), 32, 1, h_all.data_ptr(), st)
+    ops.call("gngf_hpd_first_layer_fwd_nodes", lat, ids.data_ptr(), 1000, w0.data_ptr(), b0.data_ptr(), 32, 1,
+             h_ids.data_ptr(), st)
+    assert torch.equal(h_ids, h_all[ids.long()])
+    dz = torch.randn((1000, 32), device=DEV, generator=g)
+    dz_all = torch.zeros((U, 32), device=DEV)
+    dz_all[ids.long()] = dz
+    dw_a, db_a, dw_b, db_b = (torch.zeros((32, 2), device=DEV), torch.zeros(32, device=DEV),
+                              torch.zeros((32, 2), device=DEV), torch.zeros(32, device=DEV))
+    ops.call("gngf_hpd_first_layer_bwd", lat, dz_all.data_ptr(), 32, dw_a.data_ptr(), db_a.data_ptr(), st)
+    ops.call("gngf_hpd_first_layer_bwd_nodes", lat, ids.data_ptr(), 1000, dz.data_ptr(), 32, dw_b.data_ptr(),
+             db_b.data_ptr(), st)
+    assert rel_err(dw_b.cpu().numpy(), dw_a.cpu().numpy()) < 1e-5
+    assert rel_err(db_b.cpu().numpy(), db_a.cpu().numpy()) < 1e-5
+
+
 def test_corners_empty_batch():
     scaled, grid = ops.corners_fwd(torch.empty((0, 2), device=DEV), build_lattice([8, 16]))
     assert scaled.shape == (0, 2, 2, 1) and grid.shape == (0, 2, 2, 4)

@@ -171,6 +171,58 @@ def test_streaming_tensor_core_path_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", ["cfg2_topk_only", "l8_t4096_topk_only"])
+def test_active_node_evaluation_matches_reference_golden(name):
+    """The streaming HPD evaluated only on the lattice nodes the batch touches (k11_active_nodes.cu; what the 8192^2
+    lattice of BASELINE.json configs[3] runs) against the reference's golden step and against the evaluation of the
+    whole box."""
+    from collision_handling_in_instantngp_b200 import ops
+    g = load(name)
+    net = build_net(g)
+    ops.FORCE_STREAMING = True
+    try:
+        out_box = run_step(net, g)
+        ops.FORCE_ACTIVE_NODES = True
+        out = run_step(net, g)
+    finally:
+        ops.FORCE_STREAMING = None
+        ops.FORCE_ACTIVE_NODES = None
+    st = out["state"]
+    assert out_box["state"].node_ids is None
+    assert st.node_ids is not None and 0 < st.node_ids.shape[0] < st.lat.num_nodes
+    assert st.hpd_acts[0].shape[0] == st.node_ids.shape[0] and st.utopv.shape[0] == st.lat.num_nodes
+    assert np.array_equal(out["idx"], g["idx"])
+    assert rel_err(out["rgb"], g["rgb"]) < FWD_TOL
+    assert rel_err(out["pbar"], g["pbar"]) < FWD_TOL
+    assert abs(out["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    _check_grads(out, g)
+    assert np.array_equal(out["idx"], out_box["idx"])
+    assert rel_err(out["rgb"], out_box["rgb"]) < 2e-6             # (the split of T over CTAs follows the row count)
+    for k in out["grads"]:
+        assert rel_err(out["grads"][k], out_box["grads"][k]) < GRAD_TOL, k   # (two-plane products: ~1e-5 each)
+
+
+@pytest.mark.parametrize("mix", [False, None])
+def test_active_node_evaluation_with_every_mix_mode(mix):
+    """Untouched nodes carry placeholder selections; no mix mode may turn them into NaN gradients."""
+    from collision_handling_in_instantngp_b200 import ops
+    g = load("cfg2_topk_only")
+    net = build_net(g, mix_mode=mix)
+    ops.FORCE_STREAMING = True
+    try:
+        out_box = run_step(net, g)
+        ops.FORCE_ACTIVE_NODES = True
+        out = run_step(net, g)
+    finally:
+        ops.FORCE_STREAMING = None
+        ops.FORCE_ACTIVE_NODES = None
+    assert out["state"].node_ids is not None
+    assert np.array_equal(out["idx"], out_box["idx"]) and rel_err(out["rgb"], out_box["rgb"]) < 2e-6
+    for k in out["grads"]:
+        assert np.isfinite(out["grads"][k]).all(), k
+        assert rel_err(out["grads"][k], out_box["grads"][k]) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("name", ["cfg2_topk_only", "l8_t4096_topk_only"])
 def test_fused_streaming_backward_equals_chunked_recompute(name):
     """k2_hpd_tc_bwd.cu (dlogits never materialised) against the chunked recompute through the plain GEMM."""
     from collision_handling_in_instantngp_b200 import ops
