@@ -99,6 +99,11 @@ SIGNATURES = {
                                    POINTER(c_void_p), c_int32, _P, _P, _P, _P]),
     "gngf_hpd_small_bwd": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_void_p), POINTER(c_void_p), _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gngf_hpd_small_fwd_enc": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
+                                       POINTER(c_void_p), c_int32, _P, _P, _P, Tables, c_int32, c_int32, _P, _P]),
+    "gngf_hpd_small_bwd_enc": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
+                                       POINTER(c_void_p), POINTER(c_void_p), _P, c_int32, _P, _P, _P, _P, _P, _P, _P,
+                                       Tables, Tables, c_int32, c_int32, _P, _P]),
     "gngf_mlp3_supported": (c_int, [c_int32, c_int32, c_int32, c_int32]),
     "gngf_mlp3_fwd": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_mlp3_bwd_workspace_floats": (c_int64, [c_int32, c_int32]),

@@ -96,4 +96,28 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// top-k mix weights (models.py:212-217): the normaliser of a node's K probabilities, and one weight
+__device__ __forceinline__ float mix_weight_norm(const float* tv, int K, int mode, float& mx) {
+  // returns the normaliser; mx = max (softmax mode)
+  mx = 0.0f;
+  if (mode == GNGF_MIX_SOFTMAX) {
+    mx = tv[0];
+    for (int k = 1; k < K; ++k) mx = fmaxf(mx, tv[k]);
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s += expf(tv[k] - mx);
+    return s;
+  }
+  if (mode == GNGF_MIX_WEIGHTED_AVG) {
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s += tv[k];
+    return s;
+  }
+  return 1.0f;
+}
+__device__ __forceinline__ float mix_weight(float tv, int mode, float mx, float norm) {
+  if (mode == GNGF_MIX_SOFTMAX) return expf(tv - mx) / norm;
+  if (mode == GNGF_MIX_WEIGHTED_AVG) return tv / norm;
+  return tv;
+}
+
 }  // namespace gngf

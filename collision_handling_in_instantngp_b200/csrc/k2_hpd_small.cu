@@ -30,6 +30,17 @@ struct HpdNet {
   float* dw0;                   // backward: first layer weight gradient (+=)
 };
 
+// The per-level-node passes of the encoding (k4_encode.cu node_features_fwd, k5_encode_bwd.cu node_features_bwd) folded
+// into the HPD kernels: a level node belongs to exactly one lattice node, and the warp that owns the node already holds
+// its selection.  Two launches leave the critical path of the step.
+struct SmallEnc {
+  gngf_tables tables;           // forward + backward: level tables (T, F)
+  gngf_tables tgrads;           // backward: their gradients (+=)
+  int F, mode;
+  float* nfeat;                 // forward: (S, F) mixed features per level node; NULL = not fused
+  const float* dnf;             // backward: (S, F) adjoint of nfeat; NULL = not fused
+};
+
 // 8 partial sums (one per node) x 32 lanes -> each 4-lane group ends with one node's total
 __device__ __forceinline__ float reduce_scatter8(const float (&acc)[NB], int lane, int& node_of_lane) {
   const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
@@ -75,6 +86,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -222,9 +234,9 @@ __device__ __forceinline__ void small_layer_resident(const float* wsm, const flo
 }
 
 __global__ void __launch_bounds__(SM_THREADS)
-    hpd_small_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net, int K,
-                         float* __restrict__ uprobs, float* __restrict__ utopv, int32_t* __restrict__ utopi,
-                         int resident) {
+    hpd_small_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net,
+                         const __grid_constant__ SmallEnc enc, int K, float* __restrict__ uprobs, float* utopv,
+                         int32_t* utopi, int resident) {
   extern __shared__ float sm[];
   float* bufA = sm;                       // [SM_MAXW][NB] unit-major activations
   float* bufB = sm + NB * SM_MAXW;        // [SM_MAXW][NB]
@@ -314,6 +326,36 @@ __global__ void __launch_bounds__(SM_THREADS)
       }
       __syncwarp();
       select_topk<int32_t>(z, T, K, lane, utopv + u * K, utopi + u * K);
+      if (enc.nfeat) {
+        // node pass of the encoding for this node's level nodes (same arithmetic as node_features_fwd_kernel); lane = level
+        __syncwarp();
+        const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
+        const float* tv = utopv + u * K;
+        const int32_t* ti = utopi + u * K;
+        const int F = enc.F, mode = enc.mode;
+        for (int l = lane; l < lat.num_levels; l += 32) {
+          const int i = cx - lat.lox[l], j = cy - lat.loy[l];
+          if (i < 0 || i >= lat.lwx[l] || j < 0 || j >= lat.lwy[l]) continue;
+          const float* table = enc.tables.ptr[l];
+          for (int k = 0; k < K; ++k) prefetch_l1(table + static_cast<int64_t>(ti[k]) * F);   // K misses in flight, not in turn
+          float mx;
+          const float norm = mix_weight_norm(tv, K, mode, mx);
+          float acc[GNGF_MAX_FEATURES];
+#pragma unroll
+          for (int f = 0; f < GNGF_MAX_FEATURES; ++f) acc[f] = 0.0f;
+          for (int k = 0; k < K; ++k) {
+            const float w = (mode == GNGF_MIX_WEIGHTED_AVG) ? tv[k] : mix_weight(tv[k], mode, mx, norm);
+            const float* row = table + static_cast<int64_t>(ti[k]) * F;
+#pragma unroll
+            for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+              if (f < F) acc[f] = fmaf(__ldg(row + f), w, acc[f]);
+          }
+          float* out = enc.nfeat + (lat.loff[l] + static_cast<int64_t>(i) * lat.lwy[l] + j) * F;
+#pragma unroll
+          for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+            if (f < F) out[f] = (mode == GNGF_MIX_WEIGHTED_AVG) ? acc[f] / norm : acc[f];
+        }
+      }
     }
   }
 }
@@ -321,8 +363,8 @@ __global__ void __launch_bounds__(SM_THREADS)
 // backward over NB nodes per CTA.  gT buffers are stored transposed ([width][NB]) so that a thread reads the NB
 // adjoints of one unit with two 16-byte loads.
 __global__ void __launch_bounds__(SM_THREADS)
-    hpd_small_bwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net, int K,
-                         const float* __restrict__ uprobs, const int32_t* __restrict__ utopi,
+    hpd_small_bwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ HpdNet net,
+                         const __grid_constant__ SmallEnc enc, int K, const float* __restrict__ uprobs, const int32_t* __restrict__ utopi,
                          const float* __restrict__ dtv, const int32_t* __restrict__ cnt,
                          const float* __restrict__ gcol, const float* __restrict__ gcol_k,
                          const float* __restrict__ gdense, int gt_rows, int resident) {
@@ -334,6 +376,7 @@ __global__ void __launch_bounds__(SM_THREADS)
   float* wtile = part + 2 * SM_MAXW * NB; // [2][32][SM_MAXW] weight-row tiles of the dX products, or -- resident -- every
                                           // layer's (N_i, K_i) matrix, top layer first, requested at kernel start
   __shared__ float cl_s[NB][GNGF_MAX_LEVELS];
+  __shared__ float dtv_s[NB][GNGF_MAX_TOPK];
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   const int64_t u0 = static_cast<int64_t>(blockIdx.x) * NB;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -351,6 +394,81 @@ __global__ void __launch_bounds__(SM_THREADS)
     }
   }
   const float* wres = wtile;
+
+  // ---- adjoint of the selected probabilities: the incoming one, plus -- fused -- the encoding's node pass ----
+  for (int e = tid; e < NB * K; e += SM_THREADS) {
+    const int n = e / K, k = e % K;
+    dtv_s[n][k] = (dtv && u0 + n < U) ? dtv[(u0 + n) * K + k] : 0.0f;
+  }
+  __syncthreads();
+  if (enc.dnf) {
+    // thread = (node, level) = one level node: same arithmetic as node_features_bwd_kernel (k5_encode_bwd.cu)
+    const int F = enc.F, mode = enc.mode;
+    for (int e = tid; e < NB * L; e += SM_THREADS) {
+      const int n = e / L, l = e % L;
+      const int64_t u = u0 + n;
+      if (u >= U) continue;
+      const int cx = lat.ox + static_cast<int>(u / lat.wy), cy = lat.oy + static_cast<int>(u % lat.wy);
+      const int i = cx - lat.lox[l], j = cy - lat.loy[l];
+      if (i < 0 || i >= lat.lwx[l] || j < 0 || j >= lat.lwy[l]) continue;
+      const float* dn = enc.dnf + (lat.loff[l] + static_cast<int64_t>(i) * lat.lwy[l] + j) * F;
+      float d[GNGF_MAX_FEATURES];
+      bool any = false;
+#pragma unroll
+      for (int f = 0; f < GNGF_MAX_FEATURES; ++f) {
+        d[f] = f < F ? dn[f] : 0.0f;
+        any |= d[f] != 0.0f;
+      }
+      if (!any) continue;   // untouched level node
+      const float* p = uprobs + u * T;
+      const int32_t* ti = utopi + u * K;
+      const float* table = enc.tables.ptr[l];
+      float* tgrad = enc.tgrads.ptr[l];
+      float mx = 0.0f, norm = 1.0f;
+      if (mode == GNGF_MIX_SOFTMAX) {
+        mx = p[ti[0]];
+        for (int k = 1; k < K; ++k) mx = fmaxf(mx, p[ti[k]]);
+        norm = 0.0f;
+        for (int k = 0; k < K; ++k) norm += expf(p[ti[k]] - mx);
+      } else if (mode == GNGF_MIX_WEIGHTED_AVG) {
+        norm = 0.0f;
+        for (int k = 0; k < K; ++k) norm += p[ti[k]];
+      }
+      float dotw = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        const float tvk = p[ti[k]];
+        const float w = mode == GNGF_MIX_SOFTMAX ? expf(tvk - mx) / norm
+                                                 : (mode == GNGF_MIX_WEIGHTED_AVG ? tvk / norm : tvk);
+        const int64_t row = static_cast<int64_t>(ti[k]) * F;
+        float dw = 0.0f;
+#pragma unroll
+        for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+          if (f < F) dw = fmaf(d[f], __ldg(table + row + f), dw);
+        dotw = fmaf(dw, w, dotw);
+        if (F == 2) {
+          red_add_v2(tgrad + row, d[0] * w, d[1] * w);
+        } else {
+#pragma unroll
+          for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+            if (f < F) atomicAdd(tgrad + row + f, d[f] * w);
+        }
+      }
+      for (int k = 0; k < K; ++k) {
+        const float tvk = p[ti[k]];
+        const int64_t row = static_cast<int64_t>(ti[k]) * F;
+        float dw = 0.0f;
+#pragma unroll
+        for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
+          if (f < F) dw = fmaf(d[f], __ldg(table + row + f), dw);
+        float g;
+        if (mode == GNGF_MIX_SOFTMAX) g = (expf(tvk - mx) / norm) * (dw - dotw);
+        else if (mode == GNGF_MIX_WEIGHTED_AVG) g = (dw - dotw) / norm;
+        else g = dw;
+        atomicAdd(&dtv_s[n][k], g);
+      }
+    }
+    __syncthreads();
+  }
 
   // ---- dlogits of node (u0 + warp): same arithmetic as hpd_dlogits_kernel ----
   {
@@ -371,12 +489,22 @@ __global__ void __launch_bounds__(SM_THREADS)
       __syncwarp();
       const float* p = uprobs + u * T;
       const float* gd = gdense ? gdense + u * T : nullptr;
+      // adjoint of the K selected probabilities (dtv_s: the incoming one plus the encoding's node pass above); lane
+      // owns k = lane + 32 m
+      float dtv_r[(GNGF_MAX_TOPK + 31) / 32];
+#pragma unroll
+      for (int m = 0; m < (GNGF_MAX_TOPK + 31) / 32; ++m) dtv_r[m] = lane + 32 * m < K ? dtv_s[n][lane + 32 * m] : 0.0f;
       float dot = 0.0f;
-      for (int k = lane; k < K; k += 32) {
-        float g = dtv[u * K + k];
-        if (gcol_k)
-          for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
-        dot = fmaf(g, p[utopi[u * K + k]], dot);
+#pragma unroll
+      for (int m = 0; m < (GNGF_MAX_TOPK + 31) / 32; ++m) {
+        const int k = lane + 32 * m;
+        if (k < K) {
+          float g = dtv_r[m];
+          if (gcol_k)
+            for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
+          dtv_r[m] = g;   // complete adjoint of slot k
+          dot = fmaf(g, p[utopi[u * K + k]], dot);
+        }
       }
       if (gcol || gd) {
         for (int t = lane; t < T; t += 32) {
@@ -394,12 +522,13 @@ __global__ void __launch_bounds__(SM_THREADS)
         gT[t * NB + n] = p[t] * (g - dot);
       }
       __syncwarp();
-      for (int k = lane; k < K; k += 32) {
-        float g = dtv[u * K + k];
-        if (gcol_k)
-          for (int l = 0; l < L; ++l) g = fmaf(cl[l], gcol_k[l * K + k], g);
-        const int t = utopi[u * K + k];
-        gT[t * NB + n] += p[t] * g;
+#pragma unroll
+      for (int m = 0; m < (GNGF_MAX_TOPK + 31) / 32; ++m) {
+        const int k = lane + 32 * m;
+        if (k < K) {
+          const int t = utopi[u * K + k];
+          gT[t * NB + n] += p[t] * dtv_r[m];
+        }
       }
     } else {
       for (int t = lane; t < T; t += 32) gT[t * NB + n] = 0.0f;
@@ -571,7 +700,7 @@ static size_t small_bwd_resident_smem(int n_layers, const int32_t* widths, const
     wfl += static_cast<size_t>(widths[i + 1]) * widths[i];
   }
   const size_t bytes = sizeof(float) * (static_cast<size_t>(gt_rows) * NB + SM_MAXW * NB + 2 * SM_MAXW * NB + wfl);
-  return (n_layers <= 6 && bytes <= 227 * 1024 - 2048) ? bytes : 0;
+  return (n_layers <= 6 && bytes <= 227 * 1024 - 6144) ? bytes : 0;   // (5 KB of static shared memory in the kernel)
 }
 
 }  // namespace gngf
@@ -586,12 +715,19 @@ int gngf_hpd_small_supported(int32_t n_layers, const int32_t* widths, int32_t to
 }
 
 // w / b / act: arrays of n_layers device pointers (act: n_layers - 1 hidden outputs, (U, width))
-int gngf_hpd_small_fwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
-                       const float* const* b, float* const* act, int32_t topk, float* uprobs, float* utopv,
-                       int32_t* utopi, void* stream) {
+int gngf_hpd_small_fwd_enc(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                           const float* const* b, float* const* act, int32_t topk, float* uprobs, float* utopv,
+                           int32_t* utopi, gngf_tables tables, int32_t F, int32_t mix_mode, float* nfeat, void* stream) {
   if (!gngf_hpd_small_supported(n_layers, widths, topk)) return GNGF_ERR_UNSUPPORTED;
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   if (U <= 0) return GNGF_ERR_INVALID_ARGUMENT;
+  if (nfeat && (F <= 0 || F > GNGF_MAX_FEATURES || lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS))
+    return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::SmallEnc enc{};
+  enc.tables = tables;
+  enc.F = F;
+  enc.mode = mix_mode;
+  enc.nfeat = nfeat;
   gngf::HpdNet net{};
   net.n_layers = n_layers;
   for (int i = 0; i <= n_layers; ++i) net.width[i] = widths[i];
@@ -606,21 +742,38 @@ int gngf_hpd_small_fwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths
                            static_cast<int>(smem)) != cudaSuccess)
     return gngf::check_launch();
   gngf::hpd_small_fwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::NB)), gngf::SM_THREADS, smem,
-                               gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopv, utopi, res ? 1 : 0);
+                               gngf::as_stream(stream)>>>(lat, net, enc, topk, uprobs, utopv, utopi, res ? 1 : 0);
   gngf::note_launch();
   return gngf::check_launch();
 }
 
+int gngf_hpd_small_fwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                       const float* const* b, float* const* act, int32_t topk, float* uprobs, float* utopv,
+                       int32_t* utopi, void* stream) {
+  return gngf_hpd_small_fwd_enc(lat, n_layers, widths, w, b, act, topk, uprobs, utopv, utopi, gngf_tables{}, 0, 0, nullptr,
+                                stream);
+}
+
 // gact: n_layers outputs (U, width[i+1]) receiving the pre-activation adjoints; dbias: n_layers bias gradients (+=);
 // dw0 (width[1], 2) (+=).  The weight gradients of layers >= 1 are dW_i += gact[i]^T act[i-1] (gngf_linear_bwd).
-int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
-                       float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
-                       const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
-                       const float* gcol, const float* gcol_k, const float* gdense, void* stream) {
+int gngf_hpd_small_bwd_enc(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                           float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
+                           const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                           const float* gcol, const float* gcol_k, const float* gdense, gngf_tables tables,
+                           gngf_tables table_grads, int32_t F, int32_t mix_mode, const float* dnf, void* stream) {
   if (!gngf_hpd_small_supported(n_layers, widths, topk)) return GNGF_ERR_UNSUPPORTED;
   const int64_t U = static_cast<int64_t>(lat.wx) * lat.wy;
   if (U <= 0) return GNGF_ERR_INVALID_ARGUMENT;
   if ((gcol || gcol_k) && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
+  if (!dtv && !dnf) return GNGF_ERR_INVALID_ARGUMENT;
+  if (dnf && (F <= 0 || F > GNGF_MAX_FEATURES || lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS))
+    return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::SmallEnc enc{};
+  enc.tables = tables;
+  enc.tgrads = table_grads;
+  enc.F = F;
+  enc.mode = mix_mode;
+  enc.dnf = dnf;
   gngf::HpdNet net{};
   net.n_layers = n_layers;
   for (int i = 0; i <= n_layers; ++i) net.width[i] = widths[i];
@@ -638,10 +791,19 @@ int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths
                            static_cast<int>(smem)) != cudaSuccess)
     return gngf::check_launch();
   gngf::hpd_small_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, gngf::NB)), gngf::SM_THREADS, smem,
-                               gngf::as_stream(stream)>>>(lat, net, topk, uprobs, utopi, dtv, cnt, gcol, gcol_k,
+                               gngf::as_stream(stream)>>>(lat, net, enc, topk, uprobs, utopi, dtv, cnt, gcol, gcol_k,
                                                           gdense, gt_rows, res ? 1 : 0);
   gngf::note_launch();
   return gngf::check_launch();
+}
+
+int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                       float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
+                       const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                       const float* gcol, const float* gcol_k, const float* gdense, void* stream) {
+  if (!dtv) return GNGF_ERR_INVALID_ARGUMENT;
+  return gngf_hpd_small_bwd_enc(lat, n_layers, widths, w, act, gact, dbias, dw0, topk, uprobs, utopi, dtv, cnt, gcol,
+                                gcol_k, gdense, gngf_tables{}, gngf_tables{}, 0, 0, nullptr, stream);
 }
 
 }  // extern "C"

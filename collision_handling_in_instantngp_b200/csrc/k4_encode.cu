@@ -14,29 +14,6 @@
 
 namespace gngf {
 
-__device__ __forceinline__ float mix_weight_norm(const float* tv, int K, int mode, float& mx) {
-  // returns the normaliser; mx = max (softmax mode)
-  mx = 0.0f;
-  if (mode == GNGF_MIX_SOFTMAX) {
-    mx = tv[0];
-    for (int k = 1; k < K; ++k) mx = fmaxf(mx, tv[k]);
-    float s = 0.0f;
-    for (int k = 0; k < K; ++k) s += expf(tv[k] - mx);
-    return s;
-  }
-  if (mode == GNGF_MIX_WEIGHTED_AVG) {
-    float s = 0.0f;
-    for (int k = 0; k < K; ++k) s += tv[k];
-    return s;
-  }
-  return 1.0f;
-}
-__device__ __forceinline__ float mix_weight(float tv, int mode, float mx, float norm) {
-  if (mode == GNGF_MIX_SOFTMAX) return expf(tv - mx) / norm;
-  if (mode == GNGF_MIX_WEIGHTED_AVG) return tv / norm;
-  return tv;
-}
-
 // grid (ceil(max level box / 256), L); thread per level node
 __global__ void __launch_bounds__(256)
     node_features_fwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ gngf_tables tables,

@@ -358,6 +358,7 @@ class ForwardState:
     w_planes: Optional[torch.Tensor] = None                      # (3,T,Kd) bf16 planes of the output layer
     h_planes: Optional[torch.Tensor] = None                      # (3,U,Kd) bf16 planes of its input (streaming path)
     hpd_small: bool = False                                      # fused small-lattice HPD kernels were used
+    nfeat: Optional[torch.Tensor] = None                         # (S,F) written by the HPD kernel itself (small lattices)
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
     node_ids: Optional[torch.Tensor] = None                      # (Ua,) int32 active nodes: the HPD chain (hpd_acts,
@@ -417,6 +418,8 @@ def _streaming_ok(cfg, U, T, k, kd) -> bool:
 MLP_TENSOR_CORES = True           # decoder through k6_mlp_tc.cu (tcgen05); False: the fp32 CUDA-core kernels of k6_mlp.cu
 
 SMALL_LATTICE_MAX_NODES = 8192    # fused per-node HPD kernels (k2_hpd_small.cu) below this many nodes
+SMALL_FUSE_NODE_PASSES = True     # ... which then also run the encoding's per-level-node passes (two launches fewer on the
+                                  # critical path of the step); False: separate node_features_fwd / _bwd launches
 
 
 def _hpd_small_ok(hpd_w, U, k) -> bool:
@@ -426,7 +429,7 @@ def _hpd_small_ok(hpd_w, U, k) -> bool:
     return bool(_lib.load().gngf_hpd_small_supported(len(hpd_w), _lib.int_array(widths), k))
 
 
-def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
+def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state, tables=None):
     """HashProbDistribution.forward (models.py:90-123) on every lattice node.  Fills state.hpd_acts and
     state.utopv / utopi (U,K); state.uprobs (U,T) on the dense path, state.row_max / row_sum (U) on the
     streaming path (tcgen05 GEMM fused with online softmax + running top-k, logits never written)."""
@@ -443,6 +446,13 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state):
         state.uprobs = torch.empty((U, T), dtype=torch.float32, device=device)
         state.utopv = torch.empty((U, k), dtype=torch.float32, device=device)
         state.utopi = torch.empty((U, k), dtype=torch.int32, device=device)
+        if tables is not None and SMALL_FUSE_NODE_PASSES:
+            state.nfeat = torch.empty((lat.num_level_nodes, cfg.feature_dim), dtype=torch.float32, device=device)
+            call("gngf_hpd_small_fwd_enc", lat, n, _lib.int_array(widths), _lib.ptr_array(hpd_w), _lib.ptr_array(hpd_b),
+                 _lib.ptr_array(state.hpd_acts), k, state.uprobs.data_ptr(), state.utopv.data_ptr(),
+                 state.utopi.data_ptr(), make_tables(tables), cfg.feature_dim, cfg.mix_mode, state.nfeat.data_ptr(),
+                 _stream())
+            return
         call("gngf_hpd_small_fwd", lat, n, _lib.int_array(widths), _lib.ptr_array(hpd_w), _lib.ptr_array(hpd_b),
              _lib.ptr_array(state.hpd_acts), k, state.uprobs.data_ptr(), state.utopv.data_ptr(),
              state.utopi.data_ptr(), _stream())
@@ -521,16 +531,18 @@ class GNGFPath(torch.autograd.Function):
             call("gngf_encode_hash_fwd", x.data_ptr(), P, lat, tab, T, F, enc.data_ptr(), None, st)
             colsum = uvals = None
         else:
-            hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev, cfg, state)
+            hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev, cfg, state, tables=tables)
             # API output idx_topk (P,L,4,K) int64: nothing in the step reads it -> side stream, joined at the end
             state.idx_topk = torch.empty((P, L, 4, K), dtype=torch.int64, device=dev)
             fork_idx = _Fork(dev, 0)
             with fork_idx:
                 gather_rows(x, lat, state.utopi, out=state.idx_topk)
             S = lat.num_level_nodes
-            nfeat = torch.empty((S, F), dtype=torch.float32, device=dev)
-            call("gngf_node_features_fwd", lat, tab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
-                 state.utopi.data_ptr(), nfeat.data_ptr(), st)
+            nfeat, state.nfeat = state.nfeat, None       # (not kept for the backward)
+            if nfeat is None:
+                nfeat = torch.empty((S, F), dtype=torch.float32, device=dev)
+                call("gngf_node_features_fwd", lat, tab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
+                     state.utopi.data_ptr(), nfeat.data_ptr(), st)
             # cnt (S) | cell counts (S) | err flag (1) | colsum (L*N) share one zero-initialised buffer: one memset
             N = K if cfg.topk_only else T
             # (the column sums start on a 16-byte boundary: the peer all-reduce of dp.py moves them as float4)
@@ -659,8 +671,10 @@ class GNGFPath(torch.autograd.Function):
 
         call("gngf_encode_bwd", x.data_ptr(), P, lat, F, denc.data_ptr(), dnf.data_ptr(), st)
         need_hpd = cfg.hpd_trainable
-        call("gngf_node_features_bwd", lat, make_tables(tables), gtab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
-             state.utopi.data_ptr(), dnf.data_ptr(), dtv.data_ptr() if need_hpd else None, st)
+        fuse_nodes = need_hpd and state.hpd_small and SMALL_FUSE_NODE_PASSES
+        if not fuse_nodes:
+            call("gngf_node_features_bwd", lat, make_tables(tables), gtab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
+                 state.utopi.data_ptr(), dnf.data_ptr(), dtv.data_ptr() if need_hpd else None, st)
         if not need_hpd:
             for i in range(2 * nh):
                 grads[i] = None
@@ -669,6 +683,7 @@ class GNGFPath(torch.autograd.Function):
             return (None, None, *grads)
 
         gcol = gcol_k = gdense = None
+        dtv_extra = False            # dtv holds an adjoint of utopv that did not come from the node pass
         if grad_colsum is not None:
             grad_colsum = _f32c(grad_colsum)
             if state.colsum_world > 1:
@@ -681,6 +696,7 @@ class GNGFPath(torch.autograd.Function):
             grad_uvals = _f32c(grad_uvals)
             if cfg.topk_only:
                 dtv.add_(grad_uvals.reshape(-1))
+                dtv_extra = True
             else:
                 gdense = grad_uvals
         if state.hpd_small:
@@ -688,10 +704,18 @@ class GNGFPath(torch.autograd.Function):
             # gradients dW_i += g_i^T h_{i-1} (reductions over all nodes) as split-K layer kernels
             widths = [2] + [w.shape[0] for w in hpd_w]
             gacts = [torch.empty((U, w.shape[0]), dtype=torch.float32, device=dev) for w in hpd_w]
-            call("gngf_hpd_small_bwd", lat, nh, _lib.int_array(widths), _lib.ptr_array(hpd_w),
-                 _lib.ptr_array(state.hpd_acts), _lib.ptr_array(gacts), _lib.ptr_array(g_hpd_b), g_hpd_w[0].data_ptr(), K,
-                 state.uprobs.data_ptr(), state.utopi.data_ptr(), dtv.data_ptr(), state.cnt.data_ptr(), _ptr(gcol),
-                 _ptr(gcol_k), _ptr(gdense), st)
+            if fuse_nodes:
+                # ... and the encoding's node pass: table gradients, adjoint of the selected probabilities in registers
+                call("gngf_hpd_small_bwd_enc", lat, nh, _lib.int_array(widths), _lib.ptr_array(hpd_w),
+                     _lib.ptr_array(state.hpd_acts), _lib.ptr_array(gacts), _lib.ptr_array(g_hpd_b),
+                     g_hpd_w[0].data_ptr(), K, state.uprobs.data_ptr(), state.utopi.data_ptr(),
+                     dtv.data_ptr() if dtv_extra else None, state.cnt.data_ptr(), _ptr(gcol), _ptr(gcol_k), _ptr(gdense),
+                     make_tables(tables), gtab, F, cfg.mix_mode, dnf.data_ptr(), st)
+            else:
+                call("gngf_hpd_small_bwd", lat, nh, _lib.int_array(widths), _lib.ptr_array(hpd_w),
+                     _lib.ptr_array(state.hpd_acts), _lib.ptr_array(gacts), _lib.ptr_array(g_hpd_b), g_hpd_w[0].data_ptr(),
+                     K, state.uprobs.data_ptr(), state.utopi.data_ptr(), dtv.data_ptr(), state.cnt.data_ptr(), _ptr(gcol),
+                     _ptr(gcol_k), _ptr(gdense), st)
             forks = []
             for i in range(1, nh):      # independent products: one stream each
                 f = _Fork(dev, i - 1)

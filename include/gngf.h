@@ -198,6 +198,19 @@ int gngf_hpd_small_bwd(gngf_lattice lat, int32_t n_layers, const int32_t* widths
                        float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
                        const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
                        const float* gcol, const float* gcol_k, const float* gdense, void* stream);
+/* The same two with the encoding's per-level-node passes folded in (a level node belongs to exactly one lattice
+ * node, whose selection the owning warp already holds): the forward also writes nfeat (S,F) as
+ * gngf_node_features_fwd would, the backward consumes dnf (S,F) as gngf_node_features_bwd would -- table
+ * gradients += and the adjoint of the K selected probabilities kept in registers (dtv may then be NULL, or hold
+ * an additional adjoint of utopv).  nfeat / dnf == NULL: identical to the plain entry points.               */
+int gngf_hpd_small_fwd_enc(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                           const float* const* b, float* const* act, int32_t topk, float* uprobs, float* utopv,
+                           int32_t* utopi, gngf_tables tables, int32_t F, int32_t mix_mode, float* nfeat, void* stream);
+int gngf_hpd_small_bwd_enc(gngf_lattice lat, int32_t n_layers, const int32_t* widths, const float* const* w,
+                           float* const* act, float* const* gact, float* const* dbias, float* dw0, int32_t topk,
+                           const float* uprobs, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+                           const float* gcol, const float* gcol_k, const float* gdense, gngf_tables tables,
+                           gngf_tables table_grads, int32_t F, int32_t mix_mode, const float* dnf, void* stream);
 
 /* ---- K6: fused decoder MLP (models.py:382-392, 468-470) for the reference's shape IN -> 64 -> 64 -> OUT -----
  * rgb (P,OUT) = sigmoid(W2 act(W1 act(W0 enc + b0) + b1) + b2), act = ReLU or LeakyReLU(0.01); activations stay

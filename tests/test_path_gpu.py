@@ -310,6 +310,28 @@ def test_fused_small_lattice_hpd_equals_general_path(name):
         assert rel_err(out_small["grads"][k], out_gen["grads"][k]) < 2e-5, k
 
 
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "cfg2_epoch1", "k1", "k20", "mix_raw",
+                                  "mix_weighted_avg", "bw_leaky"])
+def test_node_passes_folded_into_the_small_hpd_kernels(name):
+    """k2_hpd_small.cu with the encoding's per-level-node passes folded in (gngf_hpd_small_fwd_enc / _bwd_enc) against
+    the separate node_features_fwd / _bwd launches: same selections, same features, same gradients."""
+    from collision_handling_in_instantngp_b200 import ops
+    g = load(name)
+    net = build_net(g)
+    out_fused = run_step(net, g)
+    assert out_fused["state"].hpd_small and ops.SMALL_FUSE_NODE_PASSES
+    ops.SMALL_FUSE_NODE_PASSES = False
+    try:
+        out_sep = run_step(net, g)
+    finally:
+        ops.SMALL_FUSE_NODE_PASSES = True
+    assert np.array_equal(out_fused["idx"], out_sep["idx"])
+    assert np.array_equal(out_fused["rgb"], out_sep["rgb"])       # identical arithmetic per level node
+    for k in out_sep["grads"]:
+        assert rel_err(out_fused["grads"][k], out_sep["grads"][k]) < 2e-6, k
+    _check_grads(out_fused, g)
+
+
 def test_graphed_trainer_matches_eager_steps():
     """trainer.GraphedTrainer (whole step in CUDA graphs, fused Adam, loss adjoints seeding the backward, double-buffered
     pipelined inputs) against the same steps driven eagerly through the module API with torch.optim.Adam."""
