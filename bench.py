@@ -493,7 +493,7 @@ def run_ours(args, w):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         # tearing the NCCL communicator down after its collectives were captured in a CUDA graph was observed
         # to hang; the line is out, so leave without the teardown
@@ -502,7 +502,20 @@ def run_ours(args, w):
         os._exit(0)
 
 
+JSON_OUT = sys.stdout
+
+
+def _keep_stdout_for_the_json_line():
+    """Libraries write to file descriptor 1 (NCCL prints its version banner there): route fd 1 to stderr and keep the
+    original stdout for the one JSON line."""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -536,7 +549,7 @@ def main():
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-        }), flush=True)
+        }), file=JSON_OUT, flush=True)
         return
     run_ours(args, w)
 

@@ -117,6 +117,8 @@ SIGNATURES = {
     "gngf_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_float, c_float, c_float, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),
+    "gngf_loss_parts": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
+                                _P, _P, _P, _P, c_int32, _P]),
     "gngf_count_distinct_workspace_words": (c_int64, [c_int32, c_int32, c_int64]),
     "gngf_count_distinct_f32": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, _P]),
     "gngf_count_distinct_i64": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int64, _P, _P, _P, _P]),

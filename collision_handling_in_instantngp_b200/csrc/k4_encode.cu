@@ -193,26 +193,46 @@ __global__ void __launch_bounds__(256)
 }
 
 // out[l, n] += sum over level nodes s of level l: cnt[s] * uvals[u(s), n]
-// grid (ceil(N/128), node chunks, L), block 128: thread = one column n
+// grid (ceil(N/128), node chunks, L), block 128: thread = one column n.  The nodes of a chunk are staged 32 at a time
+// (multiplicity + lattice node in shared memory, untouched nodes dropped), so that the column loop is a run of
+// independent, coalesced row reads: the first version chained two dependent L2 reads per node (cnt -> branch -> row),
+// 32 nodes deep -- 16 us of pure latency at the published configuration, on the branch the loss waits for.
 __global__ void __launch_bounds__(128)
     lattice_colsum_kernel(const __grid_constant__ gngf_lattice lat, const int32_t* __restrict__ cnt,
                           const float* __restrict__ uvals, int64_t N, int64_t nodes_per_block,
                           float* __restrict__ out) {
+  __shared__ float c_s[32];
+  __shared__ int64_t u_s[32];
+  __shared__ int n_s;
   const int l = blockIdx.z;
   const int64_t n = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int wy = lat.lwy[l];
   const int64_t box = static_cast<int64_t>(lat.lwx[l]) * wy;
   const int64_t i0 = static_cast<int64_t>(blockIdx.y) * nodes_per_block;
   const int64_t i1 = min(box, i0 + nodes_per_block);
-  if (i0 >= box || n >= N) return;
+  if (i0 >= box) return;   // block-uniform
   float acc = 0.0f;
-  for (int64_t i = i0; i < i1; ++i) {
-    const int c = cnt[lat.loff[l] + i];
-    if (c == 0) continue;
-    const int64_t u = global_node(lat, lat.lox[l] + static_cast<int>(i / wy), lat.loy[l] + static_cast<int>(i % wy));
-    acc = fmaf(static_cast<float>(c), uvals[u * N + n], acc);
+  for (int64_t base = i0; base < i1; base += 32) {
+    if (threadIdx.x < 32) {   // warp 0: compact the touched nodes of this group
+      const int64_t i = base + threadIdx.x;
+      const int c = i < i1 ? cnt[lat.loff[l] + i] : 0;
+      const unsigned live = __ballot_sync(0xffffffffu, c != 0);
+      if (c != 0) {
+        const int slot = __popc(live & ((1u << threadIdx.x) - 1u));
+        c_s[slot] = static_cast<float>(c);
+        u_s[slot] = global_node(lat, lat.lox[l] + static_cast<int>(i / wy), lat.loy[l] + static_cast<int>(i % wy));
+      }
+      if (threadIdx.x == 0) n_s = __popc(live);
+    }
+    __syncthreads();
+    const int m = n_s;
+    if (n < N) {
+#pragma unroll 8
+      for (int k = 0; k < m; ++k) acc = fmaf(c_s[k], __ldg(uvals + u_s[k] * N + n), acc);
+    }
+    __syncthreads();
   }
-  atomicAdd(out + l * N + n, acc);
+  if (n < N) atomicAdd(out + l * N + n, acc);
 }
 
 // the same for a narrow value row (top-k-only mode: N = K <= 8): thread per level node, N register accumulators,

@@ -88,4 +88,27 @@ int gngf_loss_fwd_bwd(const float* rgb, const float* target, int64_t n_rgb, cons
   return gngf::check_launch();
 }
 
+// The two halves separately, for a caller that runs them on different streams (trainer.GraphedTrainer: the MSE half
+// seeds the decoder backward on the main stream while the divergence half waits for the column sums -- and under data
+// parallelism for their all-reduce -- on the side stream).  parts: 1 = MSE (out[0] += l_mse * mse, out[1] = mse, d_rgb),
+// 2 = levels (out[0] += sum_l ..., out[2 + l], d_colsum), 3 = both.  `out` (2 + L floats) must be ZERO on entry of the
+// first part: no memset here.
+int gngf_loss_parts(const float* rgb, const float* target, int64_t n_rgb, const float* colsum, int32_t L, int64_t N,
+                    float rows, float gamma, float epsilon, float l_mse, float l_js_kl, const float* coll_term,
+                    float* out, float* d_rgb, float* d_colsum, int32_t parts, void* stream) {
+  if ((parts & 3) == 0 || !out) return GNGF_ERR_INVALID_ARGUMENT;
+  const bool mse = parts & 1, lev = parts & 2;
+  if (mse && (n_rgb <= 0 || !rgb || !target || !d_rgb)) return GNGF_ERR_INVALID_ARGUMENT;
+  if (lev && (L <= 0 || L > GNGF_MAX_LEVELS || N <= 0 || rows <= 0 || !colsum || !d_colsum))
+    return GNGF_ERR_INVALID_ARGUMENT;
+  const int Lb = lev ? L : 0;
+  const int mse_blocks =
+      mse ? std::max(1, static_cast<int>(std::min<int64_t>(gngf::ceil_div(n_rgb, 256 * 4), 2 * gngf::sm_count()))) : 0;
+  gngf::loss_kernel<<<Lb + mse_blocks, 256, 0, gngf::as_stream(stream)>>>(rgb, target, mse ? n_rgb : 0, colsum, Lb, N, rows,
+                                                                         gamma, epsilon, l_mse, l_js_kl, coll_term, out,
+                                                                         d_rgb, d_colsum);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
 }  // extern "C"

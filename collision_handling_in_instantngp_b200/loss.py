@@ -84,3 +84,31 @@ def fused_loss_and_grads(rgb, target, colsum, rows, gamma, epsilon, l_mse=1.0, l
              None if collisions_term is None else ops._f32c(collisions_term).data_ptr(), out.data_ptr(),
              d_rgb.data_ptr(), d_colsum.data_ptr(), ops._stream())
     return out, d_rgb, d_colsum
+
+
+def fused_loss_and_grads_split(rgb, target, colsum, rows, gamma, epsilon, l_mse=1.0, l_js_kl=1.0, collisions_term=None,
+                               levels_stream=None):
+    """As :func:`fused_loss_and_grads`, as two launches of the same kernel (gngf_loss_parts): the MSE half on the current
+    stream, the divergence half on `levels_stream` -- the side stream on which the column sums are produced (and, under
+    data parallelism, all-reduced) when the forward ran with ``ops.DEFER_COLSUM_JOIN``.  The caller joins that stream
+    before it consumes `out` or `d_colsum` (GNGFPath.backward does, after the encoding's point pass).  All buffers are
+    allocated on the current stream."""
+    from . import ops
+    rgb_c, tgt_c, cs_c = ops._f32c(rgb.detach()), ops._f32c(target), ops._f32c(colsum.detach())
+    L, N = cs_c.shape
+    out = torch.zeros(2 + L, dtype=torch.float32, device=rgb_c.device)
+    d_rgb = torch.empty_like(rgb_c)
+    d_colsum = torch.empty_like(cs_c)
+    coll = None if collisions_term is None else ops._f32c(collisions_term)
+    args = (rgb_c.data_ptr(), tgt_c.data_ptr(), rgb_c.numel(), cs_c.data_ptr(), L, N, float(rows), float(gamma),
+            float(epsilon), float(l_mse), float(l_js_kl), None if coll is None else coll.data_ptr(), out.data_ptr(),
+            d_rgb.data_ptr(), d_colsum.data_ptr())
+    if levels_stream is None:
+        ops.call("gngf_loss_parts", *args, 3, ops._stream())
+        return out, d_rgb, d_colsum
+    main = torch.cuda.current_stream()
+    levels_stream.wait_stream(main)            # `out` is zeroed on the current stream
+    ops.call("gngf_loss_parts", *args, 1, ops._stream())
+    with torch.cuda.stream(levels_stream):
+        ops.call("gngf_loss_parts", *args, 2, ops._stream())
+    return out, d_rgb, d_colsum

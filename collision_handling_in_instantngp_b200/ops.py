@@ -45,6 +45,11 @@ def _stream() -> int:
 # Under CUDA-graph capture the forks become parallel branches of the graph.  Buffers are always allocated on the
 # main stream (the caching allocator ties a block to the stream it was allocated on); only launches move.
 CONCURRENT = True
+# trainer.GraphedTrainer: the forward returns WITHOUT joining the side stream that produces the column sums (and, under
+# data parallelism, all-reduces them); the caller evaluates the divergence half of the loss on that stream
+# (state.colsum_fork.side) and the backward joins it after the encoding's point pass, right before the column-sum
+# adjoint is consumed.  The column-sum branch then overlaps the decoder forward AND backward instead of gating the loss.
+DEFER_COLSUM_JOIN = False
 _SIDE_STREAMS = {}
 
 
@@ -371,6 +376,7 @@ class ForwardState:
     mlp_masks: Optional[torch.Tensor] = None                     # (P,4) int32 ReLU pattern of the hidden layers
     idx_topk: Optional[torch.Tensor] = None                      # (P,L,4,K) int64, the API output (models.py:476-484)
     colsum_world: int = 1                                        # > 1: the column sums were summed over that many ranks
+    colsum_fork: Optional["_Fork"] = None                        # un-joined column-sum branch (DEFER_COLSUM_JOIN)
     err_flag: Optional[torch.Tensor] = None
 
 
@@ -587,7 +593,10 @@ class GNGFPath(torch.autograd.Function):
                 acts.append(h)
         if not cfg.use_hash:
             fork_idx.join()
-            fork_col.join()
+            if DEFER_COLSUM_JOIN and fork_col.on:
+                state.colsum_fork = fork_col
+            else:
+                fork_col.join()
         state.mlp_acts = acts
         state.x = x
         ctx.state = state
@@ -670,6 +679,9 @@ class GNGFPath(torch.autograd.Function):
             return (None, None, *grads)
 
         call("gngf_encode_bwd", x.data_ptr(), P, lat, F, denc.data_ptr(), dnf.data_ptr(), st)
+        if state.colsum_fork is not None:      # deferred join: the column sums' consumers (and grad_colsum) live on the
+            state.colsum_fork.join()           # side stream up to here
+            state.colsum_fork = None
         need_hpd = cfg.hpd_trainable
         fuse_nodes = need_hpd and state.hpd_small and SMALL_FUSE_NODE_PASSES
         if not fuse_nodes:

@@ -19,7 +19,8 @@ import torch.distributed as dist
 
 from . import dp
 from ._lib import GngfError
-from .loss import fused_loss_and_grads
+from . import ops
+from .loss import fused_loss_and_grads_split
 
 
 class GraphedTrainer:
@@ -84,13 +85,23 @@ class GraphedTrainer:
 
     def _eager_step(self, i: int = 0):
         self.opt.zero_grad(set_to_none=True)
-        rgb, probs, _, _ = self.net(self.xs[i], 1.0)
+        # the column-sum branch (multiplicities -> column sums -> under data parallelism their all-reduce -> divergence
+        # half of the loss) stays on its side stream until the backward needs its adjoint: it overlaps the decoder
+        # forward, the MSE half of the loss, the decoder backward and the encoding's point pass
+        ops.DEFER_COLSUM_JOIN = True
+        try:
+            rgb, probs, _, _ = self.net(self.xs[i], 1.0)
+        finally:
+            ops.DEFER_COLSUM_JOIN = False
+        state = self.net.last_state
+        fork = state.colsum_fork
         # under data parallelism `probs.colsum` already is the sum over ranks: the exchange happens inside the forward,
         # on the side stream that produces the column sums (dp.enable_gradient_allreduce), and the backward scales the
         # adjoint by the world size
         colsum = probs.colsum
-        out, d_rgb, d_colsum = fused_loss_and_grads(rgb, self.ys[i], colsum, self.rows, *self.loss_args)
-        # the loss kernel emits its own adjoints: they seed the backward directly
+        out, d_rgb, d_colsum = fused_loss_and_grads_split(rgb, self.ys[i], colsum, self.rows, *self.loss_args,
+                                                          levels_stream=None if fork is None else fork.side)
+        # the loss kernel emits its own adjoints: they seed the backward directly (GNGFPath.backward joins the side stream)
         torch.autograd.backward([rgb, colsum], [d_rgb, d_colsum])
         self.opt.step()
         return out[0]

@@ -254,6 +254,12 @@ int gngf_mlp3_tc_bwd(const float* enc, const float* rgb, const float* drgb, int6
 int gngf_loss_fwd_bwd(const float* rgb, const float* target, int64_t n_rgb, const float* colsum, int32_t L, int64_t N,
                       float rows, float gamma, float epsilon, float l_mse, float l_js_kl, const float* coll_term,
                       float* out, float* d_rgb, float* d_colsum, void* stream);
+/* the two halves separately (parts: 1 = MSE half -> out[0] +=, out[1], d_rgb; 2 = divergence half -> out[0] +=,
+ * out[2 + l], d_colsum; 3 = both), for callers that run them on different streams; `out` must be zero on entry of
+ * the first part (no memset inside)                                                                          */
+int gngf_loss_parts(const float* rgb, const float* target, int64_t n_rgb, const float* colsum, int32_t L, int64_t N,
+                    float rows, float gamma, float epsilon, float l_mse, float l_js_kl, const float* coll_term,
+                    float* out, float* d_rgb, float* d_colsum, int32_t parts, void* stream);
 
 /* ---- K3: softmax + nan_to_num + top-k (models.py:85,111 and DifferentiableTopk.forward 7-19) --------
  * logits (R,T) -> probs (R,T) (may alias logits, may be NULL), topv (R,K) sorted descending,
