@@ -75,3 +75,41 @@ def test_host_side_argument_validation_needs_no_gpu():
         opt.step()
     with pytest.raises(ValueError):
         FusedAdam([p], lr=-1.0)
+
+
+def test_active_node_and_split_loss_entry_points_validate_on_the_host():
+    """k11_active_nodes.cu / gngf_loss_parts / the *_enc and *_nodes variants: sizes and bad arguments are answered on
+    the host, before any launch."""
+    lib = pkg.load()
+    lat = build_lattice(level_resolutions(16, 8192, 16))
+    U = lat.num_nodes
+    assert U == 8193 * 8193
+    assert lib.gngf_active_nodes_bitmap_words(U) == (U + 31) // 32
+    assert lib.gngf_active_nodes_bitmap_words(0) == 0 and lib.gngf_active_nodes_bitmap_words(33) == 2
+    words = (U + 31) // 32
+    assert lib.gngf_active_nodes_chunks(U) == (words + 1023) // 1024            # one block per 1024 words = 32768 nodes
+    assert lib.gngf_active_nodes_chunks(0) == 0
+    assert lib.gngf_lattice_mark_nodes(None, 0, lat, None, None) == -1          # no bitmap
+    assert lib.gngf_lattice_mark_nodes(None, -1, lat, 16, None) == -1
+    assert lib.gngf_lattice_mark_nodes(None, 0, lat, 16, None) == 0             # empty batch: nothing to launch
+    assert lib.gngf_compact_nodes(None, U, None, None, 0, None, None) == -1
+    assert lib.gngf_compact_nodes(16, 1 << 31, 16, 16, 1, 16, None) == -1       # node ids are int32
+    assert lib.gngf_compact_nodes(20, 64, 16, 16, 1, 16, None) == -1            # bitmap must be 16-byte aligned
+    assert lib.gngf_scatter_node_rows(None, 0, None, 4, None, None) == 0        # no rows
+    assert lib.gngf_scatter_node_rows(None, 5, None, 4, None, None) == -1
+    assert lib.gngf_scatter_node_rows(16, 5, 16, 0, 16, None) == -1
+    assert lib.gngf_hpd_first_layer_fwd_nodes(lat, 16, U + 1, None, None, 32, 1, None, None) == -1   # more rows than nodes
+    assert lib.gngf_hpd_first_layer_fwd_nodes(lat, 16, 0, None, None, 32, 1, None, None) == 0        # empty list
+    assert lib.gngf_hpd_first_layer_bwd_nodes(lat, 16, 0, None, 32, None, None, None) == 0
+    # loss halves: parts must name a half, each half needs its own buffers
+    args = (None, None, 0, None, 4, 256, 1.0, -2.0, 1.0, 1.0, 1.0, None)
+    assert lib.gngf_loss_parts(*args, 16, None, None, 0, None) == -1
+    assert lib.gngf_loss_parts(*args, None, None, None, 3, None) == -1
+    assert lib.gngf_loss_parts(*args, 16, None, None, 1, None) == -1            # MSE half without rgb / target / d_rgb
+    assert lib.gngf_loss_parts(*args, 16, None, None, 2, None) == -1            # divergence half without column sums
+    # the streaming backward on a node list accepts fewer rows than the box, the plain entry point does not
+    small = build_lattice(level_resolutions(8, 32, 4))
+    a = (16,) * 5
+    common = (16, 16, 16, None, None, 16, 16, 1, 16, 16, 16, 16, None)
+    assert lib.gngf_hpd_stream_bwd(small, *a, 100, 256, 128, 4, *common) == -2                    # U != box
+    assert lib.gngf_hpd_stream_bwd_nodes(small, 16, *a, small.num_nodes + 1, 256, 128, 4, *common) == -2
