@@ -31,11 +31,31 @@ __global__ void __launch_bounds__(ADAM_THREADS)
     if (b < a.chunk_end[mid]) hi = mid; else lo = mid + 1;
   }
   const gngf_adam_tensor& T = a.t[lo];
-  const int t_now = *T.step + 1;
   const int64_t chunk = b - (lo ? a.chunk_end[lo - 1] : 0);
+  const int64_t base = chunk * ADAM_CHUNK;
+  const bool vec = ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) | reinterpret_cast<uintptr_t>(T.m) |
+                     reinterpret_cast<uintptr_t>(T.v)) & 15) == 0;
+  // The kernel is a latency chain (step counter -> bias corrections -> loads -> stores -> ticket -> counters) on a few
+  // dozen blocks, so the links overlap: every thread first requests its 4 x 4 float4 operands, then thread 0 reads the
+  // step counter and evaluates the bias corrections while they are in flight.
+  float4 p4[4], g4[4], m4[4], v4[4];
+  bool on[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = base + (static_cast<int64_t>(r) * ADAM_THREADS + threadIdx.x) * 4;
+    on[r] = vec && i + 4 <= T.n;
+    if (on[r]) {
+      p4[r] = *reinterpret_cast<const float4*>(T.p + i);
+      g4[r] = *reinterpret_cast<const float4*>(T.g + i);
+      m4[r] = *reinterpret_cast<const float4*>(T.m + i);
+      v4[r] = *reinterpret_cast<const float4*>(T.v + i);
+    }
+  }
   // bias corrections: one double-precision evaluation per block (a per-thread pow() dominated this small kernel)
   __shared__ float bc_s[2];
+  __shared__ int last_s;
   if (threadIdx.x == 0) {
+    const int t_now = *T.step + 1;
     bc_s[0] = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), t_now));
     bc_s[1] = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), t_now));
   }
@@ -44,9 +64,6 @@ __global__ void __launch_bounds__(ADAM_THREADS)
   const float step_size = T.lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const float wd = T.weight_decay, omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
-  const int64_t base = chunk * ADAM_CHUNK;
-  const bool vec = ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) | reinterpret_cast<uintptr_t>(T.m) |
-                     reinterpret_cast<uintptr_t>(T.v)) & 15) == 0;
   auto upd = [&](float& p, float g, float& m, float& v) {
     g = fmaf(wd, p, g);
     m = fmaf(omb1, g - m, m);
@@ -56,20 +73,15 @@ __global__ void __launch_bounds__(ADAM_THREADS)
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int64_t i = base + (static_cast<int64_t>(r) * ADAM_THREADS + threadIdx.x) * 4;
-    if (i >= T.n) break;
-    if (vec && i + 4 <= T.n) {
-      float4 p = *reinterpret_cast<float4*>(T.p + i);
-      const float4 g = *reinterpret_cast<const float4*>(T.g + i);
-      float4 m = *reinterpret_cast<float4*>(T.m + i);
-      float4 v = *reinterpret_cast<float4*>(T.v + i);
-      upd(p.x, g.x, m.x, v.x);
-      upd(p.y, g.y, m.y, v.y);
-      upd(p.z, g.z, m.z, v.z);
-      upd(p.w, g.w, m.w, v.w);
-      *reinterpret_cast<float4*>(T.p + i) = p;
-      *reinterpret_cast<float4*>(T.m + i) = m;
-      *reinterpret_cast<float4*>(T.v + i) = v;
-    } else {
+    if (on[r]) {
+      upd(p4[r].x, g4[r].x, m4[r].x, v4[r].x);
+      upd(p4[r].y, g4[r].y, m4[r].y, v4[r].y);
+      upd(p4[r].z, g4[r].z, m4[r].z, v4[r].z);
+      upd(p4[r].w, g4[r].w, m4[r].w, v4[r].w);
+      *reinterpret_cast<float4*>(T.p + i) = p4[r];
+      *reinterpret_cast<float4*>(T.m + i) = m4[r];
+      *reinterpret_cast<float4*>(T.v + i) = v4[r];
+    } else if (i < T.n) {
       for (int64_t j = i; j < min(i + 4, T.n); ++j) {
         float p = T.p[j], m = T.m[j], v = T.v[j];
         upd(p, T.g[j], m, v);
@@ -79,15 +91,16 @@ __global__ void __launch_bounds__(ADAM_THREADS)
       }
     }
   }
-  // the last block to finish advances the step counters (every block has read its own by then)
+  // the last block to finish advances the step counters (every block has read its own by then), one thread per counter
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int done = atomicAdd(ticket, 1u);
-    if (done == gridDim.x - 1) {
-      for (int i = 0; i < a.count; ++i) *a.t[i].step += 1;
-      *ticket = 0u;
-    }
+    last_s = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last_s) {
+    for (int i = threadIdx.x; i < a.count; i += ADAM_THREADS) *a.t[i].step += 1;
+    if (threadIdx.x == 0) *ticket = 0u;
   }
 }
 
