@@ -408,6 +408,8 @@ FORCE_ACTIVE_NODES = None         # None: by size; True / False: override (tests
 def _active_nodes_wanted(U: int) -> bool:
     if not STREAM_BWD_FUSED:
         return False
+    if torch.cuda.is_current_stream_capturing():
+        return False        # the node count is read back to size the launches: not possible inside a CUDA-graph capture
     if FORCE_ACTIVE_NODES is not None:
         return bool(FORCE_ACTIVE_NODES)
     return U >= ACTIVE_NODES_MIN
