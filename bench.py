@@ -218,6 +218,11 @@ def algorithmic_cost(name, key, w, lat):
     if name == "gngf_linear_bwd":
         M, N, Kd, has_dx = key
         return "tensor", 2.0 * M * N * Kd * (2 if has_dx else 1)
+    if name.startswith("gngf_hpd_small_"):
+        # fused small-lattice HPD (fp32 CUDA cores; GEMM-shaped work, so it is put against the tensor peak): the layer
+        # chain on U nodes, forward; the dX chain in the backward (its dW products are gngf_linear_bwd launches)
+        dims = [2, *w["hpd"], T]
+        return "tensor", 2.0 * U * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
     kd = w["hpd"][-1]
     # tensor-core kernels: EXECUTED FLOPs = 6 split-precision passes over the useful 2*M*N*K;
     # the useful figure is reported next to it (roofline.useful_tflops)
@@ -245,6 +250,9 @@ def algorithmic_cost(name, key, w, lat):
         "gngf_hpd_dlogits": U * (2 * T * 4 + K * 12) + L * T * 4,
         "gngf_lattice_colsum": S * 4 + U * T * 4 + L * T * 4,
         "gngf_sigmoid_bwd": P * 3 * 4 * 3,
+        # rgb + target read, d_rgb written; column sums read, their adjoint written
+        "gngf_loss_fwd_bwd": P * 3 * 12 + L * (K if w["topk_only"] else T) * 8,
+        "gngf_loss_parts": P * 3 * 12 + L * (K if w["topk_only"] else T) * 8,
         "gngf_hpd_first_layer_fwd_nodes": Ua * w["hpd"][0] * 4,
         "gngf_hpd_first_layer_bwd_nodes": Ua * w["hpd"][0] * 4,
         # P*L*4 bit sets on a U-bit map; the compaction reads the map three times and writes the ids
