@@ -114,6 +114,7 @@ SIGNATURES = {
     "gngf_mlp3_tc_bwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_peer_allreduce": (c_int, [_P, _P, c_int32, c_int32, _P, _P, c_int64, c_int64, c_int32, c_float, _P, _P]),
+    "gngf_peer_allreduce_set_timeout_ms": (c_int, [c_int64]),
     "gngf_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_float, c_float, c_float, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),

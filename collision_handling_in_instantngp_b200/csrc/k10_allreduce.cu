@@ -19,7 +19,11 @@
 namespace gngf {
 
 constexpr int AR_THREADS = 256;
-constexpr long long AR_TIMEOUT_CYCLES = 6000000000ll;   // ~3 s: a dead peer must not hang the GPU
+// A dead peer must not hang the GPU: a rank gives up waiting after this many clock cycles (default ~30 s; every rank
+// must reach the collective within the bound -- gngf_peer_allreduce_set_timeout_ms).  Giving up is FATAL for the
+// result: the error flag state[2] is raised (sticky) and the whole output of the call is NaN, so that neither stale
+// nor partial sums can pass for reduced gradients; the host side raises on either signal (dp.PeerAllReduce.check).
+static long long g_timeout_cycles = 60000000000ll;
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -47,7 +51,9 @@ __device__ __forceinline__ float ld_peer(const float* p) {
 __global__ void __launch_bounds__(AR_THREADS)
     peer_allreduce_kernel(float* const* __restrict__ stage_ptrs, uint32_t* const* __restrict__ signal_ptrs, int rank,
                           int world, const float* __restrict__ in, float* __restrict__ out, int64_t n, int64_t cap,
-                          float scale, uint32_t* __restrict__ state) {
+                          float scale, uint32_t* __restrict__ state, long long timeout_cycles) {
+  __shared__ int timed_out_s;
+  if (threadIdx.x == 0) timed_out_s = 0;
   const uint32_t epoch = state[0] + 1;
   const int64_t par_off = static_cast<int64_t>(epoch & 1u) * cap;
   float* mine = stage_ptrs[rank] + par_off;
@@ -69,13 +75,17 @@ __global__ void __launch_bounds__(AR_THREADS)
     const uint32_t* slot = signal_ptrs[rank] + static_cast<int64_t>(blockIdx.x) * world + tid;
     const long long t0 = clock64();
     while (static_cast<int32_t>(ld_acquire_sys(slot) - epoch) < 0) {
-      if (clock64() - t0 > AR_TIMEOUT_CYCLES) {
+      if (clock64() - t0 > timeout_cycles) {
         state[2] = 1u;
+        timed_out_s = 1;
         break;
       }
     }
   }
   __syncthreads();
+  // a peer that never arrived, now or in an earlier call (the flag is sticky): poison the output
+  const bool dead = timed_out_s || *reinterpret_cast<volatile uint32_t*>(state + 2) != 0u;
+  if (dead) scale = __int_as_float(0x7fc00000);
 
   for (int64_t i = lo + tid; i < hi; i += AR_THREADS) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -120,9 +130,16 @@ int gngf_peer_allreduce(const void* stage_ptrs_dev, const void* signal_ptrs_dev,
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, max_blocks)));
   gngf::peer_allreduce_kernel<<<grid, gngf::AR_THREADS, 0, gngf::as_stream(stream)>>>(
       reinterpret_cast<float* const*>(stage_ptrs_dev), reinterpret_cast<uint32_t* const*>(signal_ptrs_dev), rank, world, in,
-      out, n, cap_floats, scale, state);
+      out, n, cap_floats, scale, state, gngf::g_timeout_cycles);
   gngf::note_launch();
   return gngf::check_launch();
+}
+
+
+int gngf_peer_allreduce_set_timeout_ms(int64_t ms) {
+  if (ms < 1) return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::g_timeout_cycles = ms * 2000000ll;   // clock64 ticks at <= 2 GHz: the bound is at least `ms`
+  return GNGF_OK;
 }
 
 }  // extern "C"

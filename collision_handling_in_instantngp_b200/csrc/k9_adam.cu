@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(ADAM_THREADS)
   __shared__ float bc_s[2];
   __shared__ int last_s;
   if (threadIdx.x == 0) {
-    const int t_now = *T.step + 1;
+    const int t_now = static_cast<int>(*T.step) + 1;   // float32 scalar holding an integer (torch's state-dict dtype)
     bc_s[0] = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), t_now));
     bc_s[1] = 1.0f - static_cast<float>(pow(static_cast<double>(beta2), t_now));
   }
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(ADAM_THREADS)
   }
   __syncthreads();
   if (last_s) {
-    for (int i = threadIdx.x; i < a.count; i += ADAM_THREADS) *a.t[i].step += 1;
+    for (int i = threadIdx.x; i < a.count; i += ADAM_THREADS) *a.t[i].step += 1.0f;
     if (threadIdx.x == 0) *ticket = 0u;
   }
 }

@@ -66,6 +66,30 @@ class PeerAllReduce:
     def timed_out(self) -> bool:
         return bool(self.state[2].item())
 
+    def check(self) -> None:
+        """Raises when a peer failed to reach one of the exchanges within the timeout (k10_allreduce.cu: the flag is
+        sticky and the outputs of the affected and all later calls are NaN).  One device->host read."""
+        if self.timed_out():
+            from ._lib import GngfError
+            raise GngfError("PeerAllReduce: a rank did not reach the collective within the timeout; the reduced buffers "
+                            "are poisoned (NaN).  Every rank must reach each exchange within the bound "
+                            "(set_peer_timeout_ms) -- restart from the last checkpoint")
+
+
+def set_peer_timeout_ms(ms: int) -> None:
+    """How long a rank waits for its peers inside the one-shot all-reduce kernel before declaring the exchange dead
+    (default ~30 s).  Eager data-parallel loops that do long rank-local work between steps (checkpoints, host-side
+    diagnostics) should raise it."""
+    from . import _lib
+    _lib.call("gngf_peer_allreduce_set_timeout_ms", int(ms))
+
+
+def check_exchanges(group=None) -> None:
+    """Raises GngfError if any one-shot exchange of this process has timed out (cheap: 4 bytes read back)."""
+    for comm in _PEER.values():
+        if comm is not None:
+            comm.check()
+
 
 def peer_allreduce_for(group=None):
     """The process-wide PeerAllReduce of `group` (created collectively on first use), or None when symmetric memory

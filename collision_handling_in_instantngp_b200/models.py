@@ -70,7 +70,10 @@ class DifferentiableTopk(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_values: torch.Tensor, grad_indices: torch.Tensor):
         (indices,) = ctx.saved_tensors
-        # should_inplace_scatter (models.py:30-35) only selects between equivalent scatter variants
+        # should_inplace_scatter (models.py:30-35): True / False select between equivalent scatter variants; None calls
+        # the out-of-place scatter and DISCARDS its result (models.py:30-31), so grad_input stays all zeros
+        if current_flags().should_inplace_scatter is None:
+            return torch.zeros(ctx.in_shape, dtype=grad_values.dtype, device=grad_values.device).movedim(-1, ctx.dim), None, None
         grad_in = ops.topk_bwd(grad_values.movedim(ctx.dim, -1), indices, ctx.in_shape[-1])
         return grad_in.movedim(-1, ctx.dim), None, None
 
@@ -266,11 +269,25 @@ class GeneralNeuralGaugeFields(nn.Module):
         self._coord_bounds = None
         self._lattice_cache = {}
         self.last_state = None
+        # sticky device flag: a coordinate fell outside the bounds promised to set_coord_bounds() (the kernels clamp it
+        # to the lattice box); read by check_errors() -- every ERR_CHECK_EVERY-th eager forward, and by GraphedTrainer
+        self._err_flag_sticky = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._forwards = 0
 
     # ------------------------------------------------------------------------------------------------
     def set_coord_bounds(self, lo=(0.0, 0.0), hi=(1.0, 1.0)) -> None:
         """Promise that every coordinate passed to forward lies in [lo, hi] (per dimension)."""
         self._coord_bounds = None if lo is None else (tuple(float(v) for v in lo), tuple(float(v) for v in hi))
+
+    ERR_CHECK_EVERY = 64
+
+    def check_errors(self) -> None:
+        """Raises GngfError if any forward since the last call saw coordinates outside the fixed bounds (one 4-byte
+        device->host read; the flag is then cleared)."""
+        if int(self._err_flag_sticky.item()):
+            self._err_flag_sticky.zero_()
+            raise GngfError(f"coordinates outside the bounds given to set_coord_bounds{self._coord_bounds} were clamped to "
+                            "the lattice box: the affected forwards used the wrong lattice nodes")
 
     def _lattice_for(self, x: torch.Tensor):
         bounds = self._coord_bounds
@@ -291,7 +308,7 @@ class GeneralNeuralGaugeFields(nn.Module):
             table_size=self._hash_table_size, feature_dim=self._feature_dim, topk_k=self._topk_k,
             n_hpd=0 if use_hash else len(self.HPD.module_list), n_mlp=len(self.mlp),
             topk_only=self._should_keep_topk_only, mix_mode=ops.mix_mode_of(flags.should_softmax_topk_features),
-            leaky=self._leaky, use_hash=use_hash,
+            leaky=self._leaky, use_hash=use_hash, drop_topk_adjoint=flags.should_inplace_scatter is None,
             hpd_trainable=(not use_hash) and any(p.requires_grad for p in self.HPD.parameters()))
 
     def _parameters_flat(self):
@@ -315,6 +332,13 @@ class GeneralNeuralGaugeFields(nn.Module):
             raise GngfError(f"x must be (P, 2), got {tuple(x.shape)}")
         lat = self._lattice_for(x)
         state = ops.ForwardState(x=x, lat=lat, cfg=self._path_config(flags))
+        if self._coord_bounds is not None:
+            # fixed bounds: out-of-box coordinates raise the sticky flag (per-forward flag otherwise: bounds derived from
+            # the batch cannot be violated)
+            state.err_flag = self._err_flag_sticky
+            self._forwards += 1
+            if self._forwards % self.ERR_CHECK_EVERY == 0 and not torch.cuda.is_current_stream_capturing():
+                self.check_errors()
         params = self._parameters_flat()
         self.last_state = state
         if self._use_hash:

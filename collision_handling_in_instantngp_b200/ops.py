@@ -348,6 +348,9 @@ class PathConfig:
     leaky: bool = False            # params.should_leaky_relu
     use_hash: bool = False         # params.should_use_hash_function
     hpd_trainable: bool = True
+    drop_topk_adjoint: bool = False  # params.should_inplace_scatter is None: DifferentiableTopk.backward returns zeros
+                                     # (models.py:30-31 discards the scatter result) -> nothing reaches the HPD through
+                                     # the selected probabilities
 
 
 @dataclass
@@ -556,7 +559,9 @@ class GNGFPath(torch.autograd.Function):
             # (the column sums start on a 16-byte boundary: the peer all-reduce of dp.py moves them as float4)
             c0 = (2 * S + 1 + 3) & ~3
             zbuf = torch.zeros(c0 + L * N, dtype=torch.int32, device=dev)
-            state.cnt, cell_cnt, state.err_flag = zbuf[:S], zbuf[S:2 * S], zbuf[2 * S:2 * S + 1]
+            state.cnt, cell_cnt = zbuf[:S], zbuf[S:2 * S]
+            if state.err_flag is None:        # (a caller with fixed coordinate bounds passes its sticky flag instead)
+                state.err_flag = zbuf[2 * S:2 * S + 1]
             colsum = zbuf[c0:].view(torch.float32).view(L, N)
             call("gngf_encode_fwd", x.data_ptr(), P, lat, F, nfeat.data_ptr(), enc.data_ptr(), state.cnt.data_ptr(),
                  cell_cnt.data_ptr(), state.err_flag.data_ptr(), st)
@@ -685,7 +690,7 @@ class GNGFPath(torch.autograd.Function):
             state.colsum_fork.join()           # side stream up to here
             state.colsum_fork = None
         need_hpd = cfg.hpd_trainable
-        fuse_nodes = need_hpd and state.hpd_small and SMALL_FUSE_NODE_PASSES
+        fuse_nodes = need_hpd and state.hpd_small and SMALL_FUSE_NODE_PASSES and not cfg.drop_topk_adjoint
         if not fuse_nodes:
             call("gngf_node_features_bwd", lat, make_tables(tables), gtab, T, F, K, cfg.mix_mode, state.utopv.data_ptr(),
                  state.utopi.data_ptr(), dnf.data_ptr(), dtv.data_ptr() if need_hpd else None, st)
@@ -698,6 +703,12 @@ class GNGFPath(torch.autograd.Function):
 
         gcol = gcol_k = gdense = None
         dtv_extra = False            # dtv holds an adjoint of utopv that did not come from the node pass
+        if cfg.drop_topk_adjoint:
+            # reference semantics of should_inplace_scatter = None: every adjoint that would pass through the top-k values
+            # (the mix weights and, in top-k-only mode, the returned probabilities) is dropped
+            dtv.zero_()
+            if cfg.topk_only:
+                grad_colsum = grad_uvals = None
         if grad_colsum is not None:
             grad_colsum = _f32c(grad_colsum)
             if state.colsum_world > 1:

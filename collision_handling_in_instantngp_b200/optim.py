@@ -4,6 +4,11 @@ launch over all parameter tensors (k9_adam.cu), with the step counter on the dev
 in a CUDA graph.  Same constructor shape as ``torch.optim.Adam`` (parameter groups with ``lr`` and ``weight_decay``;
 ``betas``; ``eps``); ``amsgrad`` / ``maximize`` are not supported (the reference does not use them).
 
+The state dict is interchangeable with ``torch.optim.Adam``'s (the reference saves it as ``whole_opt.pt``,
+functions.py:768): per parameter ``exp_avg``, ``exp_avg_sq`` and ``step``, the latter a float32 scalar tensor as in torch.
+A state loaded from a stock Adam checkpoint (whose ``step`` lives on the CPU unless capturable / fused) is moved to the
+parameter's device on the first step; a FusedAdam checkpoint loads into ``torch.optim.Adam`` as is.
+
     opt = FusedAdam([{"params": net.encoding.parameters(), "lr": 1e-4, "weight_decay": 0.0},
                      {"params": net.HPD.parameters(), "lr": 1e-3, "weight_decay": 1e-6},
                      {"params": net.mlp.parameters(), "lr": 1e-3, "weight_decay": 1e-6}], betas=(0.9, 0.99), eps=1e-15)
@@ -55,7 +60,14 @@ class FusedAdam(torch.optim.Optimizer):
                 if not st:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["step"] = torch.zeros(1, dtype=torch.int32, device=p.device)   # advanced by the kernel
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)   # advanced by the kernel
+                else:
+                    t = st["step"]      # a state loaded from torch.optim.Adam: CPU float scalar (or a Python number)
+                    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.device == p.device):
+                        st["step"] = torch.as_tensor(float(t), dtype=torch.float32, device=p.device).reshape(())
+                    for key in ("exp_avg", "exp_avg_sq"):
+                        if st[key].device != p.device or st[key].dtype != torch.float32 or not st[key].is_contiguous():
+                            st[key] = st[key].to(device=p.device, dtype=torch.float32).contiguous()
                 dev = p.device
                 entries.append((p, g, st["exp_avg"], st["exp_avg_sq"], st["step"], float(group["lr"]),
                                 float(group["weight_decay"])))

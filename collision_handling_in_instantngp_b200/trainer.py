@@ -30,7 +30,17 @@ class GraphedTrainer:
     Two buffer sets / two graphs alternate so that the host-to-device copy of batch t+1 (on a copy stream) overlaps the
     replay of step t: `step_pipelined` never blocks the host, returns the loss of the PREVIOUS step as a host float
     (None on the first call) and `flush()` returns the last one.  `step` is the blocking form (copy, replay; the
-    caller reads the returned device tensor)."""
+    caller reads the returned device tensor).
+
+    Warm-up: the constructor runs `warmup_steps` real steps (first-use allocations, lazy library loads) before the capture.
+    They are side-effect free: parameters, buffers and the optimizer state (moments and step counters) are snapshotted
+    before them and restored afterwards -- into the same storages, so the captured pointers stay valid -- which keeps
+    the first user step identical to the reference loop's first step and resumed runs' bias corrections intact.
+
+    Errors raised on the device -- a coordinate outside the bounds promised to `net.set_coord_bounds`, a data-parallel
+    peer that never reached an exchange -- are read back next to the loss and raise GngfError from
+    `step_pipelined` / `flush` (flags every `check_every` steps, and at once when a loss comes back NaN); `step` / `replay`
+    users call `check_errors()` at their own cadence."""
 
     def __init__(self, net, optimizer, points: int, gamma: float, epsilon: float, l_mse: float = 1.0,
                  l_js_kl: float = 1.0, channels: int = 3, warmup_steps: int = 3, sample_x=None, sample_y=None,
@@ -62,6 +72,10 @@ class GraphedTrainer:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.done = [None] * n_sets            # event: the last replay that read buffer set i has finished
         self.loss_host = [torch.zeros(1).pin_memory() for _ in range(n_sets)]
+        self.status_host = [torch.zeros(2, dtype=torch.int32).pin_memory() for _ in range(n_sets)]
+        self._status_pending = [False] * n_sets
+        self.check_every = 32                  # steps between read-backs of the device error flags (step_pipelined)
+        self._nsteps = 0
         self.loss_ready = [None] * n_sets      # event: loss_host[i] holds the loss of the last replay of set i
         self._pending = None                   # buffer set whose loss has not been returned yet
         self._capture(warmup_steps)
@@ -106,13 +120,39 @@ class GraphedTrainer:
         self.opt.step()
         return out[0]
 
+    def _snapshot(self):
+        model = {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+        opt = {p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+               for p, st in self.opt.state.items()}
+        return model, opt
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        model, opt = snap
+        for k, v in self.net.state_dict().items():
+            v.copy_(model[k])
+        for p, st in self.opt.state.items():
+            old = opt.get(p)
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    if old is not None and k in old:
+                        v.copy_(old[k])
+                    else:
+                        v.zero_()           # state created by the warm-up: moments and step counter start from zero
+                elif old is not None and k in old:
+                    st[k] = old[k]
+        self.net._err_flag_sticky.zero_()
+
     def _capture(self, warmup_steps):
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup_steps)):
                 self._eager_step(0)
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._restore(snap)
         torch.cuda.synchronize()
         for i in range(len(self.graphs)):
             if self.world > 1:
@@ -157,6 +197,10 @@ class GraphedTrainer:
         self.done[i] = torch.cuda.Event()
         self.done[i].record(main)
         self.loss_host[i].copy_(self.losses[i].reshape(1), non_blocking=True)
+        if self._nsteps % self.check_every == 0:       # device error flags: 3 tiny copies, amortised over check_every steps
+            self.status_host[i].copy_(self._status_dev(), non_blocking=True)
+            self._status_pending[i] = True
+        self._nsteps += 1
         self.loss_ready[i] = torch.cuda.Event()
         self.loss_ready[i].record(main)
         prev = self._take_pending()
@@ -170,7 +214,40 @@ class GraphedTrainer:
         j = self._pending
         self.loss_ready[j].synchronize()
         self._pending = None
-        return float(self.loss_host[j])
+        if self._status_pending[j]:
+            self._status_pending[j] = False
+            self._raise_on(self.status_host[j])
+        loss = float(self.loss_host[j])
+        if loss != loss:                # NaN: a poisoned exchange shows up here one step later -- find out why now
+            self.check_errors()
+        return loss
+
+    def _status_dev(self) -> torch.Tensor:
+        """(2,) int32 view: [coordinate out of bounds, peer exchange timed out] -- one persistent device buffer."""
+        if getattr(self, "_status", None) is None:
+            comm = dp.peer_allreduce_for() if self.world > 1 else None
+            # the two flags live in different allocations; a tiny gather kernel-free way: keep both and copy the 4 bytes
+            # of each into one staging tensor with two async device-to-device copies inside this call
+            self._status = torch.zeros(2, dtype=torch.int32, device=self.dev)
+            self._status_src = (self.net._err_flag_sticky, None if comm is None else comm.state[2:3])
+        self._status[0:1].copy_(self._status_src[0], non_blocking=True)
+        if self._status_src[1] is not None:
+            self._status[1:2].copy_(self._status_src[1], non_blocking=True)
+        return self._status
+
+    def _raise_on(self, status) -> None:
+        oob, dead = int(status[0]), int(status[1])
+        if oob:
+            raise GngfError("a batch contained coordinates outside the bounds given to net.set_coord_bounds(): they were "
+                            "clamped to the lattice box and the step trained on the wrong nodes")
+        if dead:
+            raise GngfError("a data-parallel peer did not reach an exchange within the timeout: the reduced gradients of "
+                            "that step (and every later one) are NaN; restart from the last checkpoint")
+
+    def check_errors(self) -> None:
+        """Blocking form of the device-error check for `step` / `replay` users."""
+        st = self._status_dev().cpu()
+        self._raise_on(st)
 
     def flush(self):
         """Waits for the last pipelined step; returns its loss (host float) or None."""

@@ -339,7 +339,8 @@ int gngf_count_distinct_i64(const int64_t* indices, int64_t P, int32_t L, int32_
  * One launch: for every tensor  g' = g + weight_decay p;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
  *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)   with t = *step + 1  (torch.optim.Adam semantics,
  * amsgrad off).  `tensors` is a HOST array (copied into kernel-parameter space); p/g/m/v/step are device pointers;
- * every tensor has its own `step` (device int32, distinct addresses), advanced by the kernel; `ticket` (device
+ * every tensor has its own `step` (device float32 scalar holding an integer value, as in torch.optim.Adam's
+ * state dict; distinct addresses), advanced by the kernel; `ticket` (device
  * uint32, zero-initialised) is scratch.                                                                             */
 #define GNGF_ADAM_MAX_TENSORS 64
 typedef struct gngf_adam_tensor {
@@ -347,7 +348,7 @@ typedef struct gngf_adam_tensor {
   const float* g;
   float* m;
   float* v;
-  int32_t* step;
+  float* step;
   int64_t n;
   float lr;
   float weight_decay;
@@ -359,12 +360,16 @@ int gngf_adam_step(const gngf_adam_tensor* tensors, int32_t count, float beta1, 
  * out (n) = scale * sum over ranks of in (n), identical bits on every rank (fixed summation order).
  * stage_ptrs_dev / signal_ptrs_dev: DEVICE arrays of `world` peer-mapped pointers (symmetric memory): staging buffers
  *   of 2 * cap_floats floats each, and zero-initialised signal pads of at least max_blocks * world uint32 each.
- * state: 3 device uint32 (epoch, ticket, error), zero-initialised, owned by this communicator; state[2] != 0 after a
- *   call means a peer did not arrive within ~3 s.  Every rank must call with the same n and max_blocks, in the same
- *   order.  in / out 16-byte aligned; out may alias in.  Asynchronous on `stream`, CUDA-graph capturable.          */
+ * state: 3 device uint32 (epoch, ticket, error), zero-initialised, owned by this communicator.  Every rank must call
+ *   with the same n and max_blocks, in the same order, and reach the call within the timeout (default ~30 s,
+ *   gngf_peer_allreduce_set_timeout_ms).  A peer that does not arrive is FATAL for the result: state[2] becomes 1 and
+ *   stays 1, and the output of that call and of every later call is NaN -- never stale or partial sums.
+ *   in / out 16-byte aligned; out may alias in.  Asynchronous on `stream`, CUDA-graph capturable.                  */
 int gngf_peer_allreduce(const void* stage_ptrs_dev, const void* signal_ptrs_dev, int32_t rank, int32_t world,
                         const float* in, float* out, int64_t n, int64_t cap_floats, int32_t max_blocks, float scale,
                         uint32_t* state, void* stream);
+/* Host-side setting, applies to launches made after it (process-wide). */
+int gngf_peer_allreduce_set_timeout_ms(int64_t ms);
 
 #ifdef __cplusplus
 }

@@ -252,6 +252,27 @@ def calc_hash_collisions_hash_mode(indices: np.ndarray, n_ls: np.ndarray, table_
 
 
 # --------------------------------------------------------------------------------------------------------
+# f-4  _calc_counts_per_level                                                          models.py:530-566
+# --------------------------------------------------------------------------------------------------------
+def calc_counts_per_level(hashed: np.ndarray, grid: np.ndarray):
+    """hashed (P,L,4) slot per (point, level, corner) [the best top-k column, or the hash]; grid (P,2,L,4) corners.
+    Per level the rows "p (v xy)" (the 8 corner coordinates of a point's cell) are de-duplicated with
+    np.unique(axis=0, return_index=True): `first[j]` is the index of the first POINT (batch order) in distinct cell j.
+    The reference then uses these point indices to index the FLATTENED "(p v)" slot vector (models.py:556-558), so the
+    slot it counts for cell j is that of corner (first[j] % 4) of point (first[j] // 4) -- restated as is.
+    Returns a list (per level) of {slot: number of distinct cells counted for it}."""
+    from collections import Counter
+    P, _, L, _ = grid.shape
+    rows = np.transpose(grid, (2, 0, 3, 1)).reshape(L, P, -1)          # "p xy l v -> l p (v xy)"
+    flat = np.transpose(hashed, (1, 0, 2)).reshape(L, -1)             # "p l v -> l (p v)"
+    out = []
+    for l in range(L):
+        _, first = np.unique(rows[l], axis=0, return_index=True)
+        out.append(dict(Counter(flat[l][first].tolist())))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
 # whole path: forward                                                                models.py:394-484
 # --------------------------------------------------------------------------------------------------------
 def gngf_forward(params: dict, x: np.ndarray, cfg: dict) -> dict:
@@ -365,6 +386,10 @@ def gngf_backward(params: dict, x: np.ndarray, target: np.ndarray, cfg: dict, fw
         G = np.zeros_like(probs)
     else:
         G = np.broadcast_to(dpbar[None, :, None, :], probs.shape).copy()
+    if cfg.get("drop_topk_adjoint", False):
+        # params.should_inplace_scatter is None (models.py:30-31): the scatter result is discarded, so the adjoint of
+        # the selected values never reaches `probs`
+        dtv = np.zeros_like(dtv)
     np.put_along_axis(G, idx, np.take_along_axis(G, idx, -1) + dtv, axis=-1)     # DifferentiableTopk.backward
     dlogit = probs * (G - (G * probs).sum(-1, keepdims=True))
     grads["dlogit"] = dlogit

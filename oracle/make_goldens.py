@@ -27,7 +27,7 @@ SEED = 2 ** 16 - 1
 BASE = dict(T=256, L=4, n_min=8, n_max=32, F=2, K=4, hpd=[32, 64, 128], mlp=[64, 64], P=333,
             topk_only=False, mix_mode=True, use_hash=False, leaky=False, bw=False,
             gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0, l_collisions=1e-3, with_collisions=False,
-            coords="image")
+            coords="image", inplace=True, counts=False)
 
 CASES = {
     # grid-search ID 4061 (README.md:15-18): the published best parameters
@@ -44,6 +44,13 @@ CASES = {
     "l8_t4096_topk_only": dict(L=8, n_min=16, n_max=339, T=4096, P=48, topk_only=True, coords="uniform"),
     "js_only": dict(gamma=-1.0, epsilon=0.0, P=64),     # should_sum_js_kl_div False, should_js_div True
     "kl_only": dict(gamma=-1.0, epsilon=1.0, P=64),     # should_sum_js_kl_div False, should_js_div False
+    # params.should_inplace_scatter = None: DifferentiableTopk.backward discards its scatter (models.py:30-31)
+    "scatter_none": dict(inplace=None, P=128),
+    "scatter_none_topk_only": dict(inplace=None, topk_only=True, P=128),
+    # should_calc_counts=True: the per-level histograms of _calc_counts_per_level (models.py:530-566)
+    "counts": dict(counts=True, P=333),
+    "counts_hash": dict(counts=True, use_hash=True, P=257),
+    "counts_l16": dict(counts=True, L=16, n_min=16, n_max=508, T=1024, P=200, coords="uniform"),
 }
 
 
@@ -65,6 +72,7 @@ def run_case(ref, name, over):
     ref_shim.set_flag(ref, "should_use_hash_function", c["use_hash"])
     ref_shim.set_flag(ref, "should_softmax_topk_features", c["mix_mode"])
     ref_shim.set_flag(ref, "should_leaky_relu", c["leaky"])
+    ref_shim.set_flag(ref, "should_inplace_scatter", c["inplace"])
     torch.manual_seed(SEED)
     net = ref.models.GeneralNeuralGaugeFields(
         input_dim=2, hash_table_size=c["T"], num_levels=c["L"], n_min=c["n_min"], n_max=c["n_max"],
@@ -94,7 +102,7 @@ def run_case(ref, name, over):
     else:
         coll, minp = torch.tensor([]), torch.tensor([])
 
-    rgb, probs, idx, _ = net(x, 1.0)
+    rgb, probs, idx, counts = net(x, 1.0, should_calc_counts=c["counts"])
     if c["use_hash"]:
         mse, kl, coll_l = loss_fn(rgb, y, None, None, None, None)
         loss = c["l_mse"] * mse
@@ -131,6 +139,12 @@ def run_case(ref, name, over):
         out.update(feat=feat, enc=enc)
         coll_k, minp_k = net.calc_hash_collisions(idx)
         out.update(chc_collisions=coll_k, chc_min_possible=minp_k)
+    if c["counts"]:                    # list (per level) of {slot: number of distinct grid corners hashed to it}
+        assert len(counts) == c["L"]
+        for l, d in enumerate(counts):
+            keys = np.array(sorted(d), dtype=np.int64)
+            out[f"counts_keys_{l}"] = keys
+            out[f"counts_vals_{l}"] = np.array([d[k] for k in keys], dtype=np.int64)
     for k, v in net.state_dict().items():
         if k.startswith("_batch_norm"):
             continue

@@ -7,8 +7,10 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 GNGF_CASES = ["cfg2_small", "cfg2_topk_only", "cfg2_epoch1", "mix_weighted_avg", "mix_raw", "k1", "k20",
-              "bw_leaky", "l16_t1024", "l8_t4096_topk_only", "js_only", "kl_only"]
-ALL_CASES = GNGF_CASES + ["hash_mode"]
+              "bw_leaky", "l16_t1024", "l8_t4096_topk_only", "js_only", "kl_only", "scatter_none",
+              "scatter_none_topk_only", "counts", "counts_l16"]
+ALL_CASES = GNGF_CASES + ["hash_mode", "counts_hash"]
+COUNTS_CASES = ["counts", "counts_hash", "counts_l16"]
 
 
 def load(name):
@@ -35,7 +37,13 @@ def params_of(g, dtype=np.float32):
 def oracle_cfg(g):
     c = g["cfg"]
     return {"n_ls": g["n_ls"].astype(np.int32), "table_size": c["T"], "topk_k": c["K"], "mix_mode": c["mix_mode"],
-            "use_hash": c["use_hash"], "leaky": c["leaky"], "topk_only": c["topk_only"]}
+            "use_hash": c["use_hash"], "leaky": c["leaky"], "topk_only": c["topk_only"],
+            "drop_topk_adjoint": c.get("inplace", True) is None}
+
+
+def golden_counts(g):
+    """The reference's counts_per_level (list per level of {slot: count}) as stored by make_goldens.py."""
+    return [dict(zip(g[f"counts_keys_{l}"].tolist(), g[f"counts_vals_{l}"].tolist())) for l in range(g["cfg"]["L"])]
 
 
 def loss_cfg(g):

@@ -12,6 +12,7 @@ def build_net(g, **over):
     M.DEFAULT_FLAGS.should_use_hash_function = c["use_hash"]
     M.DEFAULT_FLAGS.should_softmax_topk_features = c["mix_mode"]
     M.DEFAULT_FLAGS.should_leaky_relu = c["leaky"]
+    M.DEFAULT_FLAGS.should_inplace_scatter = c.get("inplace", True)
     net = M.GeneralNeuralGaugeFields(
         input_dim=2, hash_table_size=c["T"], num_levels=c["L"], n_min=c["n_min"], n_max=c["n_max"],
         MLP_hidden_layers_widths=c["mlp"], HPD_hidden_layers_widths=c["hpd"], HPD_out_features=c["T"],
@@ -25,6 +26,7 @@ def reset_flags():
     M.DEFAULT_FLAGS.should_use_hash_function = False
     M.DEFAULT_FLAGS.should_softmax_topk_features = True
     M.DEFAULT_FLAGS.should_leaky_relu = False
+    M.DEFAULT_FLAGS.should_inplace_scatter = True
 
 
 def load_golden_into(net, g):

@@ -460,6 +460,26 @@ def test_fused_adam_matches_torch_adam():
         for a, b in zip(pa, pb):
             assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
     assert ob.step_count(pb[0]) == 12 and ob.step_count(pb[7]) == 11
+    # state dicts are interchangeable with torch.optim.Adam's (the reference saves whole_opt.pt, functions.py:768):
+    # continue the FusedAdam run in a stock Adam and vice versa, then take one more step in each
+    pc, oc = make(torch.optim.Adam)
+    pd, od = make(FusedAdam)
+    oc.load_state_dict(ob.state_dict())
+    od.load_state_dict(oa.state_dict())
+    for src, dst in ((pb, pc), (pa, pd)):
+        for a, b in zip(src, dst):
+            b.data.copy_(a.data)
+    for a, b, c_, d in zip(pa, pb, pc, pd):
+        g = torch.from_numpy(rng.standard_normal(a.shape).astype(np.float32)).to(DEV)
+        a.grad, b.grad, c_.grad, d.grad = g, g.clone(), g.clone(), g.clone()
+    for o in (oa, ob, oc, od):
+        o.step()
+    for a, b, c_, d in zip(pa, pb, pc, pd):
+        assert rel_err(c_.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
+        assert rel_err(d.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
+    assert od.step_count(pd[0]) == 13 and od.step_count(pd[7]) == 12
+    sd = ob.state_dict()["state"][0]
+    assert sd["step"].dtype == torch.float32 and sd["step"].dim() == 0
     # more tensors than one launch carries (64): several launches, same result
     many_a = [torch.nn.Parameter(torch.full((5,), float(i), device=DEV)) for i in range(70)]
     many_b = [torch.nn.Parameter(p.detach().clone()) for p in many_a]

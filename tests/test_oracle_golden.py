@@ -9,7 +9,8 @@ import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
 import gngf_oracle as O  # noqa: E402
-from golden_util import ALL_CASES, GNGF_CASES, GOLDEN_DIR, load, loss_cfg, oracle_cfg, params_of, rel_err  # noqa: E402
+from golden_util import (ALL_CASES, COUNTS_CASES, GNGF_CASES, GOLDEN_DIR, golden_counts, load, loss_cfg, oracle_cfg,  # noqa: E402
+                         params_of, rel_err)
 
 FWD_TOL = 1e-5
 GRAD_TOL = 1e-4
@@ -114,6 +115,16 @@ def test_calc_hash_collisions_matches_reference(name):
         coll, minp = O.calc_hash_collisions(g["idx"].astype(np.float32), g["n_ls"], g["cfg"]["T"])
     np.testing.assert_allclose(coll, g["chc_collisions"], rtol=0, atol=0)
     np.testing.assert_array_equal(minp, g["chc_min_possible"])
+
+
+@pytest.mark.parametrize("name", COUNTS_CASES)
+def test_calc_counts_per_level_matches_reference(name):
+    """f-4: _calc_counts_per_level (models.py:530-566) incl. its (point index -> flattened (p v) slot) indexing."""
+    g = load(name)
+    _, grid = O.scale_to_grid(g["x"], g["n_ls"])
+    hashed = g["idx"] if g["cfg"]["use_hash"] else g["idx"][..., 0]
+    got = O.calc_counts_per_level(hashed, grid)
+    assert got == golden_counts(g)
 
 
 @pytest.mark.parametrize("name", ["cfg2_small", "cfg2_topk_only", "l16_t1024", "k20"])

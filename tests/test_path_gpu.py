@@ -370,15 +370,14 @@ def test_graphed_trainer_matches_eager_steps():
         net_g.set_coord_bounds((0.0, 0.0), (1.0, 1.0))
         opt_g = groups(net_g, FusedAdam)
         init = {k: v.detach().clone() for k, v in net_g.state_dict().items()}
+        # warm-up on random coordinates / zero targets (no sample batch): the constructor must leave the parameters, the
+        # buffers and the optimizer state (moments, step counters) exactly as it found them
         tr = GraphedTrainer(net_g, opt_g, points=P, gamma=c["gamma"], epsilon=c["epsilon"], l_mse=c["l_mse"],
-                            l_js_kl=c["l_js_kl"], warmup_steps=1, sample_x=batches[0][0].cuda(),
-                            sample_y=batches[0][1].cuda())
-        # capture ran warm-up + captured steps: restore parameters and optimizer state
-        net_g.load_state_dict(init)
+                            l_js_kl=c["l_js_kl"], warmup_steps=2)
+        for k, v in net_g.state_dict().items():
+            assert torch.equal(v, init[k]), k
         for st in opt_g.state.values():
-            st["exp_avg"].zero_()
-            st["exp_avg_sq"].zero_()
-            st["step"].zero_()
+            assert float(st["step"]) == 0.0 and not st["exp_avg"].any() and not st["exp_avg_sq"].any()
         losses_g = []
         if mode == "blocking":
             for x, y in batches:
@@ -393,6 +392,35 @@ def test_graphed_trainer_matches_eager_steps():
         for (k, a), (_, b) in zip(net_g.state_dict().items(), net_e.state_dict().items()):
             if a.dtype.is_floating_point:
                 assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-4, (mode, k)
+
+
+def test_graphed_trainer_raises_on_out_of_bounds_coordinates():
+    """A batch that violates the bounds promised to set_coord_bounds is clamped by the kernels; the sticky device flag
+    must surface as GngfError from the trainer (and from net.check_errors() in eager use)."""
+    from collision_handling_in_instantngp_b200 import GngfError
+    from collision_handling_in_instantngp_b200.optim import FusedAdam
+    from collision_handling_in_instantngp_b200.trainer import GraphedTrainer
+    g = load("cfg2_small")
+    c = g["cfg"]
+    P = g["x"].shape[0]
+    net = build_net(g)
+    net.set_coord_bounds((0.0, 0.0), (0.5, 0.5))
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    net(x, 1.0)
+    with pytest.raises(GngfError):
+        net.check_errors()
+    net.check_errors()                       # cleared by the raise
+    opt = FusedAdam(net.parameters(), lr=1e-3)
+    tr = GraphedTrainer(net, opt, points=P, gamma=c["gamma"], epsilon=c["epsilon"], warmup_steps=1)
+    tr.check_errors()                        # the in-bounds warm-up batches left no flag behind
+    tr.step(x, y)
+    with pytest.raises(GngfError):
+        tr.check_errors()
+    net._err_flag_sticky.zero_()
+    tr.check_every = 1
+    tr.step_pipelined(x.cpu().pin_memory(), y.cpu().pin_memory())
+    with pytest.raises(GngfError):
+        tr.flush()
 
 
 def test_side_stream_forks_do_not_change_results():
