@@ -81,6 +81,8 @@ SIGNATURES = {
     "gngf_lattice_mark_nodes": (c_int, [_P, c_int64, Lattice, _P, _P]),
     "gngf_compact_nodes": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P]),
     "gngf_scatter_node_rows": (c_int, [_P, c_int64, _P, c_int64, _P, _P]),
+    "gngf_bitmap_or": (c_int, [_P, c_int32, c_int64, _P, _P]),
+    "gngf_gather_node_adjoints": (c_int, [Lattice, _P, c_int64, c_int32, _P, _P, _P, _P, _P]),
     "gngf_split_bf16x3": (c_int, [_P, c_int64, _P, _P]),
     "gngf_split_bf16x3_t": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
     "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P]),

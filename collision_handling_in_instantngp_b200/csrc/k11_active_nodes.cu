@@ -141,9 +141,76 @@ __global__ void __launch_bounds__(256) scatter_node_rows_kernel(const int* __res
   dst[static_cast<int64_t>(node_ids[r]) * N + c] = src[i];
 }
 
+// Node-parallel HPD (dp.NodeSharding): every rank marks the nodes ITS points touch; the union over ranks is the list all
+// ranks agree on.  out[w] = OR_r maps[r * W + w]   (maps: the all-gathered per-rank bitmaps, 16 bytes per thread).
+__global__ void __launch_bounds__(256) bitmap_or_kernel(const uint4* __restrict__ maps, int n_maps, int64_t W4,
+                                                        uint4* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= W4) return;
+  uint4 acc = maps[i];
+  for (int r = 1; r < n_maps; ++r) {
+    const uint4 v = maps[static_cast<int64_t>(r) * W4 + i];
+    acc.x |= v.x;
+    acc.y |= v.y;
+    acc.z |= v.z;
+    acc.w |= v.w;
+  }
+  out[i] = acc;
+}
+
+// Node-parallel HPD, backward: this rank's share of the adjoint of the selected probabilities, per row of the agreed
+// node list:  out[r,k] = dtv[node_ids[r],k] + sum_l cnt[s(l, node)] gcol_k[l,k]   (the column-sum adjoint folded in:
+// it is linear in this rank's multiplicities).  The rows are then summed over ranks and scattered to their owners
+// (reduce-scatter); the owner's streaming backward takes them row-indexed.
+__global__ void __launch_bounds__(256)
+    gather_node_adjoints_kernel(const __grid_constant__ gngf_lattice lat, const int* __restrict__ node_ids, int64_t n, int K,
+                                const float* __restrict__ dtv, const int* __restrict__ cnt,
+                                const float* __restrict__ gcol_k, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n * K) return;
+  const int64_t r = i / K;
+  const int k = static_cast<int>(i - r * K);
+  const int64_t un = node_ids ? node_ids[r] : r;
+  float g = dtv[un * K + k];
+  if (gcol_k) {
+    const int cx = lat.ox + static_cast<int>(un / lat.wy), cy = lat.oy + static_cast<int>(un % lat.wy);
+    for (int l = 0; l < lat.num_levels; ++l) {
+      const int a = cx - lat.lox[l], b = cy - lat.loy[l];
+      if (a >= 0 && a < lat.lwx[l] && b >= 0 && b < lat.lwy[l]) {
+        const float c = static_cast<float>(cnt[lat.loff[l] + static_cast<int64_t>(a) * lat.lwy[l] + b]);
+        g = fmaf(c, gcol_k[l * K + k], g);
+      }
+    }
+  }
+  out[i] = g;
+}
+
 }  // namespace gngf
 
 extern "C" {
+
+int gngf_bitmap_or(const uint32_t* maps, int32_t n_maps, int64_t words, uint32_t* out, void* stream) {
+  if (n_maps < 1 || words < 0 || (words & 3) || !maps || !out) return GNGF_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(maps) | reinterpret_cast<uintptr_t>(out)) & 15) return GNGF_ERR_INVALID_ARGUMENT;
+  if (words == 0) return GNGF_OK;
+  const int64_t W4 = words / 4;
+  gngf::bitmap_or_kernel<<<static_cast<unsigned>(gngf::ceil_div(W4, 256)), 256, 0, gngf::as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(maps), n_maps, W4, reinterpret_cast<uint4*>(out));
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
+int gngf_gather_node_adjoints(gngf_lattice lat, const int32_t* node_ids, int64_t n_nodes, int32_t K, const float* dtv,
+                              const int32_t* cnt, const float* gcol_k, float* out, void* stream) {
+  if (n_nodes < 0 || K <= 0 || K > GNGF_MAX_TOPK || lat.num_levels <= 0 || lat.num_levels > GNGF_MAX_LEVELS)
+    return GNGF_ERR_INVALID_ARGUMENT;
+  if (n_nodes == 0) return GNGF_OK;
+  if (!dtv || !out || (gcol_k && !cnt)) return GNGF_ERR_INVALID_ARGUMENT;
+  gngf::gather_node_adjoints_kernel<<<static_cast<unsigned>(gngf::ceil_div(n_nodes * K, 256)), 256, 0,
+                                      gngf::as_stream(stream)>>>(lat, node_ids, n_nodes, K, dtv, cnt, gcol_k, out);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
 
 int64_t gngf_active_nodes_bitmap_words(int64_t U) { return U <= 0 ? 0 : (U + 31) / 32; }
 int64_t gngf_active_nodes_chunks(int64_t U) {

@@ -482,8 +482,8 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
   using namespace gngf::tc::sb;
   const int64_t box = static_cast<int64_t>(lat.wx) * lat.wy;
   if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > 2 * BK || topk <= 0 || topk > GNGF_MAX_TOPK ||
-      U >= (1ll << 31) || T >= (1ll << 31) || (node_ids ? U > box : U != box))
-    return GNGF_ERR_UNSUPPORTED;
+      U >= (1ll << 31) || T >= (1ll << 31) || (node_ids ? U > box : (gcol_k != nullptr && U != box)))
+    return GNGF_ERR_UNSUPPORTED;   // (no node list and no column-sum adjoint: plain rows, dtv indexed by the row)
   if (gcol_k && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
   if (!h_planes || !w_planes || !h || !w || !bias || !utopv || !utopi || !dtv || !row_max || !row_sum || !dh || !dw ||
       !workspace)

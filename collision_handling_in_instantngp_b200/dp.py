@@ -193,7 +193,74 @@ class GradientAllReducer:
                 p.grad.copy_(v)
 
 
-def enable_gradient_allreduce(group=None) -> None:
+class NodeSharding:
+    """Node parallelism for the HPD (last sentence).  Pixel shards alone leave the dominant cost of a
+    large configuration replicated: the HPD runs once per lattice NODE, and the nodes a rank's pixels touch overlap
+    heavily with its peers' (configs[2]: every rank evaluates all 173 400 nodes whatever its share of the image;
+    configs[3]: 2^22 points touch 30 M of the 67 M nodes, an eighth of them still 6 M).  With this helper installed
+    (`enable_gradient_allreduce(shard_nodes=True)`, the default) the streaming HPD path instead
+
+      forward   marks the nodes its own points touch, all-gathers the per-rank bitmaps and ORs them (k11: gngf_bitmap_or)
+                -> every rank derives the same ascending node list; rank r evaluates rows [r*chunk, (r+1)*chunk) of it
+                (layers, bf16 planes, streaming softmax / top-k) and the per-node selections (K values + K indices) are
+                all-gathered -- 32 bytes per node for K = 4;
+      backward  each rank gathers ITS share of the adjoint of the selected probabilities per listed node, the column-sum
+                adjoint folded in (k11: gngf_gather_node_adjoints), a sum-reduce-scatter hands every row to its owner,
+                the owner runs the streaming backward and the layer gradients on its rows, and the (partial) HPD
+                parameter gradients join the flat gradient all-reduce that already averages tables and decoder.
+
+    No other exchange is added: the column sums and the parameter gradients move as before.  Works on any backend
+    (NCCL on the GPUs, gloo in the tests)."""
+
+    ROW_ALIGN = 128          # rows per rank are a multiple of the tensor-core row tile (the last owner takes the rest)
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def chunk_rows(self, total: int) -> int:
+        per = -(-int(total) // self.world)
+        return max(self.ROW_ALIGN, -(-per // self.ROW_ALIGN) * self.ROW_ALIGN)
+
+    def bounds(self, total: int):
+        """(first row, one past the last row, rows per rank) of this rank's share of `total` listed nodes."""
+        chunk = self.chunk_rows(total)
+        r0 = min(int(total), self.rank * chunk)
+        return r0, min(int(total), r0 + chunk), chunk
+
+    def union_bitmap(self, bitmap: torch.Tensor) -> torch.Tensor:
+        """OR over ranks of an int32 bitmap (word count a multiple of 4)."""
+        words = bitmap.numel()
+        maps = torch.empty(self.world * words, dtype=bitmap.dtype, device=bitmap.device)
+        dist.all_gather_into_tensor(maps, bitmap.contiguous().reshape(-1), group=self.group)
+        if not bitmap.is_cuda:
+            maps = maps.reshape(self.world, words)
+            out = maps[0].clone()
+            for r in range(1, self.world):
+                out |= maps[r]
+            return out.reshape(bitmap.shape)
+        from . import _lib
+        out = torch.empty_like(bitmap)
+        _lib.call("gngf_bitmap_or", maps.data_ptr(), self.world, bitmap.numel(), out.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+        return out
+
+    def all_gather_rows(self, local: torch.Tensor, total: int) -> torch.Tensor:
+        """local: (chunk, C) whose first (r1 - r0) rows are this rank's -> (total, C): all ranks' rows in list order."""
+        out = torch.empty((self.world * local.shape[0], *local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out[:total]
+
+    def reduce_scatter_rows(self, padded: torch.Tensor) -> torch.Tensor:
+        """padded: (world * chunk, C), rows past the list zero -> (chunk, C): the sum over ranks of this rank's rows."""
+        chunk = padded.shape[0] // self.world
+        out = torch.empty((chunk, *padded.shape[1:]), dtype=padded.dtype, device=padded.device)
+        dist.reduce_scatter_tensor(out, padded.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+
+def enable_gradient_allreduce(group=None, shard_nodes: bool = True) -> None:
     """Installs both data-parallel exchanges inside GNGFPath: (1) the parameter gradients are averaged over ranks at
     the end of the backward -- all of them are views of one flat buffer there, so it is a single in-place all-reduce
     and no flatten / unflatten copies (vs. GradientAllReducer, which works on arbitrary parameter lists); (2) the
@@ -204,8 +271,11 @@ def enable_gradient_allreduce(group=None) -> None:
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         ops.GRAD_REDUCE_HOOK = None
         ops.COLSUM_REDUCE_HOOK = None
+        ops.NODE_SHARD = None
         return
     world = dist.get_world_size(group)
+    # (3) node parallelism of the streaming HPD path (NodeSharding): large lattices / tables only, eager steps only
+    ops.NODE_SHARD = NodeSharding(group) if shard_nodes else None
     peer_allreduce_for(group)       # collective set-up now, not inside the first (possibly graph-captured) step
 
     def hook(flat: torch.Tensor) -> None:

@@ -30,8 +30,11 @@ MAX_DENSE_LOGIT_BYTES = 96 << 30   # (U, T) fp32 logits are materialised by this
 #                               them -- on the side stream, so the exchange overlaps the decoder forward; returns the
 #                               world size (the adjoint of the local column sums is world * the adjoint of the sum,
 #                               because every rank evaluates the same function of it)
+#   NODE_SHARD                  dp.NodeSharding: the streaming HPD path evaluates 1/world of the touched lattice nodes
+#                               per rank (selections all-gathered, adjoints reduce-scattered) instead of all of them
 GRAD_REDUCE_HOOK = None
 COLSUM_REDUCE_HOOK = None
+NODE_SHARD = None
 
 
 def _stream() -> int:
@@ -191,7 +194,7 @@ def tc_gemm_planes(a_planes, b_planes, out, accumulate=False, k_splits=1) -> Non
 STREAM_FWD_REFINED = True         # streaming forward as a two-plane pass + fp32 refinement of 8 candidates (K <= 4)
 
 
-def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
+def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None, alloc_rows=None):
     """Fused K2+K3: (utopv, utopi int32, row_max, row_sum) of softmax(h w^T + b) without the (U,T) logits.
     K <= 4: half the tensor-core work -- a two-plane (1e-5) streaming pass keeps 8 candidates per row, whose logits are
     then re-evaluated in fp32 and re-ranked (gngf_hpd_stream_fwd_refined); otherwise three planes / six products."""
@@ -200,8 +203,16 @@ def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None):
     hp = split_bf16x3(h) if h_planes is None else h_planes
     wp = split_bf16x3(w) if w_planes is None else w_planes
     dev = h.device
-    utopv = torch.empty((U, k), dtype=torch.float32, device=dev)
-    utopi = torch.empty((U, k), dtype=torch.int32, device=dev)
+    # alloc_rows >= U: the selections are written into the head of larger (zero-tailed) buffers -- the equal-sized
+    # per-rank blocks of dp.NodeSharding.all_gather_rows
+    if alloc_rows is None:
+        utopv = torch.empty((U, k), dtype=torch.float32, device=dev)
+        utopi = torch.empty((U, k), dtype=torch.int32, device=dev)
+    else:
+        utopv = torch.zeros((alloc_rows, k), dtype=torch.float32, device=dev)
+        utopi = torch.zeros((alloc_rows, k), dtype=torch.int32, device=dev)
+    if U == 0:
+        return utopv, utopi, torch.empty(0, dtype=torch.float32, device=dev), torch.empty(0, dtype=torch.float32, device=dev)
     row_max = torch.empty(U, dtype=torch.float32, device=dev)
     row_sum = torch.empty(U, dtype=torch.float32, device=dev)
     if STREAM_FWD_REFINED and k <= 4:
@@ -305,9 +316,10 @@ def gather_rows(x, lat: Lattice, uvals: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
-def active_nodes(x: torch.Tensor, lat: Lattice) -> torch.Tensor:
+def active_nodes(x: torch.Tensor, lat: Lattice, shard=None) -> torch.Tensor:
     """Ascending int32 ids of the lattice nodes that the corners of x touch (k11_active_nodes.cu).  One
-    device->host read of the count (the list sizes every launch of the HPD chain)."""
+    device->host read of the count (the list sizes every launch of the HPD chain).  With `shard` (dp.NodeSharding) the
+    per-rank bitmaps are OR-ed over the ranks first: every rank gets the same list -- the nodes ANY rank touches."""
     _require_cuda(x, "x")
     x = _f32c(x)
     lib = _lib.load()
@@ -316,8 +328,10 @@ def active_nodes(x: torch.Tensor, lat: Lattice) -> torch.Tensor:
     words = int(lib.gngf_active_nodes_bitmap_words(U))
     bitmap = torch.zeros((words + 3) & ~3, dtype=torch.int32, device=dev)
     call("gngf_lattice_mark_nodes", x.data_ptr(), P, lat, bitmap.data_ptr(), _stream())
+    if shard is not None:
+        bitmap = shard.union_bitmap(bitmap)
     chunk_offsets = torch.empty(int(lib.gngf_active_nodes_chunks(U)), dtype=torch.int32, device=dev)
-    capacity = max(1, min(U, P * lat.num_levels * 4))
+    capacity = max(1, min(U, P * lat.num_levels * 4 * (1 if shard is None else shard.world)))
     ids = torch.empty(capacity, dtype=torch.int32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
     call("gngf_compact_nodes", bitmap.data_ptr(), U, chunk_offsets.data_ptr(), ids.data_ptr(), capacity,
@@ -369,6 +383,8 @@ class ForwardState:
     nfeat: Optional[torch.Tensor] = None                         # (S,F) written by the HPD kernel itself (small lattices)
     utopv: Optional[torch.Tensor] = None                         # (U,K)
     utopi: Optional[torch.Tensor] = None                         # (U,K) int32
+    shard: Optional[tuple] = None                                # (dp.NodeSharding, listed nodes, r0, r1, chunk): this rank
+    node_ids_all: Optional[torch.Tensor] = None                  #   evaluated rows r0..r1 of the agreed node list
     node_ids: Optional[torch.Tensor] = None                      # (Ua,) int32 active nodes: the HPD chain (hpd_acts,
     utopv_rows: Optional[torch.Tensor] = None                    #   h_planes, row_max / row_sum, utopv_rows / utopi_rows)
     utopi_rows: Optional[torch.Tensor] = None                    #   has one row per ACTIVE node; utopv / utopi stay (U,K)
@@ -470,18 +486,31 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state, ta
         return
     acts = []
     ids = None
-    if n > 1 and _streaming_ok(cfg, U, T, k, hpd_w[-1].shape[1]) and _active_nodes_wanted(U):
-        ids = active_nodes(state.x, lat)
-        if ids.shape[0] == 0 or (FORCE_ACTIVE_NODES is None and ids.shape[0] > ACTIVE_NODES_MAX_FRACTION * U):
+    streaming = n > 1 and _streaming_ok(cfg, U, T, k, hpd_w[-1].shape[1])
+    # (node parallelism reads the node count back and sizes collectives with it: eager steps only)
+    shard = NODE_SHARD if (streaming and STREAM_BWD_FUSED and not torch.cuda.is_current_stream_capturing()) else None
+    if streaming and _active_nodes_wanted(U):
+        ids = active_nodes(state.x, lat, shard)
+        if ids.shape[0] == 0 or (shard is None and FORCE_ACTIVE_NODES is None
+                                 and ids.shape[0] > ACTIVE_NODES_MAX_FRACTION * U):
             ids = None
+    if shard is not None:
+        # node parallelism: this rank evaluates rows r0..r1 of the node list every rank agrees on
+        total = U if ids is None else int(ids.shape[0])
+        r0, r1, chunk = shard.bounds(total)
+        state.shard = (shard, total, r0, r1, chunk)
+        state.node_ids_all = ids
+        ids = torch.arange(r0, r1, dtype=torch.int32, device=device) if ids is None else ids[r0:r1]
     state.node_ids = ids
     rows = U if ids is None else ids.shape[0]
     h = torch.empty((rows, hpd_w[0].shape[0]), dtype=torch.float32, device=device)
-    call("gngf_hpd_first_layer_fwd_nodes", lat, _ptr(ids), rows, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(),
-         hpd_w[0].shape[0], ACT_RELU if n > 1 else ACT_NONE, h.data_ptr(), _stream())
+    if rows > 0:
+        call("gngf_hpd_first_layer_fwd_nodes", lat, _ptr(ids), rows, hpd_w[0].data_ptr(), hpd_b[0].data_ptr(),
+             hpd_w[0].shape[0], ACT_RELU if n > 1 else ACT_NONE, h.data_ptr(), _stream())
     for i in range(1, n - 1):
         acts.append(h)
-        h = linear_fwd(h, hpd_w[i], hpd_b[i], ACT_RELU)
+        h = linear_fwd(h, hpd_w[i], hpd_b[i], ACT_RELU) if rows > 0 else \
+            torch.empty((0, hpd_w[i].shape[0]), dtype=torch.float32, device=device)
     state.hpd_acts = acts
     if n == 1:                      # single-layer HPD: h already holds the logits
         state.uprobs, state.utopv, state.utopi = softmax_topk_fwd(h, k, inplace=True)
@@ -490,11 +519,25 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state, ta
     kd = h.shape[1]
     if _streaming_ok(cfg, U, T, k, kd):
         state.w_planes = split_bf16x3(hpd_w[-1])
-        state.h_planes = split_bf16x3(h)
+        state.h_planes = split_bf16x3(h) if rows > 0 else None
         state.utopv, state.utopi, state.row_max, state.row_sum = hpd_stream_fwd(
-            h, hpd_w[-1], hpd_b[-1], k, h_planes=state.h_planes, w_planes=state.w_planes)
+            h, hpd_w[-1], hpd_b[-1], k, h_planes=state.h_planes, w_planes=state.w_planes,
+            alloc_rows=None if state.shard is None else state.shard[4])
         state.uprobs = None
-        if ids is not None:
+        if state.shard is not None:
+            # every rank's selections, in list order (32 bytes per node for K = 4)
+            sh, total = state.shard[0], state.shard[1]
+            topv_all = sh.all_gather_rows(state.utopv, total)
+            topi_all = sh.all_gather_rows(state.utopi, total)
+            state.utopv_rows, state.utopi_rows = state.utopv[:rows], state.utopi[:rows]
+            if state.node_ids_all is None:          # the list is the whole box
+                state.utopv, state.utopi = topv_all, topi_all
+            else:
+                state.utopv = torch.ones((U, k), dtype=torch.float32, device=device)
+                state.utopi = torch.zeros((U, k), dtype=torch.int32, device=device)
+                scatter_node_rows(state.node_ids_all, topv_all, state.utopv)
+                scatter_node_rows(state.node_ids_all, topi_all, state.utopi)
+        elif ids is not None:
             # per-node results back into (U,K) arrays for the gather / scatter kernels.  Untouched nodes: slot 0 with
             # probability 1 -- finite under every mix mode; their multiplicities and feature adjoints are zero
             state.utopv_rows, state.utopi_rows = state.utopv, state.utopi
@@ -770,10 +813,26 @@ class GNGFPath(torch.autograd.Function):
             h_last = state.hpd_acts[nh - 2]
             kd = h_last.shape[1]
             ids = state.node_ids
-            dz = hpd_stream_bwd(lat, h_last, hpd_w[nh - 1], params[2 * (nh - 1) + 1], state.h_planes, state.w_planes,
-                                state.utopv if ids is None else state.utopv_rows,
-                                state.utopi if ids is None else state.utopi_rows, dtv, state.cnt, gcol_k,
-                                state.row_max, state.row_sum, g_hpd_w[nh - 1], g_hpd_b[nh - 1], node_ids=ids)
+            if state.shard is not None:
+                # node parallelism: this rank's share of the adjoints of ALL listed nodes (column-sum adjoint folded in),
+                # summed over ranks and handed to the rows' owners; the owner's backward takes them row-indexed
+                sh, total, r0, r1, chunk = state.shard
+                adj = torch.zeros((sh.world * chunk, K), dtype=torch.float32, device=dev)
+                call("gngf_gather_node_adjoints", lat, _ptr(state.node_ids_all), total, K, dtv.data_ptr(),
+                     _ptr(state.cnt), _ptr(gcol_k), adj.data_ptr(), st)
+                mine = sh.reduce_scatter_rows(adj)
+                del adj
+                if r1 > r0:
+                    dz = hpd_stream_bwd(lat, h_last, hpd_w[nh - 1], params[2 * (nh - 1) + 1], state.h_planes,
+                                        state.w_planes, state.utopv_rows, state.utopi_rows, mine, None, None,
+                                        state.row_max, state.row_sum, g_hpd_w[nh - 1], g_hpd_b[nh - 1], node_ids=None)
+                else:
+                    dz = torch.empty((0, kd), dtype=torch.float32, device=dev)
+            else:
+                dz = hpd_stream_bwd(lat, h_last, hpd_w[nh - 1], params[2 * (nh - 1) + 1], state.h_planes, state.w_planes,
+                                    state.utopv if ids is None else state.utopv_rows,
+                                    state.utopi if ids is None else state.utopi_rows, dtv, state.cnt, gcol_k,
+                                    state.row_max, state.row_sum, g_hpd_w[nh - 1], g_hpd_b[nh - 1], node_ids=ids)
         else:
             # streaming path: recompute the logits chunk by chunk on the tensor cores, turn them into dlogits in
             # place from the saved softmax statistics, and feed the output layer's backward
@@ -803,10 +862,11 @@ class GNGFPath(torch.autograd.Function):
                 ht_planes = split_bf16x3_t(hc)                                  # (3, kd, n8)
                 tc_gemm_planes(dlt_planes, ht_planes, g_hpd_w[nh - 1], accumulate=True)
                 del buf, dlt_planes, ht_planes
-        for i in range(nh - 2, 0, -1):
-            dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
-        call("gngf_hpd_first_layer_bwd_nodes", lat, _ptr(state.node_ids), dz.shape[0], dz.data_ptr(), hpd_w[0].shape[0],
-             g_hpd_w[0].data_ptr(), g_hpd_b[0].data_ptr(), st)
+        if dz.shape[0] > 0:          # (a node-parallel rank can own no rows of a tiny list)
+            for i in range(nh - 2, 0, -1):
+                dz = linear_bwd(dz, state.hpd_acts[i - 1], hpd_w[i], ACT_RELU, True, g_hpd_w[i], g_hpd_b[i])
+            call("gngf_hpd_first_layer_bwd_nodes", lat, _ptr(state.node_ids), dz.shape[0], dz.data_ptr(),
+                 hpd_w[0].shape[0], g_hpd_w[0].data_ptr(), g_hpd_b[0].data_ptr(), st)
         if GRAD_REDUCE_HOOK is not None:
             GRAD_REDUCE_HOOK(flat_params)      # every parameter gradient is a view of it: one collective for all
         return (None, None, *grads)

@@ -121,6 +121,15 @@ int64_t gngf_active_nodes_chunks(int64_t U);
 int gngf_lattice_mark_nodes(const float* x, int64_t P, gngf_lattice lat, uint32_t* bitmap, void* stream);
 int gngf_compact_nodes(const uint32_t* bitmap, int64_t U, int32_t* chunk_offsets, int32_t* node_ids, int64_t capacity,
                        int32_t* count, void* stream);
+/* Node-parallel HPD across data-parallel ranks (last sentence: "HPD work could alternatively be sharded
+ * over unique rows"): gngf_bitmap_or: out[w] = OR over the n_maps all-gathered per-rank bitmaps maps[r * words + w]
+ * (words % 4 == 0, 16-byte aligned).  gngf_gather_node_adjoints: out[r,k] = dtv[node_ids[r],k] + sum_l cnt[s(l,node)]
+ * gcol_k[l,k] -- this rank's share of the adjoint of the selected probabilities per row of the agreed node list
+ * (node_ids NULL: row r is node r), ready for a sum-reduce-scatter to the rows' owners; gcol_k / cnt may be NULL.  The
+ * owner then calls gngf_hpd_stream_bwd with node list NULL, cnt = gcol_k = NULL and the reduced rows as dtv.       */
+int gngf_bitmap_or(const uint32_t* maps, int32_t n_maps, int64_t words, uint32_t* out, void* stream);
+int gngf_gather_node_adjoints(gngf_lattice lat, const int32_t* node_ids, int64_t n_nodes, int32_t K, const float* dtv,
+                              const int32_t* cnt, const float* gcol_k, float* out, void* stream);
 int gngf_scatter_node_rows(const int32_t* node_ids, int64_t n_nodes, const void* src, int64_t row_words, void* dst,
                            void* stream);
 

@@ -14,15 +14,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, name, out):
+def _worker(rank, world, port, name, out, streaming=None, active=None):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     import torch.distributed as dist
     from golden_util import load
     from parity_util import build_net
 
-    from collision_handling_in_instantngp_b200 import dp
+    from collision_handling_in_instantngp_b200 import dp, ops
     from collision_handling_in_instantngp_b200.loss import fused_total_loss
+    ops.FORCE_STREAMING, ops.FORCE_ACTIVE_NODES = streaming, active
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.cuda.set_device(0)
@@ -40,32 +41,55 @@ def _worker(rank, world, port, name, out):
     total, _, _ = fused_total_loss(rgb, y, colsum, rows, c["gamma"], c["epsilon"], c["l_mse"], c["l_js_kl"])
     total.backward()
     torch.cuda.synchronize()
-    out.put((rank, {k: v.grad.detach().cpu().numpy() for k, v in net.named_parameters() if v.grad is not None}))
+    st = net.last_state
+    info = None if st.shard is None else dict(total=st.shard[1], r0=st.shard[2], r1=st.shard[3],
+                                              listed=None if st.node_ids_all is None else int(st.node_ids_all.shape[0]),
+                                              nodes=st.lat.num_nodes)
+    out.put((rank, {k: v.grad.detach().cpu().numpy() for k, v in net.named_parameters() if v.grad is not None}, info))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_ranks_match_full_batch_golden_gradients():
+@pytest.mark.parametrize("name,streaming,active,world", [
+    ("cfg2_small", None, None, 2),
+    # node-parallel HPD (dp.NodeSharding): the streaming path, every rank evaluating half of the box ...
+    ("cfg2_topk_only", True, False, 2),
+    # ... or its share of the nodes ANY rank touches (bitmap union), selections all-gathered, adjoints reduce-scattered
+    ("l8_t4096_topk_only", True, True, 2),
+    ("cfg2_topk_only", True, True, 3),
+])
+def test_two_ranks_match_full_batch_golden_gradients(name, streaming, active, world):
     sys.path.insert(0, HERE)
     from golden_util import load, rel_err
-    name = "cfg2_small"
     g = load(name)
     g_x = g["x"].shape[0]
-    assert g_x % 2 == 1          # 333 points: shards of 167 and 166 -> exercise the unequal-shard weighting below
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q, streaming, active)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=300) for _ in range(2))
+    res = [q.get(timeout=300) for _ in range(world)]
+    got = {r: grads for r, grads, _ in res}
+    infos = {r: info for r, _, info in res}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    if streaming:
+        # the ranks split one agreed node list between them (and only the touched nodes when `active`)
+        spans = [(infos[r]["r0"], infos[r]["r1"]) for r in range(world)]
+        assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert spans[-1][1] == infos[0]["total"] and len({infos[r]["total"] for r in range(world)}) == 1
+        assert (infos[0]["listed"] is not None) == bool(active)
+        if active:
+            assert infos[0]["total"] <= infos[0]["nodes"]
+    else:
+        assert infos[0] is None
     for k in got[0]:
-        np.testing.assert_array_equal(got[0][k], got[1][k])       # every rank holds the same averaged gradient
+        for r in range(1, world):
+            np.testing.assert_array_equal(got[0][k], got[r][k])   # every rank holds the same averaged gradient
     # the divergence part is exact; the MSE part is a mean of per-shard means, i.e. weights 1/2 vs 167/333:
     # compare the HPD / table gradients (dominated by the divergence term through pbar) loosely and the structure
     # exactly via a single-process run with the same per-shard weighting
@@ -78,8 +102,9 @@ def test_two_ranks_match_full_batch_golden_gradients():
     c = g["cfg"]
     x, y = _t.from_numpy(g["x"]).cuda(), _t.from_numpy(g["y"]).cuda()
     rgb, probs, _, _ = net(x, 1.0)
-    a = (g_x + 1) // 2
-    w = _t.cat([_t.full((a,), 0.5 / a), _t.full((g_x - a,), 0.5 / (g_x - a))]).cuda()     # mean of shard means
+    from collision_handling_in_instantngp_b200 import dp as _dp
+    sizes = [b - a for a, b in (_dp.shard_bounds(g_x, r, world) for r in range(world))]
+    w = _t.cat([_t.full((n,), 1.0 / world / n) for n in sizes]).cuda()                     # mean of shard means
     mse = (((rgb - y) ** 2).mean(dim=1) * w).sum()
     from collision_handling_in_instantngp_b200.loss import level_divergences
     levels = level_divergences(probs.colsum / (4 * g_x), c["gamma"], c["epsilon"])

@@ -464,8 +464,9 @@ def test_fused_adam_matches_torch_adam():
     # continue the FusedAdam run in a stock Adam and vice versa, then take one more step in each
     pc, oc = make(torch.optim.Adam)
     pd, od = make(FusedAdam)
-    oc.load_state_dict(ob.state_dict())
-    od.load_state_dict(oa.state_dict())
+    import copy
+    oc.load_state_dict(copy.deepcopy(ob.state_dict()))      # (load_state_dict aliases same-device tensors: copy, as a
+    od.load_state_dict(copy.deepcopy(oa.state_dict()))      #  torch.save / torch.load round trip would)
     for src, dst in ((pb, pc), (pa, pd)):
         for a, b in zip(src, dst):
             b.data.copy_(a.data)
