@@ -107,9 +107,21 @@ def test_active_node_and_split_loss_entry_points_validate_on_the_host():
     assert lib.gngf_loss_parts(*args, None, None, None, 3, None) == -1
     assert lib.gngf_loss_parts(*args, 16, None, None, 1, None) == -1            # MSE half without rgb / target / d_rgb
     assert lib.gngf_loss_parts(*args, 16, None, None, 2, None) == -1            # divergence half without column sums
-    # the streaming backward on a node list accepts fewer rows than the box, the plain entry point does not
+    # the streaming backward on a node list accepts fewer rows than the box; the plain entry point only without a
+    # column-sum adjoint (rows whose adjoints arrive row-indexed: the node-parallel owner's call)
     small = build_lattice(level_resolutions(8, 32, 4))
     a = (16,) * 5
     common = (16, 16, 16, None, None, 16, 16, 1, 16, 16, 16, 16, None)
-    assert lib.gngf_hpd_stream_bwd(small, *a, 100, 256, 128, 4, *common) == -2                    # U != box
+    with_colsum = (16, 16, 16, 16, 16, 16, 16, 1, 16, 16, 16, 16, None)
+    assert lib.gngf_hpd_stream_bwd(small, *a, 100, 256, 128, 4, *with_colsum) == -2               # U != box
+    # node-parallel helpers
+    assert lib.gngf_bitmap_or(None, 2, 8, None, None) == -1
+    assert lib.gngf_bitmap_or(16, 2, 6, 16, None) == -1                         # whole 16-byte groups of words only
+    assert lib.gngf_bitmap_or(16, 0, 8, 16, None) == -1
+    assert lib.gngf_bitmap_or(16, 2, 0, 16, None) == 0
+    assert lib.gngf_gather_node_adjoints(small, None, 0, 4, None, None, None, None, None) == 0    # empty list
+    assert lib.gngf_gather_node_adjoints(small, None, 5, 4, None, None, None, 16, None) == -1     # no adjoints
+    assert lib.gngf_gather_node_adjoints(small, None, 5, 4, 16, None, 16, 16, None) == -1         # gcol_k without cnt
+    assert lib.gngf_gather_node_adjoints(small, None, 5, 0, 16, None, None, 16, None) == -1
+    assert lib.gngf_peer_allreduce_set_timeout_ms(0) == -1 and lib.gngf_peer_allreduce_set_timeout_ms(30000) == 0
     assert lib.gngf_hpd_stream_bwd_nodes(small, 16, *a, small.num_nodes + 1, 256, 128, 4, *common) == -2
