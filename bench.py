@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- train samples/s of the GNGF hot path (forward + loss + backward + Adam) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4_t14]
 
 One "step" = one pass of the hot path over one batch of synthetic coordinates:
 GeneralNeuralGaugeFields.forward (models.py:394-484) -> the reference's loss assembly (utils.py:78-174,
-functions.py:243-245) -> backward -> Adam (functions.py:96-127).  The default workload is BASELINE.json
-configs[1] ("cfg2": the shape of strawberry.jpeg with grid-search ID 4061: P = 57 404 pixels per batch, L = 4
-levels n = [8,12,20,32], T = 256 slots, K = 4, F = 2, HPD 2-32-64-128-256, decoder 8-64-64-3) on synthetic data
-(pixel-lattice coordinates in a seeded random order, uniform random targets, random-init weights).
+functions.py:243-245) -> backward -> Adam (functions.py:96-127).
 
-JSON line (rank 0): see README/DESIGN.md.  `value` is device time with inputs resident in HBM (CUDA events per
-step, L2 flushed between steps); `e2e` is the same step driven through the module API with HOST (pinned)
-inputs copied in and the loss read back every step; `roofline` describes the dominant kernel of the step;
-`cpu_baseline` is the oracle port (numpy restatement of the reference) timed on this box's host cores.
-`--impl reference` times that CPU port alone (the reference is PyTorch-on-CPU code that cannot travel to the
-GPU box).
+Default workload = BASELINE.json configs[3], the configuration the metric's "at 1/2/4/8 B200" names: a synthetic
+8192 x 8192 pixel lattice, 2^22 points per step, 16 levels x 2 features, K = 4, HPD 2-32-64-128-T, decoder 32-64-64-3,
+top-k-only probabilities -- with the table size T = 2^14 stated in `config` ("cfg4_t14"): at the survey's T = 2^19 one
+step executes 6e16 tensor-core FLOP (~50 s on one B200), which does not fit a default bench run; that line is
+builder-run (`--workload cfg4`, profiles/).  The step's 2^22 points are SPLIT over the N ranks (strong scaling): every
+rank runs the point passes on its 2^22 / N points and 1 / N of the lattice nodes any rank touches through the HPD
+(dp.NodeSharding).  At N = 1 the line also carries `secondary`: configs[1] (cfg2, strawberry / ID 4061 shapes) and
+configs[2] (cfg3: macaw shape, T = 2^19 as specified) measured in the same process.
+
+JSON line (rank 0): `value` is device time with inputs resident in HBM (CUDA events per step, L2 flushed between
+steps); `e2e` the same step through the module API with HOST (pinned) inputs copied in and the loss read back every
+step; `roofline` describes the dominant kernel of the step (per-call CUDA events, algorithmic cost of DESIGN.md
+section 4); `cpu_baseline` = the UNMODIFIED reference (baseline/_ref: its GeneralNeuralGaugeFields + Loss + Adam) on
+this box's host cores on a bounded sample of the workload; `gpu_eager_reference` = the same unmodified reference on
+cuda:0 (its ATen eager path) at the largest sample that fits -- the number the drop-in replaces.  `--impl reference`
+times the reference's CPU path alone.  When baseline/_ref is absent the reference legs fall back to
+oracle/torch_port.py (kind "port").
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -30,29 +39,30 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "train samples/sec (fwd+bwd GNGF hash encode+MLP)"
+_COMMON = dict(K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64], gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
+               lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6))
 WORKLOADS = {
-    # BASELINE.json configs[1]: strawberry.jpeg + param ID 4061 (README.md:15-18, params.py:26-51)
-    "cfg2": dict(P=57404, L=4, n_min=8, n_max=32, T=256, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
-                 lattice_hw=(508, 339), topk_only=False, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
-                 lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
-                 cpu_sample=16384),
+    # BASELINE.json configs[1]: strawberry.jpeg + param ID 4061 (README.md:15-18, params.py:26-51); one batch = a third of
+    # the image (batch_size = 1/3).  Per-rank batch fixed as N grows (weak scaling: the published shapes)
+    "cfg2": dict(_COMMON, P=57404, L=4, n_min=8, n_max=32, T=256, lattice_hw=(508, 339), topk_only=False,
+                 cpu_sample=57404, scaling="weak", names="configs[1]: strawberry.jpeg shapes, param ID 4061"),
     # BASELINE.json configs[2]: macaw.jpg (508x339 = 172 212 px < 2^18: the whole image is one batch), 16 levels,
     # table size 2^19, top-k-only probabilities (the full distribution would be 134 MB per sample)
-    "cfg3": dict(P=172212, L=16, n_min=16, n_max=508, T=2 ** 19, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
-                 lattice_hw=(508, 339), topk_only=True, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
-                 lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
-                 cpu_sample=4),
+    "cfg3": dict(_COMMON, P=172212, L=16, n_min=16, n_max=508, T=2 ** 19, lattice_hw=(508, 339), topk_only=True,
+                 cpu_sample=4, scaling="strong", names="configs[2]: macaw.jpg shape, 16 levels, T = 2^19"),
     # same image shape with a mid-size table (fits the dense path as well; used to compare the two HPD paths)
-    "cfg3_t14": dict(P=172212, L=16, n_min=16, n_max=508, T=2 ** 14, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
-                     lattice_hw=(508, 339), topk_only=True, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
-                     lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
-                     cpu_sample=64),
+    "cfg3_t14": dict(_COMMON, P=172212, L=16, n_min=16, n_max=508, T=2 ** 14, lattice_hw=(508, 339), topk_only=True,
+                     cpu_sample=64, scaling="strong", names="configs[2] shape with T = 2^14"),
     # BASELINE.json configs[3]: synthetic 8192 x 8192 lattice, 2^22 points per step, 16 levels x 2 features
-    "cfg4_t14": dict(P=2 ** 22, L=16, n_min=16, n_max=8192, T=2 ** 14, K=4, F=2, hpd=[32, 64, 128], mlp=[64, 64],
-                     lattice_hw=(8192, 8192), topk_only=True, gamma=-2.0, epsilon=1.0, l_mse=1.0, l_js_kl=1.0,
-                     lr=dict(encoding=1e-4, hpd=1e-3, mlp=1e-3), wd=dict(encoding=0.0, hpd=1e-6, mlp=1e-6),
-                     cpu_sample=64),
+    "cfg4_t14": dict(_COMMON, P=2 ** 22, L=16, n_min=16, n_max=8192, T=2 ** 14, lattice_hw=(8192, 8192), topk_only=True,
+                     cpu_sample=128, scaling="strong",
+                     names="configs[3]: synthetic 8192x8192 lattice, 2^22 points/step, 16 levels x 2 features, T = 2^14"),
+    "cfg4": dict(_COMMON, P=2 ** 22, L=16, n_min=16, n_max=8192, T=2 ** 19, lattice_hw=(8192, 8192), topk_only=True,
+                 cpu_sample=4, scaling="strong",
+                 names="configs[3]: synthetic 8192x8192 lattice, 2^22 points/step, 16 levels x 2 features, T = 2^19"),
 }
+DEFAULT_WORKLOAD = "cfg4_t14"
 
 
 def make_inputs(w, seed, rank=0):
@@ -66,12 +76,43 @@ def make_inputs(w, seed, rank=0):
     return x, y
 
 
+def static_config(name, w, world):
+    """The workload as both arms state it (identical dicts: the driver compares them)."""
+    return {"workload": name, "names": w["names"], "points_per_step": w["P"] * (world if w["scaling"] == "weak" else 1),
+            "levels": w["L"], "table_size": w["T"], "topk_k": w["K"], "feature_dim": w["F"], "hpd": [2, *w["hpd"], w["T"]],
+            "decoder": [w["L"] * w["F"], *w["mlp"], 3], "n_min": w["n_min"], "n_max": w["n_max"],
+            "step": "forward+loss+backward+Adam", "parallelism": f"dp{world}"}
+
+
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's path restated on PyTorch-CPU (oracle/torch_port.py), forward + loss + backward + Adam
+# reference legs: the UNMODIFIED reference (baseline/_ref) in a child process; oracle port when it is absent
 # ------------------------------------------------------------------------------------------------------------
+def reference_available():
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "models.py"))
+
+
+def time_reference(w, device, points, steps, warmup, timeout=1500):
+    """samples/s record of baseline/ref_step.py (the reference's own classes; see its docstring), or None."""
+    keep = {k: v for k, v in w.items() if not k.startswith("_")}
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_step.py"), "--device", device, "--points", str(points),
+           "--steps", str(steps), "--warmup", str(warmup), "--workload", json.dumps(keep)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "PYTHONPATH"):
+        env.pop(k, None)
+    if device == "cuda":
+        env["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout} s"}
+    if p.returncode != 0:
+        return {"error": p.stderr.strip().splitlines()[-1][:300] if p.stderr.strip() else f"rc {p.returncode}"}
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
 def time_cpu_port(w, sample_P, seed, steps, warmup):
-    """Seconds per step of the PyTorch-CPU port of the reference (oracle/torch_port.py: the same ATen operations
-    and autograd the reference issues, all host threads) on `sample_P` coordinates of the workload."""
+    """Fallback when baseline/_ref is absent: seconds per step of oracle/torch_port.py (the reference's ATen ops +
+    autograd restated on PyTorch-CPU, all host threads) on `sample_P` coordinates of the workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import gngf_oracle as O
@@ -89,9 +130,32 @@ def time_cpu_port(w, sample_P, seed, steps, warmup):
     return float(np.mean(times))
 
 
-def cpu_threads():
+def cpu_reference_record(w, steps, warmup, sample_P=None):
+    """cpu_baseline object: the reference's CPU path on a bounded sample, all host threads."""
+    sample_P = int(sample_P or w["cpu_sample"])
+    what = f"{sample_P} of the workload's {w['P']} coordinates per step, {steps} steps after {warmup} warm-up, forward+loss+backward+Adam"
+    if reference_available():
+        r = time_reference(w, "cpu", sample_P, steps, warmup)
+        if r and "error" not in r:
+            return {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "reference",
+                    "sample": what + "; the UNMODIFIED reference (baseline/_ref: GeneralNeuralGaugeFields + Loss + "
+                                     "get_optimizer, PyTorch-CPU, all host threads)", "ms_per_step": r["sec_per_step"] * 1e3}
+        err = r["error"] if r else "no output"
+    else:
+        err = "baseline/_ref absent"
     import torch
-    return int(torch.get_num_threads())
+    sec = time_cpu_port(w, sample_P, 65535, steps, warmup)
+    return {"value": sample_P / sec, "unit": "samples/s", "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": what + f"; oracle/torch_port.py (PyTorch-CPU restatement; reference unavailable: {err})",
+            "ms_per_step": sec * 1e3}
+
+
+def gpu_reference_points(w):
+    """Largest power-of-two sample whose (rows, T) fp32 tensors -- ~12 live copies in the reference's forward + autograd
+    -- stay below ~60 GB."""
+    per_point = 4 * w["L"] * w["T"] * 4 * 12
+    p = max(1, int(60e9 // per_point))
+    return int(min(w["P"], 2 ** int(np.log2(p)))) if p < w["P"] else w["P"]
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -193,7 +257,24 @@ def cost_key(name, args):
         return tuple(int(v) for v in args[3:6]) + (args[7] is not None,)
     if name == "gngf_tc_gemm_bf16x3":
         return tuple(int(v) for v in args[3:6])
+    if name == "gngf_peer_allreduce":
+        return (int(args[3]), int(args[6]))                  # (world, floats)
+    if name in ("gngf_hpd_stream_fwd", "gngf_hpd_stream_fwd_refined"):
+        return (_rows_arg(name, args),)
+    if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
+        return (_rows_arg(name, args),)
     return ()
+
+
+def _rows_arg(name, args):
+    """Rows (lattice nodes) a streaming HPD call processes: under node parallelism a rank's share of the node list."""
+    if name == "gngf_hpd_stream_fwd":
+        return int(args[3])
+    if name == "gngf_hpd_stream_fwd_refined":
+        return int(args[5])
+    if name == "gngf_hpd_stream_bwd":
+        return int(args[6])
+    return int(args[7])
 
 
 def algorithmic_cost(name, key, w, lat):
@@ -201,6 +282,11 @@ def algorithmic_cost(name, key, w, lat):
     P, L, F, K, T = w["P"], w["L"], w["F"], w["K"], w["T"]
     U, S = lat.num_nodes, lat.num_level_nodes
     Ua = w.get("_active_nodes") or U      # rows of the HPD chain (ops.active_nodes: the nodes the batch touches)
+    if name.startswith("gngf_hpd_stream_") and key:
+        Ua = key[0]                       # the rows this call processed (node parallelism: 1/world of the list)
+    if name == "gngf_peer_allreduce":
+        # every rank reads the other ranks' slices over NVLink: (world - 1) * n * 4 bytes against 900 GB/s per direction
+        return "nvlink", float((key[0] - 1) * key[1] * 4)
     if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
         # EXECUTED tensor-core FLOPs: inputs padded to 16, output layer padded to 16 columns;
         # forward: 6 split products; backward: 3 split products over recompute (2 layers) + dA2, dA1, dX + dW2, dW1, dW0
@@ -259,6 +345,9 @@ def algorithmic_cost(name, key, w, lat):
         "gngf_lattice_mark_nodes": P * 8 + U / 8,
         "gngf_compact_nodes": 2 * U / 8 + Ua * 4,
         "gngf_scatter_node_rows": Ua * (4 + K * 8),
+        "gngf_gather_node_adjoints": Ua * (4 + K * 8) + Ua * L * 4,
+        "gngf_bitmap_or": U / 8 * 3,
+        "gngf_cell_to_node_counts": S * 4 * 5,
         "gngf_split_bf16x3": 0.0,
     }
     return "hbm", float(table.get(name, 0))
@@ -284,16 +373,232 @@ def useful_tflops(name, achieved, w):
     return None
 
 
-def run_ours(args, w):
+class Runner:
+    """One workload on this rank: model, optimizer, inputs and the step closure."""
+
+    def __init__(self, torch, dist, name, w, rank, world, dev):
+        from collision_handling_in_instantngp_b200 import dp
+        from collision_handling_in_instantngp_b200.loss import fused_total_loss
+        from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+        from collision_handling_in_instantngp_b200.optim import FusedAdam
+        self.torch, self.dist, self.dp = torch, dist, dp
+        self.name, self.w, self.rank, self.world, self.dev = name, w, rank, world, dev
+        torch.manual_seed(65535)
+        self.net = net = GeneralNeuralGaugeFields(
+            input_dim=2, hash_table_size=w["T"], num_levels=w["L"], n_min=w["n_min"], n_max=w["n_max"],
+            MLP_hidden_layers_widths=w["mlp"], HPD_hidden_layers_widths=w["hpd"], HPD_out_features=w["T"],
+            feature_dim=w["F"], topk_k=w["K"], should_keep_topk_only=w["topk_only"])
+        h, wd = w["lattice_hw"]
+        m = max(h, wd) - 1
+        net.set_coord_bounds((0.0, 0.0), ((h - 1) / m, (wd - 1) / m))
+        self.opt = FusedAdam(                                                       # functions.py:96-127, one launch
+            [{"params": net.encoding.parameters(), "lr": w["lr"]["encoding"], "weight_decay": w["wd"]["encoding"]},
+             {"params": net.HPD.parameters(), "lr": w["lr"]["hpd"], "weight_decay": w["wd"]["hpd"]},
+             {"params": net.mlp.parameters(), "lr": w["lr"]["mlp"], "weight_decay": w["wd"]["mlp"]}],
+            betas=(0.9, 0.99), eps=1e-15)
+        dp.enable_gradient_allreduce()      # N > 1: column-sum + flat-gradient exchanges, node-parallel HPD
+        self.strong = w["scaling"] == "strong"
+        if self.strong:
+            # the step's points are SPLIT over the ranks: every rank draws the same global batch and keeps its shard
+            x_np, y_np = make_inputs(w, 65535, 0)
+            a, b = dp.shard_bounds(w["P"], rank, world)
+            x_np, y_np = np.ascontiguousarray(x_np[a:b]), np.ascontiguousarray(y_np[a:b])
+            self.total_points = w["P"]
+        else:
+            x_np, y_np = make_inputs(w, 65535, rank)
+            self.total_points = w["P"] * world
+        self.local_points = x_np.shape[0]
+        self.x_host, self.y_host = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(y_np).pin_memory()
+        self.x_dev, self.y_dev = self.x_host.to(dev), self.y_host.to(dev)
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.rows = 4 * self.total_points
+        self._loss_fn = fused_total_loss
+
+    def step(self, x, y):
+        w = self.w
+        self.opt.zero_grad(set_to_none=True)
+        rgb, probs, idx, _ = self.net(x, 1.0)
+        colsum = self.dp.all_reduce_colsum(probs.colsum) if self.world > 1 else probs.colsum
+        loss, _, _ = self._loss_fn(rgb, y, colsum, self.rows, w["gamma"], w["epsilon"], w["l_mse"], w["l_js_kl"])
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_step(self):
+        """The module API end to end: pinned host batch in, loss out, every step."""
+        torch = self.torch
+        loss = self.step(self.x_host.to(self.dev, non_blocking=True), self.y_host.to(self.dev, non_blocking=True))
+        self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+
+def verify_peer_allreduce(torch, dist, dp, dev, sizes):
+    """One peer-kernel vs NCCL comparison per buffer size in use, bit for bit (integer-valued floats: every summation
+    order gives the same bits), and identical results on every rank."""
+    comm = dp.peer_allreduce_for()
+    if comm is None:
+        return {"verified": False, "why": "peer all-reduce unavailable (NCCL all_reduce in use)"}
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ok, checked = True, []
+    for n in sorted({int(s) for s in sizes if 0 < int(s) * 4 <= dp.PEER_MAX_BYTES}):
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        t = torch.randint(-1000, 1000, (n,), generator=g, device=dev).float()
+        a = dp.all_reduce_sum(t)
+        b = t.clone()
+        dist.all_reduce(b)
+        same = bool(torch.equal(a, b))
+        digest = torch.stack([a.double().sum(), (a.double() * torch.arange(n, device=dev)).sum()])
+        all_d = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(all_d, digest)
+        same = same and all(bool(torch.equal(all_d[0], d)) for d in all_d)
+        ok = ok and same
+        checked.append(n)
+    comm.check()
+    return {"verified": bool(ok) and bool(checked), "floats": checked}
+
+
+def measure(torch, dist, R, steps, warmup, *, profile, eager_e2e, graph, flush):
+    """Device-timed steps (+ optional per-kernel profile and end-to-end passes) of Runner R; returns a dict."""
+    from collision_handling_in_instantngp_b200 import _lib, launch_count
+    from collision_handling_in_instantngp_b200 import ops as _ops
+    from collision_handling_in_instantngp_b200.trainer import GraphedTrainer
+    w, dev = R.w, R.dev
+    out = {}
+    for _ in range(max(warmup, 3)):
+        R.step(R.x_dev, R.y_dev)
+    R.barrier()
+    n0 = launch_count()
+    R.step(R.x_dev, R.y_dev)
+    torch.cuda.synchronize()
+    out["launches_per_step"] = launch_count() - n0
+
+    if eager_e2e:      # what the reference's own train_step gets from the drop-in module: eager, host inputs
+        R.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            R.host_step()
+        R.barrier()
+        out["e2e_eager_ms"] = (time.perf_counter() - t0) * 1e3 / steps
+
+    if profile:        # per-kernel device times (CUDA events around every C-ABI call, serial schedule) -> dominant kernel
+        prof = CallProfiler(torch)
+        _lib.PROFILER = prof
+        _ops.CONCURRENT = False
+        for _ in range(profile):
+            flush.zero_()
+            R.step(R.x_dev, R.y_dev)
+        _ops.CONCURRENT = True
+        _lib.PROFILER = None
+        out["profile"] = prof.summary()
+        out["profile_steps"] = profile
+    st = R.net.last_state
+    out["lat"] = st.lat
+    ids = st.node_ids_all if st.shard is not None else st.node_ids
+    out["listed_nodes"] = (st.shard[1] if st.shard is not None else (None if ids is None else int(ids.shape[0])))
+    out["hpd_rows_this_rank"] = None if st.node_ids is None else int(st.node_ids.shape[0])
+    R.barrier()
+
+    trainer = None
+    if graph:          # the public fast path for small lattices: the whole step captured once in a CUDA graph
+        trainer = GraphedTrainer(R.net, R.opt, points=R.local_points, gamma=w["gamma"], epsilon=w["epsilon"],
+                                 l_mse=w["l_mse"], l_js_kl=w["l_js_kl"], warmup_steps=3, sample_x=R.x_dev,
+                                 sample_y=R.y_dev)
+        for _ in range(max(warmup, 3)):
+            trainer.replay()
+        torch.cuda.synchronize()
+    out["launch_mode"] = "cuda_graph" if trainer is not None else "eager"
+
+    # ---- the device-timed region: inputs resident in HBM, CUDA events around every step, L2 flushed between ----
+    R.barrier()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        if trainer is not None:
+            trainer.replay()
+        else:
+            R.step(R.x_dev, R.y_dev)
+        b.record()
+        evs.append((a, b))
+    R.barrier()
+    out["dev_ms"] = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    # ---- end to end through the public API with HOST buffers (wall clock) ----
+    R.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if trainer is not None:
+            trainer.step_pipelined(R.x_host, R.y_host)
+        else:
+            R.host_step()
+    if trainer is not None:
+        trainer.flush()
+    R.barrier()
+    out["e2e_ms"] = (time.perf_counter() - t0) * 1e3 / steps
+    out["e2e_path"] = (
+        "trainer.GraphedTrainer.step_pipelined(x_host, y_host): pinned host batch copied into the idle one of two static "
+        "buffer sets on a copy stream, CUDA-graph replay of forward+loss+backward+Adam, loss copied to pinned host memory "
+        "and returned one step later, every step; flush() inside the timed region" if trainer is not None else
+        "module API, eager: net(x) / loss / backward / FusedAdam with pinned host inputs copied in and the loss read back "
+        "every step")
+    out["h2d_bytes"] = int(R.x_host.numel() * 4 + R.y_host.numel() * 4)
+    if trainer is not None:
+        trainer.check_errors()
+        del trainer
+    R.net.check_errors()
+    return out
+
+
+def roofline_of(m, w, steps_profiled, workload):
+    per_name = {}
+    for (name, key), (t, n) in m["profile"].items():
+        bound, amount = algorithmic_cost(name, key, w, m["lat"])
+        e = per_name.setdefault(name, dict(ms=0.0, n=0, amount=0.0, bound=bound))
+        e["ms"] += t; e["n"] += n; e["amount"] += amount * n
+    total_kernel_ms = sum(e["ms"] for e in per_name.values())
+    tname, te = max(per_name.items(), key=lambda kv: kv[1]["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # a kernel timed inside a long step sees the sustained clock; short kernels the burst figure
+    long_kernel = te["ms"] / te["n"] > 50.0
+    tc_peak = peaks.get("bf16_tflops_sustained" if long_kernel else "bf16_tflops", 1590.0)
+    per_launch_s = te["ms"] / te["n"] / 1e3
+    per_launch_amount = te["amount"] / te["n"]
+    if te["bound"] == "hbm":
+        achieved, peak, unit = per_launch_amount / per_launch_s / 1e9, hbm_peak, "GB/s"
+    elif te["bound"] == "nvlink":
+        achieved, peak, unit = per_launch_amount / per_launch_s / 1e9, 900.0, "GB/s"
+    else:
+        achieved, peak, unit = per_launch_amount / per_launch_s / 1e12, tc_peak, "TFLOP/s"
+    return {"bound": te["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": NCU_TRAFFIC.get((workload, tname)), "kernel": tname,
+            "useful_tflops": useful_tflops(tname, achieved, w), "launches_per_step": te["n"] / steps_profiled,
+            "share_of_step_kernel_time": te["ms"] / total_kernel_ms,
+            "peak_source": ("measured" if peaks else "fallback") + (
+                " (sustained bf16: the kernel runs > 50 ms per launch)" if te["bound"] == "tensor" and long_kernel else
+                " (burst bf16)" if te["bound"] == "tensor" else ""),
+            "kernels_ms_per_step": {k: round(v["ms"] / steps_profiled, 5) for k, v in
+                                    sorted(per_name.items(), key=lambda kv: -kv[1]["ms"])}}
+
+
+def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from collision_handling_in_instantngp_b200 import _lib, dp, launch_count
-    from collision_handling_in_instantngp_b200.loss import fused_total_loss as total_loss
-    from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
-    from collision_handling_in_instantngp_b200.optim import FusedAdam
-    from collision_handling_in_instantngp_b200.trainer import GraphedTrainer
+    from collision_handling_in_instantngp_b200 import dp
 
+    name = args.workload
+    w = dict(WORKLOADS[name])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -301,213 +606,115 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(65535)
-
-    net = GeneralNeuralGaugeFields(input_dim=2, hash_table_size=w["T"], num_levels=w["L"], n_min=w["n_min"],
-                                   n_max=w["n_max"], MLP_hidden_layers_widths=w["mlp"],
-                                   HPD_hidden_layers_widths=w["hpd"], HPD_out_features=w["T"], feature_dim=w["F"],
-                                   topk_k=w["K"], should_keep_topk_only=w["topk_only"])
-    h, wd = w["lattice_hw"]
-    m = max(h, wd) - 1
-    net.set_coord_bounds((0.0, 0.0), ((h - 1) / m, (wd - 1) / m))
-    opt = FusedAdam(                                                            # functions.py:96-127, one launch
-        [{"params": net.encoding.parameters(), "lr": w["lr"]["encoding"], "weight_decay": w["wd"]["encoding"]},
-         {"params": net.HPD.parameters(), "lr": w["lr"]["hpd"], "weight_decay": w["wd"]["hpd"]},
-         {"params": net.mlp.parameters(), "lr": w["lr"]["mlp"], "weight_decay": w["wd"]["mlp"]}],
-        betas=(0.9, 0.99), eps=1e-15)
-    dp.enable_gradient_allreduce()          # N > 1: one in-place NCCL all-reduce of the flat gradient buffer
-
-    x_np, y_np = make_inputs(w, 65535, rank)
-    x_host, y_host = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(y_np).pin_memory()
-    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-    loss_host = torch.zeros(1).pin_memory()
-    rows = 4 * w["P"] * world
-
-    def step(x, y):
-        opt.zero_grad(set_to_none=True)
-        rgb, probs, idx, _ = net(x, 1.0)
-        colsum = dp.all_reduce_colsum(probs.colsum) if world > 1 else probs.colsum
-        loss, _, _ = total_loss(rgb, y, colsum, rows, w["gamma"], w["epsilon"], w["l_mse"], w["l_js_kl"])
-        loss.backward()
-        opt.step()
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
-
-    # ---- warm-up (eager) ----
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev)
-    barrier()
-    n0 = launch_count()
-    step(x_dev, y_dev)
-    torch.cuda.synchronize()
-    launches_per_step = launch_count() - n0
+    R = Runner(torch, dist, name, w, rank, world, dev)
+    graph = (not args.eager) and w["T"] <= 4096
+    peer = None
+    if world > 1:
+        n_params = sum((p.numel() + 3) & ~3 for p in R.net._parameters_flat())
+        peer = verify_peer_allreduce(torch, dist, dp, dev, [w["L"] * (w["K"] if w["topk_only"] else w["T"]), n_params])
 
     sampler = ClockSampler(local)
     sampler.start()
-
-    # ---- eager module API end to end (what the reference's own train_step does with the drop-in module) ----
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        xd = x_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True)
-        loss = step(xd, yd)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    barrier()
-    e2e_eager_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    del loss, xd, yd          # (the last eager loss would keep default-stream AccumulateGrad nodes alive at capture)
-
-    # ---- per-kernel device times (eager pass, CUDA events around every C-ABI call) -> dominant kernel ----
-    prof = CallProfiler(torch)
-    _lib.PROFILER = prof
-    from collision_handling_in_instantngp_b200 import ops as _ops
-    _ops.CONCURRENT = False          # serial schedule for this pass only: an event pair around a call on a forked side
-    for _ in range(args.steps):      # stream would also time the wait for the fork point
-        flush.zero_()
-        step(x_dev, y_dev)
-    _ops.CONCURRENT = True
-    _lib.PROFILER = None
-    agg = prof.summary()
-    lat = net.last_state.lat
-    ids = net.last_state.node_ids
-    w = dict(w, _active_nodes=None if ids is None else int(ids.shape[0]))
-    barrier()
-
-    # ---- the public fast path: the whole step (our kernels, fused Adam, for N > 1 the two NCCL all-reduces)
-    #      captured once in a CUDA graph over static input buffers (trainer.GraphedTrainer) ----
-    trainer, launch_mode = None, "eager"
-    if not args.eager and w["T"] <= 4096:
-        trainer = GraphedTrainer(net, opt, points=w["P"], gamma=w["gamma"], epsilon=w["epsilon"], l_mse=w["l_mse"],
-                                 l_js_kl=w["l_js_kl"], warmup_steps=3, sample_x=x_dev, sample_y=y_dev)
-        launch_mode = "cuda_graph"
-        for _ in range(max(args.warmup, 3)):
-            trainer.replay()
-        torch.cuda.synchronize()
-
-    # ---- the device-timed region: inputs resident in HBM, CUDA events around every step, L2 flushed between ----
-    barrier()
-    evs = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        if trainer is not None:
-            trainer.replay()
-        else:
-            step(x_dev, y_dev)
-        b.record()
-        evs.append((a, b))
-    barrier()
-    dev_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-
-    # ---- end to end through the public API with HOST buffers: every step copies the batch in from pinned host
-    #      memory and reads the loss back (wall clock, max over ranks).  GraphedTrainer.step_pipelined double-buffers
-    #      the inputs: the copy of batch t+1 overlaps the replay of step t, and the loss of step t is handed to the
-    #      caller (as a host float) at step t+1; flush() inside the timed region collects the last one ----
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        if trainer is not None:
-            trainer.step_pipelined(x_host, y_host)
-        else:
-            loss = step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-    if trainer is not None:
-        trainer.flush()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    prof_steps = min(args.steps, 3 if w["P"] * w["T"] >= 2 ** 34 else args.steps)
+    m = measure(torch, dist, R, args.steps, args.warmup, profile=prof_steps, eager_e2e=graph, graph=graph, flush=flush)
     clocks = sampler.stop()
-
-    per_name = {}
-    for (name, key), (t, n) in agg.items():
-        bound, amount = algorithmic_cost(name, key, w, lat)
-        e = per_name.setdefault(name, dict(ms=0.0, n=0, amount=0.0, bound=bound))
-        e["ms"] += t; e["n"] += n; e["amount"] += amount * n
-    total_kernel_ms = sum(e["ms"] for e in per_name.values())
-    top = max(per_name.items(), key=lambda kv: kv[1]["ms"])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    tc_peak = peaks.get("bf16_tflops", 1590.0)
-    peak_src = "measured" if peaks else "fallback"
-    tname, te = top
-    per_launch_s = te["ms"] / te["n"] / 1e3
-    per_launch_amount = te["amount"] / te["n"]
-    if te["bound"] == "hbm":
-        achieved, peak, unit = per_launch_amount / per_launch_s / 1e9, hbm_peak, "GB/s"
-    else:
-        achieved, peak, unit = per_launch_amount / per_launch_s / 1e12, tc_peak, "TFLOP/s"
-    roofline = {"bound": te["bound"], "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC.get((args.workload, tname)), "kernel": tname,
-                "useful_tflops": useful_tflops(tname, achieved, w),
-                "launches_per_step": te["n"] / args.steps,
-                "share_of_step_kernel_time": te["ms"] / total_kernel_ms, "peak_source": peak_src,
-                "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 5) for k, v in
-                                        sorted(per_name.items(), key=lambda kv: -kv[1]["ms"])}}
-
-    # max over ranks
+    wp = dict(w, P=R.local_points, _active_nodes=m["hpd_rows_this_rank"])
+    roofline = roofline_of(m, wp, prof_steps, name)
+    dev_ms, e2e_ms, e2e_eager_ms = m["dev_ms"], m["e2e_ms"], m.get("e2e_eager_ms", m["e2e_ms"])
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms, e2e_eager_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms, e2e_eager_ms = float(t[0]), float(t[1]), float(t[2])
-
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_P = args.cpu_sample or w["cpu_sample"]
-        sec = time_cpu_port(w, sample_P, 65535, steps=3, warmup=1)
-        cpu_base = {"value": sample_P / sec, "unit": "samples/s", "cores": cpu_threads(), "kind": "port",
-                    "sample": f"{sample_P} of the workload's {w['P']} coordinates per step, 3 steps after 1 warm-up, "
-                              "oracle/torch_port.py (PyTorch-CPU restatement of the reference: same ATen ops + autograd) "
-                              "forward+loss+backward+Adam"}
+        dp.check_exchanges()
+    total = R.total_points
+    lat = m["lat"]
+    line = None
     if rank == 0:
-        total = w["P"] * world
         line = {
-            "metric": "train samples/sec (fwd+bwd GNGF hash encode+MLP)", "value": total / (dev_ms / 1e3),
-            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "points_per_gpu_step": w["P"], "levels": w["L"],
-                       "table_size": w["T"], "topk_k": w["K"], "feature_dim": w["F"], "hpd": [2, *w["hpd"], w["T"]],
-                       "decoder": [w["L"] * w["F"], *w["mlp"], 3], "step": "forward+loss+backward+Adam",
-                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"dp{world}",
-                       "launch_mode": launch_mode,
-                       "lattice_nodes": lat.num_nodes, "level_nodes": lat.num_level_nodes,
-                       "active_nodes": w["_active_nodes"] or lat.num_nodes},
+            "metric": METRIC, "value": total / (dev_ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": w["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": static_config(name, w, world),
+            "run": {"points_this_rank": R.local_points, "launch_mode": m["launch_mode"],
+                    "l2": "flushed between timed steps (256 MiB write)", "lattice_nodes": lat.num_nodes,
+                    "level_nodes": lat.num_level_nodes, "hpd_nodes_listed": m["listed_nodes"] or lat.num_nodes,
+                    "hpd_rows_rank0": m["hpd_rows_this_rank"] or lat.num_nodes,
+                    "node_parallel_hpd": bool(world > 1 and R.net.last_state.shard is not None)},
             "e2e": {"value": total / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
-                    "path": ("trainer.GraphedTrainer.step_pipelined(x_host, y_host): pinned host batch copied into the idle "
-                             "one of two static buffer sets on a copy stream, CUDA-graph replay of "
-                             "forward+loss+backward+Adam, loss copied to pinned host memory and returned one step later, "
-                             "every step; flush() inside the timed region"
-                             if trainer is not None else
-                             "module API, eager, pinned host inputs copied in and loss read back every step"),
+                    "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": 4, "path": m["e2e_path"],
                     "eager_module_api": {"value": total / (e2e_eager_ms / 1e3), "unit": "samples/s",
                                          "ms_per_step": e2e_eager_ms,
                                          "path": "net(x) / loss / backward / Adam driven eagerly from Python, as the "
                                                  "reference's train_step drives the drop-in module"}},
-            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+            "gpu_launches": int(m["launches_per_step"] * args.steps), "gpu_launches_per_step": int(m["launches_per_step"]),
             "clocks": clocks, "roofline": roofline,
         }
-        if cpu_base is not None:
-            line["cpu_baseline"] = cpu_base
+        if peer is not None:
+            line["peer_allreduce_verified"] = peer["verified"]
+            line["peer_allreduce_check"] = peer
+
+    # ---- N = 1: the other named configurations in the same process, then the reference legs ----
+    if world == 1 and not args.no_secondary:
+        del R, m
+        gc.collect()
+        torch.cuda.empty_cache()
+        secondary = {}
+        for sname in [s for s in args.secondary.split(",") if s and s != name]:
+            sw = dict(WORKLOADS[sname])
+            S = Runner(torch, dist, sname, sw, 0, 1, dev)
+            sgraph = sw["T"] <= 4096
+            ssteps = args.steps if sgraph else min(args.steps, 5)
+            sm = measure(torch, dist, S, ssteps, 3, profile=0, eager_e2e=False, graph=sgraph, flush=flush)
+            secondary[sname] = {"names": sw["names"], "value": S.total_points / (sm["dev_ms"] / 1e3), "unit": "samples/s",
+                                "ms_per_step": sm["dev_ms"], "steps": ssteps, "launch_mode": sm["launch_mode"],
+                                "e2e": {"value": S.total_points / (sm["e2e_ms"] / 1e3), "unit": "samples/s",
+                                        "ms_per_step": sm["e2e_ms"], "h2d_bytes_per_step": sm["h2d_bytes"],
+                                        "d2h_bytes_per_step": 4},
+                                "config": static_config(sname, sw, 1), "lattice_nodes": sm["lat"].num_nodes}
+            del S, sm
+            gc.collect()
+            torch.cuda.empty_cache()
+        line["secondary"] = secondary
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        gc.collect()
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_reference_record(w, steps=3, warmup=1, sample_P=args.cpu_sample)
+        if reference_available():
+            pts = gpu_reference_points(w)
+            r = time_reference(w, "cuda", pts, steps=5, warmup=2)
+            if r and "error" not in r:
+                line["gpu_eager_reference"] = {
+                    "value": r["samples_per_s"], "unit": "samples/s", "ms_per_step": r["sec_per_step"] * 1e3,
+                    "sample": f"{pts} of the workload's {w['P']} coordinates per step (largest power of two whose "
+                              f"(rows, T) tensors fit: peak {r.get('peak_mem_gb', 0):.1f} GB), 5 steps after 2 warm-up",
+                    "what": "the UNMODIFIED reference (baseline/_ref) on cuda:0: its ATen eager path, same step",
+                    "speedup_of_value": line["value"] / r["samples_per_s"]}
+            else:
+                line["gpu_eager_reference"] = {"unavailable": (r or {}).get("error", "no output")}
+    if rank == 0:
         print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
-        # tearing the NCCL communicator down after its collectives were captured in a CUDA graph was observed
-        # to hang; the line is out, so leave without the teardown
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        teardown(torch, dist)
+
+
+def teardown(torch, dist):
+    """Leave the process group cleanly: graphs and symmetric-memory users are gone by now (measure() deletes its
+    trainer), so the communicator can be destroyed.  A watchdog exits the process if the teardown does not return (a
+    captured NCCL collective was once observed to hang it)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    gc.collect()
+    torch.cuda.synchronize()
+    timer = threading.Timer(30.0, lambda: os._exit(0))
+    timer.daemon = True
+    timer.start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        timer.cancel()
 
 
 JSON_OUT = sys.stdout
@@ -526,10 +733,12 @@ def main():
     _keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--secondary", default="cfg2,cfg3", help="other configurations measured in the same run at N = 1")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="points per CPU-baseline step (0: the workload's default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the timed step in a CUDA graph")
@@ -540,26 +749,21 @@ def main():
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return
-        sample_P = args.cpu_sample or w["cpu_sample"]
-        sec = time_cpu_port(w, sample_P, 65535, steps=args.steps, warmup=args.warmup)
-        val = sample_P / sec
-        cores = cpu_threads()
-        sample = (f"{sample_P} of the workload's {w['P']} coordinates per step; oracle/torch_port.py (PyTorch-CPU "
-                  "restatement of the reference: same ATen ops + autograd, all host threads) forward+loss+backward+Adam")
+        # the reference's CPU path on the box's host cores, on a bounded sample of OUR arm's configuration (the sample
+        # is sized so that W + K steps end within a few minutes: cpu_sample in WORKLOADS)
+        steps, warmup = args.steps, args.warmup
+        rec = cpu_reference_record(w, steps=steps, warmup=warmup, sample_P=args.cpu_sample)
         print(json.dumps({
-            "impl": "reference", "metric": "train samples/sec (fwd+bwd GNGF hash encode+MLP)", "value": val,
-            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "points_per_step_sample": sample_P, "levels": w["L"],
-                       "table_size": w["T"], "topk_k": w["K"], "feature_dim": w["F"],
-                       "step": "forward+loss+backward+Adam"},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+            "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": static_config(args.workload, w, args.gpus),
+            "cpu_baseline": rec,
+            "e2e": {"value": rec["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }), file=JSON_OUT, flush=True)
         return
-    run_ours(args, w)
+    run_ours(args)
 
 
 if __name__ == "__main__":
