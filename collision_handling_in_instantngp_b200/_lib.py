@@ -117,6 +117,7 @@ SIGNATURES = {
                                  _P, _P, _P, _P, _P, _P, _P, _P]),
     "gngf_peer_allreduce": (c_int, [_P, _P, c_int32, c_int32, _P, _P, c_int64, c_int64, c_int32, c_float, _P, _P]),
     "gngf_peer_allreduce_set_timeout_ms": (c_int, [c_int64]),
+    "gngf_counts_per_level": (c_int, [_P, c_int64, Lattice, _P, c_int64, c_int64, _P, _P, _P, _P]),
     "gngf_adam_step": (c_int, [POINTER(AdamTensor), c_int32, c_float, c_float, c_float, _P, _P]),
     "gngf_loss_fwd_bwd": (c_int, [_P, _P, c_int64, _P, c_int32, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   _P, _P, _P, _P, _P]),

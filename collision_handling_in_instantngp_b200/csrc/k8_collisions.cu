@@ -70,9 +70,78 @@ static int count_distinct(const T* idx, int64_t P, int L, int V, int C, int64_t 
   return check_launch();
 }
 
+// ---- f-4: _calc_counts_per_level (models.py:530-566) -----------------------------------------------------------------
+// The reference de-duplicates, per level, the rows "p (v xy)" -- the 8 corner coordinates of a point's grid cell -- with
+// np.unique(axis=0, return_index=True) on the host, and then indexes the FLATTENED "(p v)" slot vector with the
+// returned first-occurrence POINT indices (models.py:556-558): for every distinct cell the slot counted is that of
+// corner (j % 4) of point (j / 4), j = first point (batch order) in the cell.  Two passes here: (1) per (point, level)
+// an atomicMin of the point index into the cell's entry (cells are indexed like the level nodes of their floor
+// corner), (2) per cell with an entry, one histogram increment.  Exact, order-free.
+__global__ void __launch_bounds__(256)
+    cell_first_point_kernel(const float* __restrict__ grid, int64_t P, const __grid_constant__ gngf_lattice lat,
+                            int32_t* __restrict__ first, int32_t* __restrict__ outliers) {
+  const int L = lat.num_levels;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= P * L) return;
+  const int64_t p = i / L;
+  const int l = static_cast<int>(i - p * L);
+  // grid (P,2,L,4): the floor corner is v = 0
+  const float fx = grid[((p * 2 + 0) * L + l) * 4], fy = grid[((p * 2 + 1) * L + l) * 4];
+  const int a = static_cast<int>(fx) - lat.lox[l], b = static_cast<int>(fy) - lat.loy[l];
+  if (!(fx == floorf(fx) && fy == floorf(fy)) || a < 0 || a >= lat.lwx[l] || b < 0 || b >= lat.lwy[l]) {
+    *outliers = 1;
+    return;
+  }
+  atomicMin(first + lat.loff[l] + static_cast<int64_t>(a) * lat.lwy[l] + b, static_cast<int32_t>(p));
+}
+
+__global__ void __launch_bounds__(256)
+    cell_slot_histogram_kernel(const int32_t* __restrict__ first, const __grid_constant__ gngf_lattice lat,
+                               const int64_t* __restrict__ hashed, int64_t stride, int64_t P, int64_t T,
+                               int32_t* __restrict__ hist, int32_t* __restrict__ outliers) {
+  const int l = blockIdx.y;
+  const int L = lat.num_levels;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l]) return;
+  const int32_t j = first[lat.loff[l] + i];
+  if (j == 0x7f7f7f7f) return;   // (the memset pattern: no point in this cell)
+  // element j of "p l v -> l (p v)": point j / 4, corner j % 4
+  const int64_t slot = hashed[(((j >> 2) * static_cast<int64_t>(L) + l) * 4 + (j & 3)) * stride];
+  if (slot < 0 || slot >= T) {
+    *outliers = 1;
+    return;
+  }
+  atomicAdd(hist + static_cast<int64_t>(l) * T + slot, 1);
+}
+
 }  // namespace gngf
 
 extern "C" {
+
+int gngf_counts_per_level(const float* grid, int64_t P, gngf_lattice lat, const int64_t* hashed, int64_t hashed_stride,
+                          int64_t T, int32_t* first, int32_t* hist, int32_t* outliers, void* stream) {
+  if (P < 0 || P >= 0x7f7f7f7fll || T <= 0 || hashed_stride <= 0 || lat.num_levels <= 0 ||
+      lat.num_levels > GNGF_MAX_LEVELS || !first || !hist || !outliers || (P > 0 && (!grid || !hashed)))
+    return GNGF_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = gngf::as_stream(stream);
+  const int L = lat.num_levels;
+  const int64_t S = lat.loff[L];
+  if (cudaMemsetAsync(first, 0x7f, sizeof(int32_t) * S, st) != cudaSuccess) return gngf::check_launch();   // 0x7f7f7f7f
+  if (cudaMemsetAsync(hist, 0, sizeof(int32_t) * L * T, st) != cudaSuccess) return gngf::check_launch();
+  if (cudaMemsetAsync(outliers, 0, sizeof(int32_t), st) != cudaSuccess) return gngf::check_launch();
+  if (P == 0) return GNGF_OK;
+  gngf::cell_first_point_kernel<<<static_cast<unsigned>(gngf::ceil_div(P * L, 256)), 256, 0, st>>>(grid, P, lat, first,
+                                                                                                 outliers);
+  gngf::note_launch();
+  int rc = gngf::check_launch();
+  if (rc) return rc;
+  int64_t box = 0;
+  for (int l = 0; l < L; ++l) box = std::max<int64_t>(box, static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l]);
+  dim3 g(static_cast<unsigned>(gngf::ceil_div(box, 256)), L);
+  gngf::cell_slot_histogram_kernel<<<g, 256, 0, st>>>(first, lat, hashed, hashed_stride, P, T, hist, outliers);
+  gngf::note_launch();
+  return gngf::check_launch();
+}
 
 int64_t gngf_count_distinct_workspace_words(int32_t L, int32_t C, int64_t range) {
   return gngf::ceil_div(range, 32) * C * L;

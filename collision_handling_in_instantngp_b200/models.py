@@ -373,15 +373,49 @@ class GeneralNeuralGaugeFields(nn.Module):
 
     @torch.no_grad()
     def _calc_counts_per_level(self, hash: torch.Tensor, grid: torch.Tensor):
-        """Diagnostic histogram (models.py:530-566), host numpy like the reference; runs on histogram epochs only."""
+        """Diagnostic histogram (models.py:530-566): per level {slot: number of distinct grid cells counted for it},
+        with the reference's own indexing (first point of each distinct cell -> element of the flattened "(p v)" slot
+        vector).  The reference de-duplicates on the host (np.unique(axis=0) per level); here two GPU passes
+        (k8_collisions.cu) and one (L,T) histogram read-back.  Inputs that are not grid corners of this model's levels
+        (or not CUDA tensors) take the reference's host route."""
+        L = self._num_levels
+        if grid.is_cuda and hash.is_cuda and grid.dim() == 4 and tuple(grid.shape[1:]) == (2, L, 4):
+            # corners of x in [0,1] (main.py:48-49); wider boxes as the corners demand
+            try:
+                lat = self._counts_lattice(grid)
+            except ValueError:                       # corners too far apart for a lattice box
+                lat = None
+            hist = None
+            if lat is not None and lat.num_level_nodes <= 2 ** 30:
+                hist, outliers = ops.counts_per_level(grid, lat, hash, self._hash_table_size)
+            if hist is not None and int(outliers.item()) == 0:
+                h = hist.cpu().numpy()
+                out = []
+                for level in range(L):
+                    nz = np.nonzero(h[level])[0]
+                    out.append({int(k): int(h[level][k]) for k in nz})
+                return out
         P = grid.shape[0]
-        rearranged = grid.permute(2, 0, 3, 1).reshape(self._num_levels, P, -1).cpu().numpy()   # "p xy l v -> l p (v xy)"
-        vertices = hash.permute(1, 0, 2).reshape(self._num_levels, -1).cpu().numpy()           # "p l v -> l (p v)"
+        rearranged = grid.permute(2, 0, 3, 1).reshape(L, P, -1).cpu().numpy()                  # "p xy l v -> l p (v xy)"
+        vertices = hash.permute(1, 0, 2).reshape(L, -1).cpu().numpy()                          # "p l v -> l (p v)"
         out = []
-        for level in range(self._num_levels):
+        for level in range(L):
             _, first = np.unique(rearranged[level], axis=0, return_index=True)
             out.append(dict(Counter(vertices[level][first].tolist())))
         return out
+
+    def _counts_lattice(self, grid: torch.Tensor):
+        """Lattice whose level boxes hold every corner of `grid`: the [0,1] box of the image task, or -- when the
+        coordinates were batch-normalised (params.should_batchnorm_data) -- the box of the corners themselves."""
+        if self._coord_bounds is not None:
+            return self._lattice_cache.get(self._coord_bounds) or build_lattice(self._n_ls_host, *self._coord_bounds)
+        lo = grid[:, :, :, 0].amin(dim=0)                                                       # (2, L) floor corners
+        hi = grid[:, :, :, 0].amax(dim=0)
+        n = torch.from_numpy(self._n_ls_host.astype(np.float32)).to(grid.device)
+        # coordinates that reproduce these corner ranges on every level: (corner + 0.5) / n_l lies inside the cell
+        lo_c = ((lo + 0.5) / n).min(dim=1).values.tolist()
+        hi_c = ((hi + 0.5) / n).max(dim=1).values.tolist()
+        return build_lattice(self._n_ls_host, (min(lo_c[0], 0.0), min(lo_c[1], 0.0)), (max(hi_c[0], 1.0), max(hi_c[1], 1.0)))
 
     @torch.no_grad()
     def calc_hash_collisions(self, indices: torch.Tensor):

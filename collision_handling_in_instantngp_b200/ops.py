@@ -302,6 +302,28 @@ def count_distinct(indices: torch.Tensor, value_range: int):
     return uniq, outliers
 
 
+def counts_per_level(grid: torch.Tensor, lat: Lattice, hashed: torch.Tensor, table_size: int):
+    """_calc_counts_per_level (models.py:530-566) on the GPU: grid (P,2,L,4) fp32 corners, hashed (P,L,4) int64 slots
+    (any view with a uniform element stride, e.g. idx_topk[..., 0]) -> (hist (L,T) int32, outliers flag tensor)."""
+    _require_cuda(grid, "grid")
+    grid = _f32c(grid)
+    P, L = grid.shape[0], lat.num_levels
+    if hashed.dtype != torch.int64:
+        hashed = hashed.long()
+    # (P,L,4) with strides (L*4*s, 4*s, s): a column of a contiguous (P,L,4,K) tensor, or a contiguous (P,L,4) tensor
+    s = hashed.stride(2) if P > 0 else 1
+    if P > 0 and (hashed.stride(1) != 4 * s or hashed.stride(0) != L * 4 * s or s < 1):
+        hashed = hashed.contiguous()
+        s = 1
+    dev = grid.device
+    first = torch.empty(lat.num_level_nodes, dtype=torch.int32, device=dev)
+    hist = torch.empty((L, int(table_size)), dtype=torch.int32, device=dev)
+    outliers = torch.empty(1, dtype=torch.int32, device=dev)
+    call("gngf_counts_per_level", grid.data_ptr(), P, lat, hashed.data_ptr(), s, int(table_size), first.data_ptr(),
+         hist.data_ptr(), outliers.data_ptr(), _stream())
+    return hist, outliers
+
+
 def gather_rows(x, lat: Lattice, uvals: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(P,L,4,N) rows of a per-node array; int32 input gives the int64 API dtype."""
     P, N = x.shape[0], uvals.shape[1]

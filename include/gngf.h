@@ -344,6 +344,16 @@ int gngf_count_distinct_f32(const float* indices, int64_t P, int32_t L, int32_t 
 int gngf_count_distinct_i64(const int64_t* indices, int64_t P, int32_t L, int32_t V, int32_t C, int64_t range,
                             uint32_t* bitmap, int32_t* uniq, int32_t* outliers, void* stream);
 
+/* ---- f-4: _calc_counts_per_level (models.py:530-566) -----------------------------------------------------------
+ * grid (P,2,L,4) fp32 grid corners (gngf_corners_fwd); hashed: int64 slot of (point p, level l, corner v) at
+ * hashed[((p*L + l)*4 + v) * hashed_stride] (stride K selects the best top-k column of a (P,L,4,K) index tensor, 1 a
+ * (P,L,4) hash tensor).  hist (L,T) int32 = per level, for every DISTINCT grid cell, one count for the slot
+ * hashed_flat[l][j], j = index of the first point (batch order) in that cell -- the reference's np.unique(axis=0,
+ * return_index=True) + flattened "(p v)" indexing, as is.  first: lat.loff[L] int32 of scratch; *outliers = 1 when a
+ * corner lies outside the lattice box or a slot outside [0,T) (the caller then counts on the host).               */
+int gngf_counts_per_level(const float* grid, int64_t P, gngf_lattice lat, const int64_t* hashed, int64_t hashed_stride,
+                          int64_t T, int32_t* first, int32_t* hist, int32_t* outliers, void* stream);
+
 /* ---- f-3: fused Adam over all parameter tensors (functions.py:96-127, 281) ------------------------------------------
  * One launch: for every tensor  g' = g + weight_decay p;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
  *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)   with t = *step + 1  (torch.optim.Adam semantics,

@@ -376,7 +376,9 @@ def test_streaming_hpd_matches_unfused(U, T, Kd, K):
     srt = -np.sort(-p_ref, axis=-1)
     gap = (srt[:, :K] - srt[:, 1:K + 1]).min(-1) / srt[:, 0]
     ok = gap > 2e-5                                                  # rows whose selection is not a rounding-level tie
-    assert ok.mean() > 0.9
+    # measured rate of such ties on these inputs: a few 1e-4 of the rows (5 order statistics of T logits per row)
+    print(f"rows exempt as rounding-level ties: {int((~ok).sum())} of {U}")
+    assert (~ok).sum() <= max(1, 0.005 * U)
     assert np.array_equal(utopi.cpu().numpy()[ok], i_ref[ok])
     assert rel_err(utopv.cpu().numpy()[ok], v_ref[ok]) < 1e-5
     assert rel_err(rmax.cpu().numpy(), logits.max(-1)) < 1e-5
@@ -384,6 +386,86 @@ def test_streaming_hpd_matches_unfused(U, T, Kd, K):
     # every selected index is a true top-k member up to the tie tolerance, on all rows
     sel = np.take_along_axis(p_ref, utopi.cpu().numpy().astype(np.int64), -1)
     assert (sel >= srt[:, K - 1:K] * (1 - 2e-5)).all()
+
+
+def test_streaming_hpd_at_the_size_of_configs2():
+    """The streaming path at the size BASELINE.json configs[2] names -- 173 400 lattice nodes (macaw lattice, 16 levels)
+    x T = 2^19 slots: 4 096 column tiles, Kahan row sums over 5e5 terms, the column-split merge -- against a float64
+    evaluation of EVERY row (torch fp64 on the GPU, row chunks): selections, probabilities, softmax statistics, and
+    the three gradients of the fused backward (dh, dW3, db3) at full size.
+    Bars: indices exact on every row that an fp32 evaluation can decide (fp64 gap among the top K+1 logits > 2e-6;
+    the exempt rows are counted), probabilities / row sums 1e-5, gradients 1e-4."""
+    from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+    torch.manual_seed(65535)
+    T, K, Kd = 2 ** 19, 4, 128
+    net = GeneralNeuralGaugeFields(input_dim=2, hash_table_size=T, num_levels=16, n_min=16, n_max=508,
+                                   MLP_hidden_layers_widths=[64, 64], HPD_hidden_layers_widths=[32, 64, 128],
+                                   HPD_out_features=T, topk_k=K, should_keep_topk_only=True)
+    lat = build_lattice(level_resolutions(16, 508, 16), (0.0, 0.0), (1.0, 338 / 507))
+    U = lat.num_nodes
+    assert U == 173400
+    ws, bs = net.HPD.weights()
+    with torch.no_grad():
+        # the real activations of the last hidden layer on the real lattice (random-init HPD, nn.Linear bounds)
+        h = torch.empty((U, 32), device=DEV)
+        ops.call("gngf_hpd_first_layer_fwd_nodes", lat, None, U, ws[0].data_ptr(), bs[0].data_ptr(), 32, ops.ACT_RELU,
+                 h.data_ptr(), ops._stream())
+        for i in (1, 2):
+            h = ops.linear_fwd(h, ws[i], bs[i], ops.ACT_RELU)
+        w, b = ws[3].detach().contiguous(), bs[3].detach().contiguous()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    dtv = torch.randn((U, K), generator=g, device=DEV)
+    hp, wp = ops.split_bf16x3(h), ops.split_bf16x3(w)
+    utopv, utopi, rmax, rsum = ops.hpd_stream_fwd(h, w, b, K, h_planes=hp, w_planes=wp)
+    dw = torch.zeros((T, Kd), device=DEV)
+    db = torch.zeros(T, device=DEV)
+    dh = ops.hpd_stream_bwd(_flat_lattice(U), h, w, b, hp, wp, utopv, utopi, dtv, None, None, rmax, rsum, dw, db)
+    torch.cuda.synchronize()
+    del hp, wp
+
+    w64, b64 = w.double(), b.double()
+    dw64 = torch.zeros((T, Kd), dtype=torch.float64, device=DEV)
+    db64 = torch.zeros(T, dtype=torch.float64, device=DEV)
+    CH = 1024
+    wrong, undecidable, worst = 0, 0, dict(topv=0.0, rsum=0.0, rmax=0.0, dh=0.0)
+    dh_scale = float(dh.abs().max())
+    for r0 in range(0, U, CH):
+        r1 = min(U, r0 + CH)
+        h64 = h[r0:r1].double()
+        z = torch.addmm(b64, h64, w64.t())                                   # (rows, T) fp64
+        zt, it = z.topk(K + 1, dim=-1)
+        m = zt[:, 0:1]
+        z.sub_(m).exp_()                                                     # e = exp(z - max), in place
+        ssum = z.sum(-1, keepdim=True)
+        ti = utopi[r0:r1].long()
+        same = (ti == it[:, :K]).all(-1)
+        gap = (zt[:, :-1] - zt[:, 1:]).min(-1).values
+        decidable = gap > 2e-6
+        wrong += int((~same & decidable).sum())
+        undecidable += int((~decidable).sum())
+        p_sel = z.gather(1, ti) / ssum                                       # probabilities of OUR selection
+        pv_ref = zt[:, :K].sub(m).exp() / ssum
+        ok = same
+        worst["topv"] = max(worst["topv"], float(((utopv[r0:r1].double() - pv_ref).abs() / pv_ref)[ok].max()))
+        worst["rsum"] = max(worst["rsum"], float(((rsum[r0:r1].double() - ssum[:, 0]).abs() / ssum[:, 0]).max()))
+        worst["rmax"] = max(worst["rmax"], float((rmax[r0:r1].double() - m[:, 0]).abs().max()))
+        # backward in fp64, differentiating the kernel's own selection: dl = -<g, p_sel> p + scatter(p_sel g)
+        pg = p_sel * dtv[r0:r1].double()
+        z.mul_(-pg.sum(-1, keepdim=True) / ssum)                             # dl, in place
+        z.scatter_add_(1, ti, pg)
+        dw64.addmm_(z.t(), h64)
+        db64.add_(z.sum(0))
+        dh64 = (z @ w64) * (h64 > 0)
+        worst["dh"] = max(worst["dh"], float((dh[r0:r1].double() - dh64).abs().max()) / dh_scale)
+        del z, dh64
+    print(f"\nconfigs[2] size (U = {U}, T = 2^19): rows with a wrong selection {wrong}, rows no fp32 evaluation can decide "
+          f"{undecidable}; worst relative errors {worst}")
+    assert wrong == 0
+    assert undecidable <= 0.001 * U
+    assert worst["topv"] < 1e-5 and worst["rsum"] < 1e-5 and worst["rmax"] < 1e-5
+    assert worst["dh"] < 1e-4
+    assert float((dw.double() - dw64).abs().max() / dw64.abs().max()) < 1e-4
+    assert float((db.double() - db64).abs().max() / db64.abs().max()) < 1e-4
 
 
 def _flat_lattice(U):

@@ -10,7 +10,8 @@ import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
 import gngf_oracle as O  # noqa: E402
-from golden_util import ALL_CASES, GNGF_CASES, load, loss_cfg, oracle_cfg, params_of, rel_err  # noqa: E402
+from golden_util import (ALL_CASES, COUNTS_CASES, GNGF_CASES, golden_counts, load, loss_cfg, oracle_cfg, params_of,  # noqa: E402
+                         rel_err)
 from parity_util import decoder_masks, build_net, reset_flags, run_step  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -106,6 +107,28 @@ def test_full_size_cfg2_against_oracle():
         assert rel_err(out["grads"][f"mlp.{i}.0.bias"], grads["mlp_b"][i]) < GRAD_TOL
 
 
+@pytest.mark.parametrize("name", COUNTS_CASES)
+def test_counts_per_level_match_reference(name):
+    """f-4: forward(..., should_calc_counts=True) returns the reference's per-level histograms (models.py:431-439,
+    530-566) -- GPU de-duplication (k8_collisions.cu) instead of np.unique(axis=0) on the host."""
+    g = load(name)
+    net = build_net(g)
+    x = torch.from_numpy(g["x"]).cuda()
+    n0 = __import__("collision_handling_in_instantngp_b200").launch_count()
+    _, _, idx, counts = net(x, 1.0, should_calc_counts=True)
+    assert counts == golden_counts(g)
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    # ... and through the stand-alone method on materialised tensors, as a caller of the reference's API would
+    scaled, grid = net._scale_to_grid(x)
+    hashed = idx if g["cfg"]["use_hash"] else idx[..., 0]
+    assert net._calc_counts_per_level(hashed, grid) == golden_counts(g)
+    # a non-contiguous / odd-stride view takes the same route
+    assert net._calc_counts_per_level(hashed.clone(), grid) == golden_counts(g)
+    # inputs the kernel cannot place (corners outside every box) fall back to the reference's host route
+    far = grid + 1.0e6
+    assert sum(sum(d.values()) for d in net._calc_counts_per_level(hashed, far)) > 0
+
+
 def test_state_dict_keys_and_optimizer_groups():
     g = load("cfg2_small")
     net = build_net(g)
@@ -199,6 +222,58 @@ def test_active_node_evaluation_matches_reference_golden(name):
     assert rel_err(out["rgb"], out_box["rgb"]) < 2e-6             # (the split of T over CTAs follows the row count)
     for k in out["grads"]:
         assert rel_err(out["grads"][k], out_box["grads"][k]) < GRAD_TOL, k   # (two-plane products: ~1e-5 each)
+
+
+def test_active_nodes_on_a_large_lattice_equal_the_whole_box():
+    """Active-node evaluation at scale: the 8192-resolution lattice of BASELINE.json configs[3] (16 levels), a quarter
+    box (4097^2 = 16.8 M nodes, so that the whole-box evaluation it is compared with fits comfortably), 2^20 pixel-lattice
+    points: the touched-node list, the scatter back into (U, K) and the node-list backward against the evaluation of
+    every node of the box."""
+    from collision_handling_in_instantngp_b200 import ops
+    from collision_handling_in_instantngp_b200.loss import fused_total_loss
+    from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+    torch.manual_seed(65535)
+    T, K = 1024, 4
+    net = GeneralNeuralGaugeFields(input_dim=2, hash_table_size=T, num_levels=16, n_min=16, n_max=8192,
+                                   MLP_hidden_layers_widths=[64, 64], HPD_hidden_layers_widths=[32, 64, 128],
+                                   HPD_out_features=T, topk_k=K, should_keep_topk_only=True)
+    with torch.no_grad():
+        for t in net.encoding.tables():
+            t.mul_(300.0)                          # table gradients well above fp32 noise (as in the goldens)
+    half = 4096
+    net.set_coord_bounds((0.0, 0.0), (half / 8191, half / 8191))
+    rng = np.random.default_rng(3)
+    flat = rng.permutation((half + 1) * (half + 1))[: 2 ** 20]
+    x = torch.from_numpy(np.stack([flat // (half + 1), flat % (half + 1)], 1).astype(np.float32) / np.float32(8191)).cuda()
+    y = torch.from_numpy(rng.random((2 ** 20, 3), dtype=np.float32)).cuda()
+
+    def run(active):
+        ops.FORCE_ACTIVE_NODES = active
+        try:
+            net.zero_grad()
+            rgb, probs, idx, _ = net(x, 1.0)
+            loss, _, _ = fused_total_loss(rgb, y, probs.colsum, 4 * x.shape[0], -2.0, 1.0, 1.0, 1.0)
+            loss.backward()
+            st = net.last_state
+            n_ids = None if st.node_ids is None else int(st.node_ids.shape[0])
+            return (rgb.detach().clone(), idx.clone(), probs.colsum.detach().clone(), float(loss),
+                    {k: v.grad.detach().clone() for k, v in net.named_parameters() if v.grad is not None}, n_ids,
+                    st.lat.num_nodes)
+        finally:
+            ops.FORCE_ACTIVE_NODES = None
+
+    rgb_a, idx_a, cs_a, loss_a, g_a, n_a, U = run(True)
+    rgb_b, idx_b, cs_b, loss_b, g_b, n_b, _ = run(False)
+    assert U == (half + 2) ** 2 or U >= half * half
+    assert n_b is None and 0 < n_a < 0.75 * U
+    print(f"\nlattice nodes {U}, touched {n_a} ({n_a / U:.1%})")
+    assert torch.equal(idx_a, idx_b)
+    assert float((rgb_a - rgb_b).abs().max()) < 2e-6
+    assert float(((cs_a - cs_b).abs() / cs_b.abs()).max()) < 1e-5
+    assert abs(loss_a - loss_b) < 1e-5 * abs(loss_b)
+    for k in g_b:
+        err = float((g_a[k] - g_b[k]).abs().max() / (g_b[k].abs().max() + 1e-30))
+        assert err < GRAD_TOL, (k, err)
 
 
 @pytest.mark.parametrize("mix", [False, None])
