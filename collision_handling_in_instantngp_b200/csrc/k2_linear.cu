@@ -173,25 +173,43 @@ __global__ void __launch_bounds__(256) first_layer_fwd_kernel(const __grid_const
 }
 
 // dw0[j, :] += sum_r dz[r, j] * (cx, cy);  db0[j] += sum_r dz[r, j]
+// A block takes a contiguous run of rows; warp w walks rows r0 + w, r0 + w + 8, ... with lane = output unit (coalesced
+// 128-byte row reads, the node coordinate computed once per row and warp), the eight warps' partials meet in shared
+// memory and leave as one atomic per (block, unit, term).  (The first version walked the rows serially in n_out
+// threads: 18 ms for 30 M rows; this form streams dz at HBM speed.)
 __global__ void __launch_bounds__(256) first_layer_bwd_kernel(const __grid_constant__ gngf_lattice lat,
                                                               const int* __restrict__ node_ids, int64_t rows,
                                                               const float* __restrict__ dz, int n_out,
                                                               int64_t rows_per_block, float* __restrict__ dw0,
                                                               float* __restrict__ db0) {
+  __shared__ float part[8][3][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
-  for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+  for (int j0 = 0; j0 < n_out; j0 += 32) {
+    const int j = j0 + lane;
     float sx = 0.0f, sy = 0.0f, sb = 0.0f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const float g = dz[r * n_out + j];
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
       const int64_t u = node_ids ? node_ids[r] : r;
-      sx = fmaf(g, static_cast<float>(lat.ox + static_cast<int>(u / lat.wy)), sx);
-      sy = fmaf(g, static_cast<float>(lat.oy + static_cast<int>(u % lat.wy)), sy);
+      const int qx = static_cast<int>(u / lat.wy);
+      const float cx = static_cast<float>(lat.ox + qx), cy = static_cast<float>(lat.oy + static_cast<int>(u - int64_t(qx) * lat.wy));
+      const float g = j < n_out ? dz[r * n_out + j] : 0.0f;
+      sx = fmaf(g, cx, sx);
+      sy = fmaf(g, cy, sy);
       sb += g;
     }
-    atomicAdd(&dw0[j * 2 + 0], sx);
-    atomicAdd(&dw0[j * 2 + 1], sy);
-    atomicAdd(&db0[j], sb);
+    part[warp][0][lane] = sx;
+    part[warp][1][lane] = sy;
+    part[warp][2][lane] = sb;
+    __syncthreads();
+    if (warp < 3 && j < n_out) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][warp][lane];
+      if (warp == 2) atomicAdd(&db0[j], t);
+      else atomicAdd(&dw0[j * 2 + warp], t);
+    }
+    __syncthreads();
   }
 }
 
@@ -233,8 +251,8 @@ int gngf_hpd_first_layer_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, in
   if (U <= 0 || n_out <= 0 || rows < 0 || rows > U) return GNGF_ERR_INVALID_ARGUMENT;
   if (rows == 0) return GNGF_OK;
   // enough blocks to cover the chip even for a few hundred nodes
-  const int64_t rows_per_block = std::max<int64_t>(4, gngf::ceil_div(rows, 4 * gngf::sm_count()));
-  gngf::first_layer_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(rows, rows_per_block)), 128, 0,
+  const int64_t rows_per_block = std::max<int64_t>(8, gngf::ceil_div(rows, 8 * gngf::sm_count()));
+  gngf::first_layer_bwd_kernel<<<static_cast<unsigned>(gngf::ceil_div(rows, rows_per_block)), 256, 0,
                                  gngf::as_stream(stream)>>>(lat, node_ids, rows, dz, n_out, rows_per_block, dw0, db0);
   gngf::note_launch();
   return gngf::check_launch();

@@ -110,16 +110,14 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// grid (ceil(max level box / 256), L); thread per level node
-__global__ void __launch_bounds__(256)
-    node_features_bwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ gngf_tables tables,
-                             const __grid_constant__ gngf_tables tgrads, int64_t T, int F, int K, int mode,
-                             const float* __restrict__ utopv, const int32_t* __restrict__ utopi,
-                             const float* __restrict__ dnf, float* __restrict__ dtv) {
-  const int l = blockIdx.y;
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+// One level node: table scatter-add (into `tgrad`: the global gradient table, or a CTA-private copy of it in shared
+// memory) and the adjoint of the selected probabilities.
+template <bool SHARED>
+__device__ __forceinline__ void node_bwd(const gngf_lattice& lat, int l, int64_t i, const float* __restrict__ table,
+                                         float* tgrad, int F, int K, int mode, const float* __restrict__ utopv,
+                                         const int32_t* __restrict__ utopi, const float* __restrict__ dnf,
+                                         float* __restrict__ dtv) {
   const int wy = lat.lwy[l];
-  if (i >= static_cast<int64_t>(lat.lwx[l]) * wy) return;
   float d[GNGF_MAX_FEATURES];
   bool any = false;
 #pragma unroll
@@ -132,8 +130,6 @@ __global__ void __launch_bounds__(256)
   const int64_t u = global_node(lat, cx, cy);
   const float* tv = utopv + u * K;
   const int32_t* ti = utopi + u * K;
-  const float* table = tables.ptr[l];
-  float* tgrad = tgrads.ptr[l];
 
   // mix weights (same arithmetic as the forward node pass)
   float mx = 0.0f, norm = 1.0f;
@@ -157,7 +153,7 @@ __global__ void __launch_bounds__(256)
     for (int f = 0; f < GNGF_MAX_FEATURES; ++f)
       if (f < F) dw = fmaf(d[f], table[row + f], dw);
     dot = fmaf(dw, w, dot);
-    if (F == 2) {
+    if (!SHARED && F == 2) {
       red_add_v2(tgrad + row, d[0] * w, d[1] * w);
     } else {
 #pragma unroll
@@ -178,6 +174,48 @@ __global__ void __launch_bounds__(256)
     else if (mode == GNGF_MIX_WEIGHTED_AVG) g = (dw - dot) / norm;
     else g = dw;
     atomicAdd(dtv + u * K + k, g);
+  }
+}
+
+// grid (ceil(max level box / 256), L); thread per level node
+__global__ void __launch_bounds__(256)
+    node_features_bwd_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ gngf_tables tables,
+                             const __grid_constant__ gngf_tables tgrads, int64_t T, int F, int K, int mode,
+                             const float* __restrict__ utopv, const int32_t* __restrict__ utopi,
+                             const float* __restrict__ dnf, float* __restrict__ dtv) {
+  const int l = blockIdx.y;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l]) return;
+  node_bwd<false>(lat, l, i, tables.ptr[l], tgrads.ptr[l], F, K, mode, utopv, utopi, dnf, dtv);
+}
+
+// Small tables (T * F * 4 bytes fit shared memory: T = 2^14, F = 2 is 128 KB): millions of level nodes scatter-add into
+// a few thousand rows, and same-address reductions in the L2 serialise (64 ms at BASELINE.json configs[3] with T = 2^14:
+// 40 M touched level nodes into 16 x 16 384 rows).  A CTA keeps a private copy of its level's gradient table in shared
+// memory, walks its share of the level's nodes with shared-memory atomics, and adds the non-zero entries to the global
+// table once.  grid (ctas, L): CTA b of level l takes nodes b, b + ctas_l, ... in 512-node strides (ctas_l grows with the
+// level: coarse levels have a few hundred nodes).
+__global__ void __launch_bounds__(512)
+    node_features_bwd_private_kernel(const __grid_constant__ gngf_lattice lat, const __grid_constant__ gngf_tables tables,
+                                     const __grid_constant__ gngf_tables tgrads, int64_t T, int F, int K, int mode,
+                                     const float* __restrict__ utopv, const int32_t* __restrict__ utopi,
+                                     const float* __restrict__ dnf, float* __restrict__ dtv, int nodes_per_cta) {
+  extern __shared__ float tg_s[];
+  const int l = blockIdx.y;
+  const int64_t n = static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l];
+  const int64_t ctas = min(static_cast<int64_t>(gridDim.x), (n + nodes_per_cta - 1) / nodes_per_cta);
+  if (blockIdx.x >= ctas) return;
+  const int64_t TF = T * F;
+  for (int64_t e = threadIdx.x; e < TF; e += blockDim.x) tg_s[e] = 0.0f;
+  __syncthreads();
+  const float* table = tables.ptr[l];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += ctas * blockDim.x)
+    node_bwd<true>(lat, l, i, table, tg_s, F, K, mode, utopv, utopi, dnf, dtv);
+  __syncthreads();
+  float* tgrad = tgrads.ptr[l];
+  for (int64_t e = threadIdx.x; e < TF; e += blockDim.x) {
+    const float v = tg_s[e];
+    if (v != 0.0f) atomicAdd(tgrad + e, v);
   }
 }
 
@@ -253,6 +291,20 @@ int gngf_node_features_bwd(gngf_lattice lat, gngf_tables tables, gngf_tables tab
     return GNGF_ERR_INVALID_ARGUMENT;
   int64_t box = 0;
   for (int l = 0; l < lat.num_levels; ++l) box = std::max<int64_t>(box, static_cast<int64_t>(lat.lwx[l]) * lat.lwy[l]);
+  const size_t private_bytes = sizeof(float) * static_cast<size_t>(T) * F;
+  if (private_bytes <= 160 * 1024 && box >= (1 << 18)) {
+    // small table, many nodes: CTA-private gradient tables in shared memory (one CTA per SM and level)
+    if (cudaFuncSetAttribute(gngf::node_features_bwd_private_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(private_bytes)) != cudaSuccess)
+      return gngf::check_launch();
+    const int nodes_per_cta = 8192;
+    dim3 grid(static_cast<unsigned>(std::min<int64_t>(gngf::sm_count(), gngf::ceil_div(box, nodes_per_cta))),
+              lat.num_levels);
+    gngf::node_features_bwd_private_kernel<<<grid, 512, private_bytes, gngf::as_stream(stream)>>>(
+        lat, tables, table_grads, T, F, K, mix_mode, utopv, utopi, dnf, dtv, nodes_per_cta);
+    gngf::note_launch();
+    return gngf::check_launch();
+  }
   dim3 grid(static_cast<unsigned>(gngf::ceil_div(box, 256)), lat.num_levels);
   gngf::node_features_bwd_kernel<<<grid, 256, 0, gngf::as_stream(stream)>>>(lat, tables, table_grads, T, F, K,
                                                                             mix_mode, utopv, utopi, dnf, dtv);

@@ -53,6 +53,9 @@ CONCURRENT = True
 # (state.colsum_fork.side) and the backward joins it after the encoding's point pass, right before the column-sum
 # adjoint is consumed.  The column-sum branch then overlaps the decoder forward AND backward instead of gating the loss.
 DEFER_COLSUM_JOIN = False
+# The API output idx_topk (P,L,4,K) int64 (models.py:476-484) is a pure gather that nothing inside a training step reads
+# (8.6 GB per step at BASELINE.json configs[3]); callers that never look at it -- trainer.GraphedTrainer -- switch it off
+WANT_IDX_TOPK = True
 _SIDE_STREAMS = {}
 
 
@@ -609,10 +612,12 @@ class GNGFPath(torch.autograd.Function):
         else:
             hpd_forward_nodes(lat, hpd_w, hpd_b, K, dev, cfg, state, tables=tables)
             # API output idx_topk (P,L,4,K) int64: nothing in the step reads it -> side stream, joined at the end
-            state.idx_topk = torch.empty((P, L, 4, K), dtype=torch.int64, device=dev)
-            fork_idx = _Fork(dev, 0)
-            with fork_idx:
-                gather_rows(x, lat, state.utopi, out=state.idx_topk)
+            fork_idx = None
+            if WANT_IDX_TOPK:
+                state.idx_topk = torch.empty((P, L, 4, K), dtype=torch.int64, device=dev)
+                fork_idx = _Fork(dev, 0)
+                with fork_idx:
+                    gather_rows(x, lat, state.utopi, out=state.idx_topk)
             S = lat.num_level_nodes
             nfeat, state.nfeat = state.nfeat, None       # (not kept for the backward)
             if nfeat is None:
@@ -664,7 +669,8 @@ class GNGFPath(torch.autograd.Function):
                 h = linear_fwd(h, mlp_w[i], mlp_b[i], hidden_act if i < nm - 1 else ACT_SIGMOID)
                 acts.append(h)
         if not cfg.use_hash:
-            fork_idx.join()
+            if fork_idx is not None:
+                fork_idx.join()
             if DEFER_COLSUM_JOIN and fork_col.on:
                 state.colsum_fork = fork_col
             else:

@@ -103,10 +103,12 @@ class GraphedTrainer:
         # half of the loss) stays on its side stream until the backward needs its adjoint: it overlaps the decoder
         # forward, the MSE half of the loss, the decoder backward and the encoding's point pass
         ops.DEFER_COLSUM_JOIN = True
+        ops.WANT_IDX_TOPK = False          # the step never reads the (P,L,4,K) int64 index output: no gather in the graph
         try:
             rgb, probs, _, _ = self.net(self.xs[i], 1.0)
         finally:
             ops.DEFER_COLSUM_JOIN = False
+            ops.WANT_IDX_TOPK = True
         state = self.net.last_state
         fork = state.colsum_fork
         # under data parallelism `probs.colsum` already is the sum over ranks: the exchange happens inside the forward,

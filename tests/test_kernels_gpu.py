@@ -576,3 +576,50 @@ def test_fused_adam_matches_torch_adam():
         ob2.step()
     for a, b in zip(many_a, many_b):
         assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("levels,T,mix", [((300, 600), 512, 0), ((40, 700), 16384, 0), ((600,), 300, 1), ((600,), 256, 2)])
+def test_node_pass_backward_with_private_tables(levels, T, mix):
+    """gngf_node_features_bwd on lattices large enough for the CTA-private table path (shared-memory copies of a level's
+    gradient table, k5_encode_bwd.cu) against a float64 torch restatement: table gradients and the adjoint of the
+    selected probabilities, all three mix modes."""
+    from collision_handling_in_instantngp_b200 import _lib
+    F, K = 2, 4
+    lat = build_lattice(np.array(levels, dtype=np.int32))
+    L, U, S = lat.num_levels, lat.num_nodes, lat.num_level_nodes
+    assert max(lat.lwx[l] * lat.lwy[l] for l in range(L)) >= 1 << 18
+    g = torch.Generator(device=DEV).manual_seed(T + len(levels))
+    tables = [torch.randn((T, F), generator=g, device=DEV) for _ in range(L)]
+    tgrads = [torch.zeros((T, F), device=DEV) for _ in range(L)]
+    utopv = torch.rand((U, K), generator=g, device=DEV) * 0.5 + 0.01
+    utopi = torch.randint(0, T, (U, K), generator=g, device=DEV, dtype=torch.int32)
+    dnf = torch.randn((S, F), generator=g, device=DEV)
+    dnf[torch.rand(S, generator=g, device=DEV) < 0.3] = 0.0             # untouched level nodes
+    dtv = torch.zeros((U, K), device=DEV)
+    mode = [_lib.MIX_SOFTMAX, _lib.MIX_WEIGHTED_AVG, _lib.MIX_RAW][mix]
+    ops.call("gngf_node_features_bwd", lat, _lib.make_tables(tables), _lib.make_tables(tgrads), T, F, K, mode,
+             utopv.data_ptr(), utopi.data_ptr(), dnf.data_ptr(), dtv.data_ptr(), ops._stream())
+    torch.cuda.synchronize()
+    dtv_ref = torch.zeros((U, K), dtype=torch.float64, device=DEV)
+    for l in range(L):
+        wx, wy = lat.lwx[l], lat.lwy[l]
+        ii = torch.arange(wx * wy, device=DEV)
+        cx, cy = lat.lox[l] + ii // wy, lat.loy[l] + ii % wy
+        u = (cx - lat.ox) * lat.wy + (cy - lat.oy)
+        d = dnf[lat.loff[l]:lat.loff[l] + wx * wy].double()                       # (n, F)
+        tv, ti = utopv[u].double(), utopi[u].long()
+        if mix == 0:
+            w = torch.softmax(tv, -1)
+        elif mix == 1:
+            w = tv / tv.sum(-1, keepdim=True)
+        else:
+            w = tv
+        rows = tables[l].double()[ti]                                            # (n, K, F)
+        ref = torch.zeros((T, F), dtype=torch.float64, device=DEV)
+        ref.index_add_(0, ti.reshape(-1), (d[:, None, :] * w[:, :, None]).reshape(-1, F))
+        assert float((tgrads[l].double() - ref).abs().max() / ref.abs().max()) < 1e-5, l
+        dw = (rows * d[:, None, :]).sum(-1)                                      # (n, K)
+        dot = (dw * w).sum(-1, keepdim=True)
+        gk = w * (dw - dot) if mix == 0 else ((dw - dot) / tv.sum(-1, keepdim=True) if mix == 1 else dw)
+        dtv_ref.index_add_(0, u, gk)
+    assert float((dtv.double() - dtv_ref).abs().max() / dtv_ref.abs().max()) < 1e-5
