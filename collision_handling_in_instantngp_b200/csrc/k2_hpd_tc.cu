@@ -222,6 +222,19 @@ constexpr int A_KBLOCKS = 2;                             // resident A tile: K <
 constexpr uint32_t A_BYTES = A_KBLOCKS * PLANES * PLANE_BYTES;   // 96 KB
 constexpr uint32_t B_STAGE_BYTES = PLANES * PLANE_BYTES;         // 48 KB: one k-block of one column tile
 constexpr size_t STREAM_SMEM_BYTES = A_BYTES + STAGES * B_STAGE_BYTES + 1024 + 256;
+// Shared-memory plan of the streaming forward by number of split products: three planes (NPROD = 6) leave room for a
+// 2-deep ring of 48 KB column-tile stages next to the 96 KB resident row tile; the two-plane pass (NPROD = 3) packs its
+// operands (64 KB resident tile, 32 KB stages) and spends what it saves on a 4-deep ring -- 128 KB of W3 in flight per SM
+// instead of 64 KB (every (row tile, column tile) pair pulls 64 KB through the L2 in ~1.1 us of MMA time: with two stages
+// the stream was bound by TMA latency, not bandwidth).
+template <int NPROD>
+struct StreamPlan {
+  static constexpr int NPL = NPROD == 3 ? 2 : PLANES;
+  static constexpr int NSTAGES = NPROD == 3 ? 4 : 2;
+  static constexpr uint32_t A_BYTES_ = A_KBLOCKS * NPL * PLANE_BYTES;
+  static constexpr uint32_t B_STAGE_ = NPL * PLANE_BYTES;
+  static constexpr size_t SMEM = A_BYTES_ + NSTAGES * B_STAGE_ + 1024 + 256;
+};
 constexpr int STREAM_EPI_WARPS = 16;                     // four per TMEM lane quarter: each takes 32 of a tile's 128 columns
 constexpr int STREAM_COL_PARTS = STREAM_EPI_WARPS / 4;   // column parts per tile
 constexpr int STREAM_THREADS = 64 + 32 * STREAM_EPI_WARPS;
@@ -264,6 +277,10 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                           int* __restrict__ part_topi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Plan = StreamPlan<NPROD>;
+  constexpr int NPL = Plan::NPL;                 // planes loaded = planes laid out
+  constexpr int STAGES = Plan::NSTAGES;          // (shadow the namespace-level constants of the plain GEMM)
+  constexpr uint32_t A_BYTES = Plan::A_BYTES_, B_STAGE_BYTES = Plan::B_STAGE_;
   uint8_t* a_buf = smem;
   uint8_t* b_ring = smem + A_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + A_BYTES + STAGES * B_STAGE_BYTES);
@@ -313,12 +330,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int m0 = (w / n_split) * BM, sp = w % n_split;
         const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
-        constexpr int NPL = NPROD == 3 ? 2 : PLANES;   // planes actually loaded (the layout keeps room for three)
         mbar_wait(a_empty, a_phase ^ 1);
         mbar_expect_tx(a_full, kblocks * NPL * PLANE_BYTES);
         for (int kb = 0; kb < kblocks; ++kb)
           for (int pl = 0; pl < NPL; ++pl)
-            tma_load_3d(a_buf + (kb * PLANES + pl) * PLANE_BYTES, &map_a, kb * BK, m0, pl, a_full);
+            tma_load_3d(a_buf + (kb * NPL + pl) * PLANE_BYTES, &map_a, kb * BK, m0, pl, a_full);
         a_phase ^= 1;
         for (int nt = nt0; nt < nt1; ++nt) {
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -357,7 +373,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(b_full + stage, phase);
             tc_fence_after();
-            const uint32_t a_lo = a_lo0 + kb * ((PLANES * PLANE_BYTES) >> 4);
+            const uint32_t a_lo = a_lo0 + kb * ((NPL * PLANE_BYTES) >> 4);
             const uint32_t b_lo = b_lo0 + stage * (B_STAGE_BYTES >> 4);
 #pragma unroll
             for (int pr = 0; pr < NPROD; ++pr) {
@@ -771,10 +787,10 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
   int* part_topi = reinterpret_cast<int*>(part_topv + U * n_parts * topk);
   cudaStream_t st = gngf::as_stream(stream);
   if (cudaFuncSetAttribute(hpd_stream_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(STREAM_SMEM_BYTES)) != cudaSuccess)
+                           static_cast<int>(StreamPlan<6>::SMEM)) != cudaSuccess)
     return gngf::check_launch();
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
-  hpd_stream_fwd_kernel<6><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
+  hpd_stream_fwd_kernel<6><<<grid, STREAM_THREADS, StreamPlan<6>::SMEM, st>>>(map_a, map_b, bias, static_cast<int>(U),
                                                                      static_cast<int>(T), static_cast<int>(Kdim), topk,
                                                                      n_split, part_max, part_sum, part_topv, part_topi);
   gngf::note_launch();
@@ -818,10 +834,10 @@ int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const uint16_t* b_plan
   int* cand_i = reinterpret_cast<int*>(cand_v + U * KTOP);
   cudaStream_t st = gngf::as_stream(stream);
   if (cudaFuncSetAttribute(hpd_stream_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           static_cast<int>(STREAM_SMEM_BYTES)) != cudaSuccess)
+                           static_cast<int>(StreamPlan<3>::SMEM)) != cudaSuccess)
     return gngf::check_launch();
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
-  hpd_stream_fwd_kernel<3><<<grid, STREAM_THREADS, STREAM_SMEM_BYTES, st>>>(map_a, map_b, bias, static_cast<int>(U),
+  hpd_stream_fwd_kernel<3><<<grid, STREAM_THREADS, StreamPlan<3>::SMEM, st>>>(map_a, map_b, bias, static_cast<int>(U),
                                                                      static_cast<int>(T), static_cast<int>(Kdim), KTOP,
                                                                      n_split, part_max, part_sum, part_topv, part_topi);
   gngf::note_launch();
