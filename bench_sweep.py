@@ -20,8 +20,8 @@ products (forward + backward); cells where that exceeds --hpd-cap FLOP are run W
 ("hpd": "capped") -- the corner where a step takes tens of seconds.
 
 Peaks: encode kernels are put against the measured HBM copy peak (MEASURED_PEAKS.json) and, where the node-feature
-array / tables are L2-resident, against the measured L2-resident copy bandwidth (profiles/measure_l2.py, run first by
-this script).  Algorithmic bytes per point (hash-mod rows): fwd 8 + L*4*F*4 + L*F*4 = 648 B,
+array / tables are L2-resident, against the measured L2-resident copy bandwidth (measure_l2_copy below: the first line
+this script prints).  Algorithmic bytes per point (hash-mod rows): fwd 8 + L*4*F*4 + L*F*4 = 648 B,
 bwd 128 + 512 + 8 = 648 B; the GNGF point passes move the same bytes (node features instead of table rows) and the node
 passes add S*(K*(8+F*4)+F*4) B fwd / S*(F*4+K*(8+2*F*4+4)) B bwd over the touched level nodes.
 """
