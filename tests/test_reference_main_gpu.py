@@ -140,21 +140,33 @@ def test_psnr_trajectory_matches_the_reference_cuda_eager_path(tmp_path):
 
 
 def test_full_run_fixture_of_the_reference():
-    """tests/golden/ref_cuda_trajectory_4061.npz (baseline/full_run_fixture.py, recorded on a B200): complete runs --
-    params.py's 5 000 epochs with the reference's early stopping -- of the unmodified reference (several: its runs differ
-    from each other) and of the drop-in, all through the unmodified main.py.  The statistic that survives the chaotic
-    trajectory is the best PSNR of a run (what functions.py:761-780 checkpoints): the drop-in's must lie within 0.1 dB +
-    the reference's own run-to-run range of the reference's."""
+    """tests/golden/ref_cuda_trajectory_4061.npz (baseline/full_run_fixture.py, recorded on one B200, all runs side by side):
+    three runs of the UNMODIFIED reference (its CUDA-eager path; ~3 240 epochs each -- the 25-minute budget per process
+    ended them before params.py's 5 000) and two complete runs of the drop-in (one early-stopped by the reference's own
+    EarlyStopping at epoch 2 967, one through all 5 000 epochs), everything driven by the unmodified main.py from the same
+    seed.  The statistic that survives the chaotic trajectory is the best PSNR of a run (what functions.py:761-780
+    checkpoints), taken over the epochs every run covers: the drop-in's must lie within 0.1 dB + the reference's own
+    run-to-run range of the reference's."""
     path = os.path.join(GOLDEN_DIR, "ref_cuda_trajectory_4061.npz")
     if not os.path.isfile(path):
         pytest.skip("no full-run fixture recorded yet")
     z = np.load(path)
-    summary = json.loads(str(z["summary"]))
-    ref_best = np.array([r["best_psnr"] for r in summary["reference"]])
-    our_best = np.array([r["best_psnr"] for r in summary["dropin"]])
-    print(f"\nfull runs: reference best PSNR {np.round(ref_best, 3)} ({[r['epochs'] for r in summary['reference']]} epochs), "
-          f"drop-in best PSNR {np.round(our_best, 3)} ({[r['epochs'] for r in summary['dropin']]} epochs)")
+    refs = [z[f"ref_psnr_{i}"] for i in range(int(z["ref_runs"]))]
+    ours = [z[f"ours_psnr_{i}"] for i in range(int(z["ours_runs"]))]
+    n = min(len(r) for r in refs)
+    ref_best = np.array([r[:n].max() for r in refs])
+    our_best = np.array([o[:n].max() for o in ours])
     rng = float(ref_best.max() - ref_best.min())
-    assert len(ref_best) >= 2 and len(our_best) >= 1
+    print(f"\nbest PSNR over the first {n} epochs: reference {np.round(ref_best, 3)} (range {rng:.3f} dB), drop-in "
+          f"{np.round(our_best, 3)}; drop-in run lengths {[len(o) for o in ours]}, best over a complete run "
+          f"{max(float(o.max()) for o in ours):.3f} dB (reference README.md:30: 20.331 dB)")
+    assert len(ref_best) >= 2 and len(our_best) >= 1 and n >= 3000
     for v in our_best:
         assert ref_best.min() - 0.1 - rng <= v <= ref_best.max() + 0.1 + rng, (v, ref_best)
+    # and at fixed epochs the drop-in's 200-epoch means stay within the band of the reference runs (+- its width)
+    for e in (1000, 2000, 3000):
+        rm = np.array([r[e - 200:e].mean() for r in refs])
+        w = float(rm.max() - rm.min())
+        for o in ours:
+            if len(o) >= e:
+                assert rm.min() - 0.1 - w <= o[e - 200:e].mean() <= rm.max() + 0.1 + w, (e, rm, float(o[e - 200:e].mean()))
