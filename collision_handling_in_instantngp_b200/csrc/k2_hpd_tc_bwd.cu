@@ -415,49 +415,103 @@ __global__ void __launch_bounds__(256)
   m2neg[u] = m;
 }
 
-// warp per node: the K selected slots.  dh[u,:] = (dh[u,:] + sum_k spk W3[t_k,:]) .* act'(h[u,:]);
+// The K selected slots of every node:  dh[u,:] = (dh[u,:] + sum_k spk W3[t_k,:]) .* act'(h[u,:]);
 // dW3[t_k,:] += spk h[u,:];  db3[t_k] += spk.  Runs after the dense pass, as the last writer of dh.
+//
+// A warp walks a RUN of consecutive rows (lane = 4 of the row's <= 128 features).  Consecutive rows are neighbouring
+// lattice nodes and the HPD is a smooth function of the node coordinate, so neighbours mostly select the SAME slots:
+// the warp keeps the last SP_CACHE distinct slots it met -- their W3 row (read once instead of once per node) and the
+// running sums  sum_u spk h[u,:]  and  sum_u spk  in registers -- and only issues the vector reduction into dW3 / db3
+// when a slot leaves the cache or the run ends.  With one reduction per (node, slot) (the first form of this kernel,
+// a warp per node) 30 M nodes x 4 slots x 128 floats went into the 16 384 rows of BASELINE.json configs[3]'s T = 2^14
+// table as same-address L2 reductions: 132 ms per step; cache misses only occur where the selection changes.
+constexpr int SP_CACHE = 8;
+constexpr int SP_RUN = 64;
+
 __global__ void __launch_bounds__(256)
     hpd_stream_bwd_sparse_kernel(int64_t U, int K, int Kdim, const int* __restrict__ utopi, const float* __restrict__ spk,
                                  const float* __restrict__ h, const float* __restrict__ w, int act_prev,
                                  float* __restrict__ dh, float* __restrict__ dw, float* __restrict__ db) {
-  const int64_t u = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
+  const int64_t run = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
   const int lane = threadIdx.x % 32;
-  if (u >= U) return;
+  const int64_t u0 = run * SP_RUN;
+  if (u0 >= U) return;
+  const int64_t u1 = min(U, u0 + SP_RUN);
   const int c = lane * 4;
   const bool on = c < Kdim;   // Kdim % 4 == 0
-  float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (on) {
-    hv = *reinterpret_cast<const float4*>(h + u * Kdim + c);
-    acc = *reinterpret_cast<const float4*>(dh + u * Kdim + c);
-  }
-  for (int k = 0; k < K; ++k) {
-    const int t = utopi[u * K + k];
-    const float s = spk[u * K + k];
+  int cs[SP_CACHE];           // cached slot ids (-1: empty); identical in every lane
+  float4 cw[SP_CACHE], ca[SP_CACHE];
+  float cb[SP_CACHE];
+#pragma unroll
+  for (int e = 0; e < SP_CACHE; ++e) cs[e] = -1;
+  int victim = 0;
+  auto flush = [&](int t, const float4& a, float bsum) {
+    if (on) red_add_v4(dw + static_cast<int64_t>(t) * Kdim + c, a.x, a.y, a.z, a.w);
+    if (lane == 0 && db) atomicAdd(db + t, bsum);
+  };
+  for (int64_t u = u0; u < u1; ++u) {
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (on) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<int64_t>(t) * Kdim + c));
-      acc.x = fmaf(s, wv.x, acc.x);
-      acc.y = fmaf(s, wv.y, acc.y);
-      acc.z = fmaf(s, wv.z, acc.z);
-      acc.w = fmaf(s, wv.w, acc.w);
-      red_add_v4(dw + static_cast<int64_t>(t) * Kdim + c, s * hv.x, s * hv.y, s * hv.z, s * hv.w);
+      hv = *reinterpret_cast<const float4*>(h + u * Kdim + c);
+      acc = *reinterpret_cast<const float4*>(dh + u * Kdim + c);
     }
-    if (lane == 0 && db) atomicAdd(db + t, s);
-  }
-  if (on) {
-    if (act_prev == GNGF_ACT_RELU) {
-      acc.x = hv.x > 0.0f ? acc.x : 0.0f;
-      acc.y = hv.y > 0.0f ? acc.y : 0.0f;
-      acc.z = hv.z > 0.0f ? acc.z : 0.0f;
-      acc.w = hv.w > 0.0f ? acc.w : 0.0f;
-    } else if (act_prev == GNGF_ACT_LEAKY_RELU) {
-      acc.x = hv.x > 0.0f ? acc.x : 0.01f * acc.x;
-      acc.y = hv.y > 0.0f ? acc.y : 0.01f * acc.y;
-      acc.z = hv.z > 0.0f ? acc.z : 0.01f * acc.z;
-      acc.w = hv.w > 0.0f ? acc.w : 0.01f * acc.w;
+    for (int k = 0; k < K; ++k) {
+      const int t = utopi[u * K + k];
+      const float sv = spk[u * K + k];
+      bool hit = false;
+#pragma unroll
+      for (int e = 0; e < SP_CACHE; ++e) {
+        if (cs[e] == t) {   // (warp-uniform: t and cs[] are the same in every lane)
+          hit = true;
+          acc.x = fmaf(sv, cw[e].x, acc.x);
+          acc.y = fmaf(sv, cw[e].y, acc.y);
+          acc.z = fmaf(sv, cw[e].z, acc.z);
+          acc.w = fmaf(sv, cw[e].w, acc.w);
+          ca[e].x = fmaf(sv, hv.x, ca[e].x);
+          ca[e].y = fmaf(sv, hv.y, ca[e].y);
+          ca[e].z = fmaf(sv, hv.z, ca[e].z);
+          ca[e].w = fmaf(sv, hv.w, ca[e].w);
+          cb[e] += sv;
+        }
+      }
+      if (!hit) {
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<int64_t>(t) * Kdim + c));
+        acc.x = fmaf(sv, wv.x, acc.x);
+        acc.y = fmaf(sv, wv.y, acc.y);
+        acc.z = fmaf(sv, wv.z, acc.z);
+        acc.w = fmaf(sv, wv.w, acc.w);
+#pragma unroll
+        for (int e = 0; e < SP_CACHE; ++e) {
+          if (e == victim) {
+            if (cs[e] >= 0) flush(cs[e], ca[e], cb[e]);
+            cs[e] = t;
+            cw[e] = wv;
+            ca[e] = make_float4(sv * hv.x, sv * hv.y, sv * hv.z, sv * hv.w);
+            cb[e] = sv;
+          }
+        }
+        victim = (victim + 1) % SP_CACHE;
+      }
     }
-    *reinterpret_cast<float4*>(dh + u * Kdim + c) = acc;
+    if (on) {
+      if (act_prev == GNGF_ACT_RELU) {
+        acc.x = hv.x > 0.0f ? acc.x : 0.0f;
+        acc.y = hv.y > 0.0f ? acc.y : 0.0f;
+        acc.z = hv.z > 0.0f ? acc.z : 0.0f;
+        acc.w = hv.w > 0.0f ? acc.w : 0.0f;
+      } else if (act_prev == GNGF_ACT_LEAKY_RELU) {
+        acc.x = hv.x > 0.0f ? acc.x : 0.01f * acc.x;
+        acc.y = hv.y > 0.0f ? acc.y : 0.01f * acc.y;
+        acc.z = hv.z > 0.0f ? acc.z : 0.01f * acc.z;
+        acc.w = hv.w > 0.0f ? acc.w : 0.01f * acc.w;
+      }
+      *reinterpret_cast<float4*>(dh + u * Kdim + c) = acc;
+    }
   }
+#pragma unroll
+  for (int e = 0; e < SP_CACHE; ++e)
+    if (cs[e] >= 0) flush(cs[e], ca[e], cb[e]);
 }
 
 static int split_count(int64_t x_tiles, int64_t y_tiles) {
@@ -532,7 +586,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
-  hpd_stream_bwd_sparse_kernel<<<static_cast<unsigned>(gngf::ceil_div(U * 32, 256)), 256, 0, st>>>(
+  hpd_stream_bwd_sparse_kernel<<<static_cast<unsigned>(gngf::ceil_div(gngf::ceil_div(U, SP_RUN) * 32, 256)), 256, 0, st>>>(
       U, topk, static_cast<int>(Kdim), utopi, spk, h, w, act_prev, dh, dw, db);
   gngf::note_launch();
   return gngf::check_launch();

@@ -224,11 +224,19 @@ def test_active_node_evaluation_matches_reference_golden(name):
         assert rel_err(out["grads"][k], out_box["grads"][k]) < GRAD_TOL, k   # (two-plane products: ~1e-5 each)
 
 
-def test_active_nodes_on_a_large_lattice_equal_the_whole_box():
+@pytest.mark.parametrize("regime", ["unit_scale_inputs", "raw_init"])
+def test_active_nodes_on_a_large_lattice_equal_the_whole_box(regime):
     """Active-node evaluation at scale: the 8192-resolution lattice of BASELINE.json configs[3] (16 levels), a quarter
-    box (4097^2 = 16.8 M nodes, so that the whole-box evaluation it is compared with fits comfortably), 2^20 pixel-lattice
+    box (4098^2 = 16.8 M nodes, so that the whole-box evaluation it is compared with fits comfortably), 2^20 pixel-lattice
     points: the touched-node list, the scatter back into (U, K) and the node-list backward against the evaluation of
-    every node of the box."""
+    every node of the box.
+
+    The HPD is fed integer lattice coordinates (models.py:416-418) -- up to 4 097 here -- so with nn.Linear's initial
+    weights its logits are O(1e4), the softmax is one-hot and ANY fp32 evaluation of the HPD gradients (the reference's
+    included) carries rounding noise far above 1e-4: the two evaluations then agree only to that noise ("raw_init":
+    forward exact, table / decoder gradients 1e-4, HPD gradients reported and bounded loosely).  "unit_scale_inputs"
+    scales the first layer by 1/4096 -- logits O(1) -- where every gradient must agree to the 1e-4 bar: that is the check
+    of the active-node machinery itself."""
     from collision_handling_in_instantngp_b200 import ops
     from collision_handling_in_instantngp_b200.loss import fused_total_loss
     from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
@@ -240,6 +248,8 @@ def test_active_nodes_on_a_large_lattice_equal_the_whole_box():
     with torch.no_grad():
         for t in net.encoding.tables():
             t.mul_(300.0)                          # table gradients well above fp32 noise (as in the goldens)
+        if regime == "unit_scale_inputs":
+            net.HPD.module_list[0][0].weight.mul_(1.0 / 4096)
     half = 4096
     net.set_coord_bounds((0.0, 0.0), (half / 8191, half / 8191))
     rng = np.random.default_rng(3)
@@ -264,16 +274,19 @@ def test_active_nodes_on_a_large_lattice_equal_the_whole_box():
 
     rgb_a, idx_a, cs_a, loss_a, g_a, n_a, U = run(True)
     rgb_b, idx_b, cs_b, loss_b, g_b, n_b, _ = run(False)
-    assert U == (half + 2) ** 2 or U >= half * half
+    assert U >= half * half
     assert n_b is None and 0 < n_a < 0.75 * U
-    print(f"\nlattice nodes {U}, touched {n_a} ({n_a / U:.1%})")
+    errs = {k: float((g_a[k] - g_b[k]).abs().max() / (g_b[k].abs().max() + 1e-30)) for k in g_b}
+    hpd_worst = max(v for k, v in errs.items() if k.startswith("HPD"))
+    rest_worst = max(v for k, v in errs.items() if not k.startswith("HPD"))
+    print(f"\n[{regime}] lattice nodes {U}, touched {n_a} ({n_a / U:.1%}); gradient differences active vs whole box: HPD "
+          f"{hpd_worst:.2e}, tables + decoder {rest_worst:.2e}")
     assert torch.equal(idx_a, idx_b)
     assert float((rgb_a - rgb_b).abs().max()) < 2e-6
     assert float(((cs_a - cs_b).abs() / cs_b.abs()).max()) < 1e-5
     assert abs(loss_a - loss_b) < 1e-5 * abs(loss_b)
-    for k in g_b:
-        err = float((g_a[k] - g_b[k]).abs().max() / (g_b[k].abs().max() + 1e-30))
-        assert err < GRAD_TOL, (k, err)
+    assert rest_worst < GRAD_TOL, errs
+    assert hpd_worst < (GRAD_TOL if regime == "unit_scale_inputs" else 1e-2), errs
 
 
 @pytest.mark.parametrize("mix", [False, None])
