@@ -271,10 +271,10 @@ def _rows_arg(name, args):
     if name == "gngf_hpd_stream_fwd":
         return int(args[3])
     if name == "gngf_hpd_stream_fwd_refined":
-        return int(args[5])
+        return int(args[7])
     if name == "gngf_hpd_stream_bwd":
-        return int(args[6])
-    return int(args[7])
+        return int(args[8])
+    return int(args[9])
 
 
 def algorithmic_cost(name, key, w, lat):
@@ -349,6 +349,8 @@ def algorithmic_cost(name, key, w, lat):
         "gngf_bitmap_or": U / 8 * 3,
         "gngf_cell_to_node_counts": S * 4 * 5,
         "gngf_split_bf16x3": 0.0,
+        # |x| max pass (read) + split pass (read, two fp16 planes written)
+        "gngf_split_f16x2": 0.0,
     }
     return "hbm", float(table.get(name, 0))
 

@@ -36,7 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HPD_CALLS = ("gngf_lattice_mark_nodes", "gngf_compact_nodes", "gngf_hpd_first_layer_fwd_nodes",
-             "gngf_hpd_first_layer_bwd_nodes", "gngf_linear_fwd", "gngf_linear_bwd", "gngf_split_bf16x3",
+             "gngf_hpd_first_layer_bwd_nodes", "gngf_linear_fwd", "gngf_linear_bwd", "gngf_split_bf16x3", "gngf_split_f16x2",
              "gngf_hpd_stream_fwd", "gngf_hpd_stream_fwd_refined", "gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes",
              "gngf_scatter_node_rows", "gngf_softmax_topk_fwd", "gngf_hpd_dlogits", "gngf_tc_gemm_bf16x3",
              "gngf_hpd_small_fwd", "gngf_hpd_small_bwd", "gngf_hpd_small_fwd_enc", "gngf_hpd_small_bwd_enc")

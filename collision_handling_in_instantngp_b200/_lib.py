@@ -81,21 +81,23 @@ SIGNATURES = {
     "gngf_lattice_mark_nodes": (c_int, [_P, c_int64, Lattice, _P, _P]),
     "gngf_compact_nodes": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P]),
     "gngf_scatter_node_rows": (c_int, [_P, c_int64, _P, c_int64, _P, _P]),
+    "gngf_tc_gemm_set_formats": (c_int, [c_int32, c_int32]),
     "gngf_bitmap_or": (c_int, [_P, c_int32, c_int64, _P, _P]),
     "gngf_gather_node_adjoints": (c_int, [Lattice, _P, c_int64, c_int32, _P, _P, _P, _P, _P]),
     "gngf_split_bf16x3": (c_int, [_P, c_int64, _P, _P]),
+    "gngf_split_f16x2": (c_int, [_P, c_int64, _P, _P, _P]),
     "gngf_split_bf16x3_t": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
     "gngf_tc_gemm_bf16x3": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "gngf_hpd_stream_workspace_floats": (c_int64, [c_int64, c_int64, c_int32]),
     "gngf_hpd_stream_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "gngf_hpd_stream_refined_workspace_floats": (c_int64, [c_int64, c_int64]),
-    "gngf_hpd_stream_fwd_refined": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P,
-                                            _P]),
+    "gngf_hpd_stream_fwd_refined": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P,
+                                            _P, _P]),
     "gngf_hpd_stream_bwd_workspace_floats": (c_int64, [c_int64, c_int32]),
-    "gngf_hpd_stream_bwd": (c_int, [Lattice, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P,
-                                    _P, _P, c_int32, _P, _P, _P, _P, _P]),
-    "gngf_hpd_stream_bwd_nodes": (c_int, [Lattice, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P,
-                                          _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P]),
+    "gngf_hpd_stream_bwd": (c_int, [Lattice, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P,
+                                    _P, _P, _P, c_int32, _P, _P, _P, _P, _P]),
+    "gngf_hpd_stream_bwd_nodes": (c_int, [Lattice, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P,
+                                          _P, _P, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P]),
     "gngf_hpd_small_supported": (c_int, [c_int32, POINTER(c_int32), c_int32]),
     "gngf_hpd_small_fwd": (c_int, [Lattice, c_int32, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_void_p), c_int32, _P, _P, _P, _P]),

@@ -17,6 +17,8 @@
 // optimizer step).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace gngf {
@@ -45,7 +47,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K, int act,
-                       int accumulate, int k_splits) {
+                       int accumulate, int k_splits, uint32_t idesc_arg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
   } else if (warp == 1) {
     {  // ---- MMA issuer: the whole warp runs the loop, an elected lane issues (see tc_common.cuh) ----
-      constexpr uint32_t idesc = umma_idesc(BM, BN);
+      const uint32_t idesc = idesc_arg;   // (operand formats are a launch parameter: gngf_tc_gemm_set_formats)
       // partial products of order <= 2 of (hi + mid + lo)(hi + mid + lo)
       constexpr int pa[6] = {0, 0, 1, 0, 2, 1};
       constexpr int pb[6] = {0, 1, 0, 2, 0, 1};
@@ -272,7 +274,8 @@ __device__ __forceinline__ void top_insert(RowTop& t, int K, float z, int n) {
 template <int NPROD>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
     hpd_stream_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                          const float* __restrict__ bias, int U, int T, int Kdim, int topk, int n_split,
+                          const float* __restrict__ bias, const float* __restrict__ a_scale,
+                          const float* __restrict__ b_scale, int U, int T, int Kdim, int topk, int n_split,
                           float* __restrict__ part_max, float* __restrict__ part_sum, float* __restrict__ part_topv,
                           int* __restrict__ part_topi) {
   extern __shared__ uint8_t smem_raw[];
@@ -352,7 +355,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     }
   } else if (warp == 1) {
     {  // ---- MMA issuer: the whole warp runs the loop, an elected lane issues (see tc_common.cuh) ----
-      constexpr uint32_t idesc = umma_idesc(BM, BN);
+      // NPROD = 3: two fp16 planes (11-bit mantissas, operands pre-scaled by powers of two: gngf_split_f16x2);
+      // NPROD = 6: three bf16 planes
+      constexpr uint32_t idesc = umma_idesc_fmt(BM, BN, NPROD == 3 ? 0 : 1, NPROD == 3 ? 0 : 1);
       constexpr int pa[6] = {0, 0, 1, 0, 2, 1};
       constexpr int pb[6] = {0, 1, 0, 2, 0, 1};
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -406,6 +411,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;        // which 32 of the tile's 128 columns
     const int n_parts = STREAM_COL_PARTS * n_split;
+    // the accumulator holds (h 2^sa)(W 2^sb)^T: undo the operands' power-of-two scales in the bias FMA
+    const float inv = (a_scale ? __ldg(a_scale) : 1.0f) * (b_scale ? __ldg(b_scale) : 1.0f);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
@@ -446,14 +453,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 b = bb[ch * 4 + j / 4];
-              z[j + 0] = __uint_as_float(v[j + 0]) + b.x;
-              z[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-              z[j + 2] = __uint_as_float(v[j + 2]) + b.z;
-              z[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+              z[j + 0] = fmaf(__uint_as_float(v[j + 0]), inv, b.x);
+              z[j + 1] = fmaf(__uint_as_float(v[j + 1]), inv, b.y);
+              z[j + 2] = fmaf(__uint_as_float(v[j + 2]), inv, b.z);
+              z[j + 3] = fmaf(__uint_as_float(v[j + 3]), inv, b.w);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = (nb + j < T) ? __uint_as_float(v[j]) + __ldg(bias + nb + j) : -INFINITY;
+            for (int j = 0; j < 16; ++j)
+              z[j] = (nb + j < T) ? fmaf(__uint_as_float(v[j]), inv, __ldg(bias + nb + j)) : -INFINITY;
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) cmax = fmaxf(cmax, z[j]);
@@ -660,6 +668,49 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- two fp16 planes with a power-of-two scale ---------------------------------------------------------------------
+// x 2^s = hi + mid (fp16 each, round-to-nearest), s chosen so that max |x| 2^s lies in [2^13, 2^14): 22 mantissa bits
+// per element (two bf16 planes: 16), at the same tensor-core cost.  With two bf16 planes the recomputed logits of the
+// streaming backward carry an absolute error of ~1.5e-5 sum|h w|, which exp() turns into a RELATIVE error of that
+// size in every probability: measured at BASELINE.json configs[2] (T = 2^19, random-init HPD, |logit| up to 73)
+// 1.8e-3 in dW3 against the 1e-4 bar, where a plain fp32 evaluation is at 1e-6.  fp16 has no exponent range to spare,
+// hence the scale: exact (a power of two), per tensor, computed on the device (no host round trip), undone in the
+// consumers' epilogues.  Elements more than 2^27 below the tensor's maximum lose relative (not absolute) precision.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.0f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
+  for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    } else {
+      for (int64_t j = i; j < n; ++j) m = fmaxf(m, fabsf(src[j]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f && m <= 3.0e38f) atomicMax(out, __float_as_uint(m));   // (non-negative floats order like their bits)
+}
+
+__device__ __forceinline__ int f16_shift_of(float absmax) {
+  if (!(absmax > 0.0f) || !(absmax <= 3.0e38f)) return 0;
+  return 13 - ilogbf(absmax);   // max |x| 2^s in [2^13, 2^14)
+}
+
+__global__ void __launch_bounds__(256) split_f16x2_kernel(const float* __restrict__ src, int64_t n,
+                                                         float* __restrict__ scale, __half* __restrict__ planes) {
+  const int s = f16_shift_of(__uint_as_float(*reinterpret_cast<const unsigned*>(scale + 1)));
+  const float f = ldexpf(1.0f, s);
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i == 0) scale[0] = ldexpf(1.0f, -s);   // what a consumer multiplies its accumulator with
+  if (i >= n) return;
+  const float x = src[i] * f;
+  const __half hi = __float2half_rn(x);
+  const __half mid = __float2half_rn(x - __half2float(hi));
+  planes[i] = hi;
+  planes[n + i] = mid;
+}
+
 // x = hi + mid + lo, each bf16 (round-to-nearest): planes[0][i], planes[1][i], planes[2][i]
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int64_t n,
                                                           __nv_bfloat16* __restrict__ planes) {
@@ -721,6 +772,23 @@ int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* strea
   return gngf::check_launch();
 }
 
+int gngf_split_f16x2(const float* src, int64_t n, uint16_t* planes, float* scale, void* stream) {
+  if (n < 0 || !scale) return GNGF_ERR_INVALID_ARGUMENT;
+  if (reinterpret_cast<uintptr_t>(src) & 15) return GNGF_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = gngf::as_stream(stream);
+  if (cudaMemsetAsync(scale, 0, 2 * sizeof(float), st) != cudaSuccess) return gngf::check_launch();
+  if (n == 0) return GNGF_OK;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(gngf::ceil_div(n, 1024), 8 * gngf::sm_count()));
+  gngf::tc::absmax_kernel<<<blocks, 256, 0, st>>>(src, n, reinterpret_cast<unsigned*>(scale + 1));
+  gngf::note_launch();
+  int rc = gngf::check_launch();
+  if (rc) return rc;
+  gngf::tc::split_f16x2_kernel<<<static_cast<unsigned>(gngf::ceil_div(n, 256)), 256, 0, st>>>(
+      src, n, scale, reinterpret_cast<__half*>(planes));
+  gngf::note_launch();
+  return gngf::check_launch();
+}
+
 int gngf_split_bf16x3_t(const float* src, int64_t rows, int64_t cols, int64_t ld, uint16_t* planes, void* stream) {
   if (rows <= 0 || cols <= 0 || ld < rows) return GNGF_ERR_INVALID_ARGUMENT;
   dim3 grid(static_cast<unsigned>(gngf::ceil_div(cols, 32)), static_cast<unsigned>(gngf::ceil_div(ld, 32)));
@@ -729,6 +797,17 @@ int gngf_split_bf16x3_t(const float* src, int64_t rows, int64_t cols, int64_t ld
                                                                             reinterpret_cast<__nv_bfloat16*>(planes));
   gngf::note_launch();
   return gngf::check_launch();
+}
+
+// 16-bit operand formats of gngf_tc_gemm_bf16x3's planes (tcgen05 instruction descriptor: 0 = fp16, 1 = bf16; default
+// bf16 x bf16).  The A and B fields are independent: bf16 x fp16 products are what the streaming backward uses for
+// E (bf16, wide range) times fp16 operand planes (11-bit mantissas); tests/test_kernels_gpu.py checks the combination.
+static int g_gemm_a_fmt = 1, g_gemm_b_fmt = 1;
+int gngf_tc_gemm_set_formats(int32_t a_fmt, int32_t b_fmt) {
+  if ((a_fmt != 0 && a_fmt != 1) || (b_fmt != 0 && b_fmt != 1)) return GNGF_ERR_INVALID_ARGUMENT;
+  g_gemm_a_fmt = a_fmt;
+  g_gemm_b_fmt = b_fmt;
+  return GNGF_OK;
 }
 
 int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
@@ -753,7 +832,8 @@ int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, cons
   const int64_t tiles = out_tiles * k_splits;
   const int grid = static_cast<int>(std::min<int64_t>(tiles, gngf::sm_count()));
   gemm_bf16x3_kernel<<<grid, THREADS, SMEM_BYTES, gngf::as_stream(stream)>>>(
-      map_a, map_b, bias, C, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), act, accumulate, k_splits);
+      map_a, map_b, bias, C, static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), act, accumulate, k_splits,
+      umma_idesc_fmt(BM, BN, g_gemm_a_fmt, g_gemm_b_fmt));
   gngf::note_launch();
   return gngf::check_launch();
 }
@@ -790,7 +870,7 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
                            static_cast<int>(StreamPlan<6>::SMEM)) != cudaSuccess)
     return gngf::check_launch();
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
-  hpd_stream_fwd_kernel<6><<<grid, STREAM_THREADS, StreamPlan<6>::SMEM, st>>>(map_a, map_b, bias, static_cast<int>(U),
+  hpd_stream_fwd_kernel<6><<<grid, STREAM_THREADS, StreamPlan<6>::SMEM, st>>>(map_a, map_b, bias, nullptr, nullptr, static_cast<int>(U),
                                                                      static_cast<int>(T), static_cast<int>(Kdim), topk,
                                                                      n_split, part_max, part_sum, part_topv, part_topi);
   gngf::note_launch();
@@ -809,18 +889,20 @@ int64_t gngf_hpd_stream_refined_workspace_floats(int64_t U, int64_t T) {
   return gngf_hpd_stream_workspace_floats(U, T, KTOP) + 2 * U * KTOP + 4;
 }
 
-int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const uint16_t* b_planes, const float* h, const float* w,
-                                const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk, float* utopv,
-                                int32_t* utopi, float* row_max, float* row_sum, float* workspace, void* stream) {
+int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const float* a_scale, const uint16_t* b_planes,
+                                const float* b_scale, const float* h, const float* w, const float* bias, int64_t U,
+                                int64_t T, int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max,
+                                float* row_sum, float* workspace, void* stream) {
   using namespace gngf::tc;
   if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > A_KBLOCKS * BK || topk <= 0 || 2 * topk > KTOP ||
       topk > T || U >= (1ll << 31) || T >= (1ll << 31) || !h || !w || !row_max || !row_sum)
     return GNGF_ERR_UNSUPPORTED;
+  if (!a_planes || !b_planes || !a_scale || !b_scale) return GNGF_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w)) & 15) return GNGF_ERR_INVALID_ARGUMENT;
-  CUtensorMap map_a, map_b;
-  int rc = make_plane_map(&map_a, a_planes, U, Kdim);
+  CUtensorMap map_a, map_b;   // two fp16 planes each (gngf_split_f16x2)
+  int rc = make_plane_map(&map_a, a_planes, U, Kdim, BM, 2);
   if (rc) return rc;
-  rc = make_plane_map(&map_b, b_planes, T, Kdim);
+  rc = make_plane_map(&map_b, b_planes, T, Kdim, BM, 2);
   if (rc) return rc;
   const int64_t row_tiles = gngf::ceil_div(U, BM), col_tiles = gngf::ceil_div(T, BN);
   const int n_split =
@@ -837,7 +919,7 @@ int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const uint16_t* b_plan
                            static_cast<int>(StreamPlan<3>::SMEM)) != cudaSuccess)
     return gngf::check_launch();
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
-  hpd_stream_fwd_kernel<3><<<grid, STREAM_THREADS, StreamPlan<3>::SMEM, st>>>(map_a, map_b, bias, static_cast<int>(U),
+  hpd_stream_fwd_kernel<3><<<grid, STREAM_THREADS, StreamPlan<3>::SMEM, st>>>(map_a, map_b, bias, a_scale, b_scale, static_cast<int>(U),
                                                                      static_cast<int>(T), static_cast<int>(Kdim), KTOP,
                                                                      n_split, part_max, part_sum, part_topv, part_topi);
   gngf::note_launch();

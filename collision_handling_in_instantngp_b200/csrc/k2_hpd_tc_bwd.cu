@@ -21,11 +21,18 @@
 // per 128x128x16 MMA = 64 B/clk).  History: E through shared memory with 64-row Y tiles reached 67 % of the measured
 // bf16 peak (the N = 64 first product was bound by 6 KB of operand reads per MMA), X as a TMEM operand 71 %, E in TMEM
 // with 128-row tiles 85 %.  TMEM: S/E 2 x 128 columns, O 128, X 128 = all 512.
-// Operands are two bf16 planes (hi, mid) of the fp32 values and each product is hi.hi + hi.mid + mid.hi (relative
-// error ~1e-5: the gradient tolerance is 1e-4; the forward, which must reproduce top-k selections exactly, uses three
-// planes and six products).  MMA issue order S(j+1), O(j) keeps the tensor pipe busy while the epilogue turns S(j)
-// into E(j).
+// Operands are two fp16 planes (hi, mid) of the power-of-two-scaled fp32 values (gngf_split_f16x2: 22 mantissa bits)
+// and each product is hi.hi + hi.mid + mid.hi.  (Two bf16 planes -- 16 bits -- were measured at the size of BASELINE.json
+// configs[2] to put 1.8e-3 into dW3: the recomputed logits' absolute error becomes a relative error of every E.)
+// tcgen05.mma kind::f16 wants A and B in the SAME 16-bit format (bf16 x fp16 traps as an illegal instruction), so E is
+// fp16 as well and its range is managed by exponent offsets inside the exp2 argument:
+//   DW = false:  E' = 2^12 exp(z - max_r)            the row factor a_r is applied to the O tile when it is flushed;
+//   DW = true :  E''= sgn(a_r) 2^(log2|a_r| + sa) exp(z - max_r),   sa = 13 - ceil(max_r log2|a_r|)  (device scalar)
+// and the flush multiplies O by the inverse powers of two (and the operand scale of Y).  MMA issue order S(j+1), O(j)
+// keeps the tensor pipe busy while the epilogue turns S(j) into E(j).
 #include <algorithm>
+
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 
@@ -47,10 +54,21 @@ constexpr uint32_t X_COL = 384;                           // resident X tile: pl
 constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t p) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&p));
+}
+
+// device scalars shared by the prep kernel and the two dense passes (consts[] in the workspace)
+constexpr int C_K1 = 0;        // log2(e) / (scale_h scale_w): turns the scaled accumulator into a base-2 logit
+constexpr int C_OUT_DH = 1;    // 2^-12 / scale_w
+constexpr int C_OUT_DW = 2;    // 2^-sa / scale_h
+constexpr int C_SA = 3;        // sa (as a float): exponent offset of the DW = true pass
+constexpr int C_MAXLA = 4;     // scratch: max over rows of log2|a_r| as ordered-int bits
+constexpr float E_SHIFT = 12.0f;
 
 // x_rows / y_rows: number of valid rows of X / Y (U or T); Kdim <= 128.
 // DW = false: X = h tile, rows carry (a, -max log2e), columns the bias;  DW = true: X = W3 tile, the other way round.
@@ -64,8 +82,10 @@ template <bool DW>
 __global__ void __launch_bounds__(THREADS, 1)
     hpd_stream_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                           int x_rows, int y_rows, int Kdim, int n_split, const float* __restrict__ bias,
-                          const float* __restrict__ m2neg, const float* __restrict__ ascale, float* __restrict__ out,
-                          float* __restrict__ dbias) {
+                          const float* __restrict__ m2neg, const float* __restrict__ ascale,
+                          const float* __restrict__ consts, float* __restrict__ out, float* __restrict__ dbias) {
+  // m2neg / ascale: DW = false: per ROW  -max_r log2e          / a_r (applied at the flush);
+  //                 DW = true : per COLUMN -max_r log2e + log2|a_r| / sgn(a_r)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
@@ -138,8 +158,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   } else if (warp == 1) {
     {  // ---- MMA issuer: the whole warp runs the loop, an elected lane issues (see tc_common.cuh) ----
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform copy
-      constexpr uint32_t idesc1 = umma_idesc(BM, SBN);
-      const uint32_t idesc2 = umma_idesc(BM, n2) | UMMA_B_MN_MAJOR;
+      constexpr uint32_t idesc1 = umma_idesc_fmt(BM, SBN, 0, 0);                    // fp16 x fp16
+      const uint32_t idesc2 = umma_idesc_fmt(BM, n2, 0, 0) | UMMA_B_MN_MAJOR;
       const uint32_t y_lo = umma_desc_lo(smem_u32(ring));                      // K-major view (first product)
       const uint32_t y_lo_mn = umma_desc_lo(smem_u32(ring), NP * TP_BYTES);    // MN-major view (second product)
       uint32_t nent = 0;                       // ring entries consumed before this item
@@ -230,14 +250,17 @@ __global__ void __launch_bounds__(THREADS, 1)
       if (t0 >= t1) continue;
       const int row = m0 + row_l;
       const bool row_ok = row < x_rows;
+      const float k1 = __ldg(consts + C_K1);
+      const float out_scale = __ldg(consts + (DW ? C_OUT_DW : C_OUT_DH));
       float r_off, r_scale;
       if (DW) {
-        r_off = row_ok ? __ldg(bias + row) * LOG2E : 0.0f;
+        r_off = row_ok ? fmaf(__ldg(bias + row), LOG2E, __ldg(consts + C_SA)) : 0.0f;
         r_scale = row_ok ? 1.0f : 0.0f;
       } else {
-        r_off = row_ok ? __ldg(m2neg + row) : 0.0f;
-        r_scale = row_ok ? __ldg(ascale + row) : 0.0f;
+        r_off = row_ok ? __ldg(m2neg + row) + E_SHIFT : 0.0f;
+        r_scale = row_ok ? 1.0f : 0.0f;
       }
+      const float flush_scale = DW ? out_scale : (row_ok ? out_scale * __ldg(ascale + row) : 0.0f);
       {  // X tile: ring slot (TMA, 128-byte swizzle) -> tensor memory; warp (q, half) copies plane `half` of rows 32q..
         const uint32_t slot = nent % RING;
         mbar_wait(r_full + slot, (nent / RING) & 1);
@@ -269,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const uint32_t se = tmem_base + lane_off + SE_COL + buf * SBN + half * 64;
         mbar_wait(s_full + buf, ph);
         tc_fence_after();
-        uint32_t hi[32], mid[32];   // this thread's 64 columns of E as bf16 pairs: hi plane, mid plane
+        uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const int c0 = t * SBN + half * 64 + cb * 32;
@@ -288,10 +311,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                 off = make_float4(b.x * LOG2E, b.y * LOG2E, b.z * LOG2E, b.w * LOG2E);
                 sc = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
               }
-              e[j + 0] = fast_exp2(fmaf(__uint_as_float(v[j + 0]), LOG2E, r_off + off.x)) * (r_scale * sc.x);
-              e[j + 1] = fast_exp2(fmaf(__uint_as_float(v[j + 1]), LOG2E, r_off + off.y)) * (r_scale * sc.y);
-              e[j + 2] = fast_exp2(fmaf(__uint_as_float(v[j + 2]), LOG2E, r_off + off.z)) * (r_scale * sc.z);
-              e[j + 3] = fast_exp2(fmaf(__uint_as_float(v[j + 3]), LOG2E, r_off + off.w)) * (r_scale * sc.w);
+              e[j + 0] = fast_exp2(fmaf(__uint_as_float(v[j + 0]), k1, r_off + off.x)) * (r_scale * sc.x);
+              e[j + 1] = fast_exp2(fmaf(__uint_as_float(v[j + 1]), k1, r_off + off.y)) * (r_scale * sc.y);
+              e[j + 2] = fast_exp2(fmaf(__uint_as_float(v[j + 2]), k1, r_off + off.z)) * (r_scale * sc.z);
+              e[j + 3] = fast_exp2(fmaf(__uint_as_float(v[j + 3]), k1, r_off + off.w)) * (r_scale * sc.w);
             }
           } else {
 #pragma unroll
@@ -307,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                   sc = 1.0f;
                 }
               }
-              const float ev = fast_exp2(fmaf(__uint_as_float(v[j]), LOG2E, r_off + off)) * (r_scale * sc);
+              const float ev = fast_exp2(fmaf(__uint_as_float(v[j]), k1, r_off + off)) * (r_scale * sc);
               e[j] = c < y_rows ? ev : 0.0f;   // (zero-filled Y rows give S = 0, not a logit: exp2 may overflow there)
             }
           }
@@ -321,10 +344,12 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float a = e[2 * i], b = e[2 * i + 1];
-            const uint32_t h2 = pack_bf16x2(a, b);
+            // (values above fp16's largest finite number -- an exp2 argument gone wrong -- must not become inf)
+            const float a = fminf(fmaxf(e[2 * i], -65504.0f), 65504.0f), b = fminf(fmaxf(e[2 * i + 1], -65504.0f), 65504.0f);
+            const uint32_t h2 = pack_f16x2(a, b);
+            const float2 hf = unpack_f16x2(h2);
             hi[cb * 16 + i] = h2;
-            mid[cb * 16 + i] = pack_bf16x2(a - __uint_as_float(h2 << 16), b - __uint_as_float(h2 & 0xffff0000u));
+            mid[cb * 16 + i] = pack_f16x2(a - hf.x, b - hf.y);
           }
         }
         // E over S, in place: this thread's 64 fp32 columns become 32 columns of hi pairs + 32 columns of mid pairs
@@ -351,19 +376,19 @@ __global__ void __launch_bounds__(THREADS, 1)
           if ((Kdim & 3) == 0 && col0 + 32 <= Kdim) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              red_add_v4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                         __uint_as_float(v[j + 3]));
+              red_add_v4(o + j, __uint_as_float(v[j]) * flush_scale, __uint_as_float(v[j + 1]) * flush_scale,
+                         __uint_as_float(v[j + 2]) * flush_scale, __uint_as_float(v[j + 3]) * flush_scale);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < Kdim) atomicAdd(o + j, __uint_as_float(v[j]));
+              if (col0 + j < Kdim) atomicAdd(o + j, __uint_as_float(v[j]) * flush_scale);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      if (DW && row_ok && dbias) atomicAdd(dbias + row, rsum);
+      if (DW && row_ok && dbias) atomicAdd(dbias + row, rsum * exp2f(-__ldg(consts + C_SA)));   // (E'' carries 2^sa)
     }
   }
 
@@ -376,43 +401,76 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 // per node u: g_k = dtv[u,k] + sum_l cnt[s(l,u)] gcol_k[l,k];  spk[u,k] = p_k g_k;  a_u = -sum_k spk / row_sum;
-// m2neg_u = -row_max log2e.  (The dense-adjoint inputs of gngf_hpd_dlogits do not exist in top-k-only mode.)
+// m2neg_u = -row_max log2e;  coff_u = m2neg_u + log2|a_u| (-inf when a_u = 0), sgn_u = sign(a_u): the column offset / sign
+// of the DW = true pass, whose E carries a_u inside the exp2 argument; the largest log2|a_u| goes to consts[C_MAXLA].
+// (The dense-adjoint inputs of gngf_hpd_dlogits do not exist in top-k-only mode.)
 // With node_ids the rows are the active nodes (k11_active_nodes.cu): row r <-> lattice node node_ids[r]; dtv and cnt are
 // indexed by the lattice node, everything else by the row.
+__device__ __forceinline__ int ordered_key(float x) {   // monotone float -> int map (for atomicMax on signed values)
+  const int b = __float_as_int(x);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_value(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+constexpr int MAXLA_INIT = static_cast<int>(0x80808080u);   // what cudaMemsetAsync(.., 0x80, ..) leaves: below every key
+
 __global__ void __launch_bounds__(256)
     hpd_stream_bwd_prep_kernel(gngf_lattice lat, const int* __restrict__ node_ids, int64_t U, int K,
                                const float* __restrict__ utopv,
                                const float* __restrict__ dtv, const int* __restrict__ cnt,
                                const float* __restrict__ gcol_k, const float* __restrict__ row_max,
                                const float* __restrict__ row_sum, float* __restrict__ ascale,
-                               float* __restrict__ m2neg, float* __restrict__ spk) {
+                               float* __restrict__ m2neg, float* __restrict__ coff, float* __restrict__ sgn,
+                               float* __restrict__ spk, float* __restrict__ consts) {
   const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (u >= U) return;
-  const int L = lat.num_levels;
-  const int64_t un = node_ids ? node_ids[u] : u;
-  const int cx = lat.ox + static_cast<int>(un / lat.wy), cy = lat.oy + static_cast<int>(un % lat.wy);
-  float dot = 0.0f;
-  for (int k = 0; k < K; ++k) {
-    float g = dtv[un * K + k];
-    if (gcol_k) {
-      for (int l = 0; l < L; ++l) {
-        const int i = cx - lat.lox[l], j = cy - lat.loy[l];
-        if (i >= 0 && i < lat.lwx[l] && j >= 0 && j < lat.lwy[l]) {
-          const float c = static_cast<float>(cnt[lat.loff[l] + static_cast<int64_t>(i) * lat.lwy[l] + j]);
-          g = fmaf(c, gcol_k[l * K + k], g);
+  float la = -INFINITY;
+  if (u < U) {
+    const int L = lat.num_levels;
+    const int64_t un = node_ids ? node_ids[u] : u;
+    const int cx = lat.ox + static_cast<int>(un / lat.wy), cy = lat.oy + static_cast<int>(un % lat.wy);
+    float dot = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      float g = dtv[un * K + k];
+      if (gcol_k) {
+        for (int l = 0; l < L; ++l) {
+          const int i = cx - lat.lox[l], j = cy - lat.loy[l];
+          if (i >= 0 && i < lat.lwx[l] && j >= 0 && j < lat.lwy[l]) {
+            const float c = static_cast<float>(cnt[lat.loff[l] + static_cast<int64_t>(i) * lat.lwy[l] + j]);
+            g = fmaf(c, gcol_k[l * K + k], g);
+          }
         }
       }
+      const float pg = utopv[u * K + k] * g;
+      spk[u * K + k] = pg;
+      dot += pg;
     }
-    const float pg = utopv[u * K + k] * g;
-    spk[u * K + k] = pg;
-    dot += pg;
+    float a = -dot / row_sum[u];
+    float m = -row_max[u] * LOG2E;
+    if (!(fabsf(a) <= 3.0e38f)) a = 0.0f;   // nan_to_num of a degenerate row (models.py:111)
+    if (!(fabsf(m) <= 3.0e38f)) m = 0.0f;
+    ascale[u] = a;
+    m2neg[u] = m;
+    if (a != 0.0f) la = log2f(fabsf(a));
+    coff[u] = m + la;
+    sgn[u] = a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f);
   }
-  float a = -dot / row_sum[u];
-  float m = -row_max[u] * LOG2E;
-  if (!(fabsf(a) <= 3.0e38f)) a = 0.0f;   // nan_to_num of a degenerate row (models.py:111)
-  if (!(fabsf(m) <= 3.0e38f)) m = 0.0f;
-  ascale[u] = a;
-  m2neg[u] = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) la = fmaxf(la, __shfl_xor_sync(0xffffffffu, la, o));
+  if ((threadIdx.x & 31) == 0 && la > -INFINITY)
+    atomicMax(reinterpret_cast<int*>(consts + C_MAXLA), ordered_key(la));
+}
+
+// one thread: the device scalars of the dense passes from the operand scales (gngf_split_f16x2) and the largest log2|a|
+__global__ void hpd_stream_bwd_consts_kernel(const float* __restrict__ scale_h, const float* __restrict__ scale_w,
+                                             float* __restrict__ consts) {
+  const float ih = scale_h[0], iw = scale_w[0];   // inverse operand scales (powers of two)
+  const int key = *reinterpret_cast<const int*>(consts + C_MAXLA);
+  float sa = 0.0f;
+  if (key != MAXLA_INIT) sa = 13.0f - ceilf(ordered_value(key));
+  sa = fminf(fmaxf(sa, -100.0f), 100.0f);
+  consts[C_K1] = LOG2E * ih * iw;
+  consts[C_OUT_DH] = exp2f(-E_SHIFT) * iw;
+  consts[C_OUT_DW] = exp2f(-sa) * ih;
+  consts[C_SA] = sa;
 }
 
 // The K selected slots of every node:  dh[u,:] = (dh[u,:] + sum_k spk W3[t_k,:]) .* act'(h[u,:]);
@@ -524,10 +582,13 @@ static int split_count(int64_t x_tiles, int64_t y_tiles) {
 
 extern "C" {
 
-int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk) { return U * (2 + static_cast<int64_t>(topk)) + 4; }
+int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk) {
+  return 4 * ((U + 3) & ~int64_t(3)) + U * static_cast<int64_t>(topk) + 16;
+}
 
-int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes,
-                              const uint16_t* w_planes, const float* h, const float* w, const float* bias, int64_t U,
+int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes, const float* h_scale,
+                              const uint16_t* w_planes, const float* w_scale, const float* h, const float* w,
+                              const float* bias, int64_t U,
                               int64_t T, int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi,
                               const float* dtv, const int32_t* cnt, const float* gcol_k, const float* row_max,
                               const float* row_sum, int32_t act_prev, float* dh, float* dw, float* db, float* workspace,
@@ -539,27 +600,34 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
       U >= (1ll << 31) || T >= (1ll << 31) || (node_ids ? U > box : (gcol_k != nullptr && U != box)))
     return GNGF_ERR_UNSUPPORTED;   // (no node list and no column-sum adjoint: plain rows, dtv indexed by the row)
   if (gcol_k && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
-  if (!h_planes || !w_planes || !h || !w || !bias || !utopv || !utopi || !dtv || !row_max || !row_sum || !dh || !dw ||
-      !workspace)
+  if (!h_planes || !w_planes || !h_scale || !w_scale || !h || !w || !bias || !utopv || !utopi || !dtv || !row_max ||
+      !row_sum || !dh || !dw || !workspace)
     return GNGF_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(dh) |
        reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w)) & 15)
     return GNGF_ERR_INVALID_ARGUMENT;
   cudaStream_t st = gngf::as_stream(stream);
-  // workspace: ascale (U, rounded up to 4) | m2neg (U, rounded up to 4) | spk (U, topk)
+  // workspace: ascale | m2neg | coff | sgn (U each, rounded up to 4) | spk (U, topk) | consts (8, 16-byte aligned)
   const int64_t U4 = (U + 3) & ~int64_t(3);
   float* ascale = workspace;
   float* m2neg = workspace + U4;
-  float* spk = workspace + 2 * U4;
+  float* coff = workspace + 2 * U4;
+  float* sgn = workspace + 3 * U4;
+  float* spk = workspace + 4 * U4;
+  float* consts = spk + ((U * topk + 3) & ~int64_t(3));
+  if (cudaMemsetAsync(consts, 0x80, 8 * sizeof(float), st) != cudaSuccess) return gngf::check_launch();
   hpd_stream_bwd_prep_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 256)), 256, 0, st>>>(
-      lat, node_ids, U, topk, utopv, dtv, cnt, gcol_k, row_max, row_sum, ascale, m2neg, spk);
+      lat, node_ids, U, topk, utopv, dtv, cnt, gcol_k, row_max, row_sum, ascale, m2neg, coff, sgn, spk, consts);
   gngf::note_launch();
   int rc = gngf::check_launch();
   if (rc) return rc;
+  hpd_stream_bwd_consts_kernel<<<1, 1, 0, st>>>(h_scale, w_scale, consts);
+  gngf::note_launch();
+  if ((rc = gngf::check_launch())) return rc;
 
-  CUtensorMap map_h, map_w;   // 128-row boxes serve both roles (resident X tile, streamed Y tiles)
-  if ((rc = make_plane_map(&map_h, h_planes, U, Kdim, BM))) return rc;
-  if ((rc = make_plane_map(&map_w, w_planes, T, Kdim, BM))) return rc;
+  CUtensorMap map_h, map_w;   // 128-row boxes serve both roles (resident X tile, streamed Y tiles); two fp16 planes
+  if ((rc = make_plane_map(&map_h, h_planes, U, Kdim, BM, NP))) return rc;
+  if ((rc = make_plane_map(&map_w, w_planes, T, Kdim, BM, NP))) return rc;
   if (cudaFuncSetAttribute(hpd_stream_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(SMEM_BYTES)) != cudaSuccess ||
       cudaFuncSetAttribute(hpd_stream_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -572,7 +640,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(map_h, map_w, static_cast<int>(U),
                                                                    static_cast<int>(T), static_cast<int>(Kdim), ns, bias,
-                                                                   m2neg, ascale, dh, nullptr);
+                                                                   m2neg, ascale, consts, dh, nullptr);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
@@ -582,7 +650,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(map_w, map_h, static_cast<int>(T),
                                                                   static_cast<int>(U), static_cast<int>(Kdim), ns, bias,
-                                                                  m2neg, ascale, dw, db);
+                                                                  coff, sgn, consts, dw, db);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
@@ -592,12 +660,14 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
   return gngf::check_launch();
 }
 
-int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16_t* w_planes, const float* h,
-                        const float* w, const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk,
+int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const float* h_scale, const uint16_t* w_planes,
+                        const float* w_scale, const float* h, const float* w, const float* bias, int64_t U, int64_t T,
+                        int64_t Kdim, int32_t topk,
                         const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
                         const float* gcol_k, const float* row_max, const float* row_sum, int32_t act_prev, float* dh,
                         float* dw, float* db, float* workspace, void* stream) {
-  return gngf_hpd_stream_bwd_nodes(lat, nullptr, h_planes, w_planes, h, w, bias, U, T, Kdim, topk, utopv, utopi, dtv, cnt,
+  return gngf_hpd_stream_bwd_nodes(lat, nullptr, h_planes, h_scale, w_planes, w_scale, h, w, bias, U, T, Kdim, topk, utopv,
+                                   utopi, dtv, cnt,
                                    gcol_k, row_max, row_sum, act_prev, dh, dw, db, workspace, stream);
 }
 

@@ -55,6 +55,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// the same with explicit 16-bit operand formats (0 = fp16, 1 = bf16), independently for A and B
+__host__ __device__ constexpr uint32_t umma_idesc_fmt(int M, int N, int a_fmt, int b_fmt) {
+  return (1u << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
@@ -197,11 +202,13 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// planes (3, rows, K) bf16 row-major -> 3-D tensor map {K, rows, 3}, box {64, 128, 1}, 128-byte swizzle
-inline int make_plane_map(CUtensorMap* map, const void* planes, int64_t rows, int64_t K, int box_rows = BM) {
+// planes (n_planes, rows, K) 16-bit row-major -> 3-D tensor map {K, rows, n_planes}, box {64, 128, 1}, 128-byte swizzle
+// (bf16 x 3 planes, or fp16 x 2 planes: the element type only names the 2-byte size here)
+inline int make_plane_map(CUtensorMap* map, const void* planes, int64_t rows, int64_t K, int box_rows = BM,
+                          int n_planes = PLANES) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return GNGF_ERR_CUDA;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), 3};
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(n_planes)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(rows) * K * 2};
   cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};

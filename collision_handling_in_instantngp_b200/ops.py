@@ -164,6 +164,24 @@ def split_bf16x3(t: torch.Tensor) -> torch.Tensor:
     return planes
 
 
+class Planes16:
+    """Two fp16 planes of a power-of-two-scaled fp32 tensor (gngf_split_f16x2): the operands of the streaming HPD
+    kernels.  `data` (2, *shape) float16; `scale` 2 device floats (scale[0] = 2^-s, undone in the consumers' epilogues)."""
+    __slots__ = ("data", "scale")
+
+    def __init__(self, data, scale):
+        self.data, self.scale = data, scale
+
+
+def split_f16x2(t: torch.Tensor) -> Planes16:
+    """x 2^s = hi + mid in fp16 with the scale chosen on the device from max|x| (no host synchronisation)."""
+    t = _f32c(t)
+    planes = torch.empty((2, *t.shape), dtype=torch.float16, device=t.device)
+    scale = torch.empty(2, dtype=torch.float32, device=t.device)
+    call("gngf_split_f16x2", t.data_ptr(), t.numel(), planes.data_ptr(), scale.data_ptr(), _stream())
+    return Planes16(planes, scale)
+
+
 def tc_linear_fwd(x, w, b, act, x_planes=None, w_planes=None) -> torch.Tensor:
     """y = act(x w^T + b) on the tensor cores (tcgen05, split-bf16 operands, fp32 accumulate in TMEM)."""
     M, K = x.shape
@@ -199,12 +217,12 @@ STREAM_FWD_REFINED = True         # streaming forward as a two-plane pass + fp32
 
 def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None, alloc_rows=None):
     """Fused K2+K3: (utopv, utopi int32, row_max, row_sum) of softmax(h w^T + b) without the (U,T) logits.
-    K <= 4: half the tensor-core work -- a two-plane (1e-5) streaming pass keeps 8 candidates per row, whose logits are
-    then re-evaluated in fp32 and re-ranked (gngf_hpd_stream_fwd_refined); otherwise three planes / six products."""
+    K <= 4: half the tensor-core work -- a two-plane streaming pass (fp16 planes of the scaled operands, Planes16) keeps
+    8 candidates per row, whose logits are then re-evaluated in fp32 and re-ranked (gngf_hpd_stream_fwd_refined);
+    otherwise three bf16 planes / six products.  h_planes / w_planes: Planes16 (what the backward uses as well)."""
     U, Kd = h.shape
     T = w.shape[0]
-    hp = split_bf16x3(h) if h_planes is None else h_planes
-    wp = split_bf16x3(w) if w_planes is None else w_planes
+    refined = STREAM_FWD_REFINED and k <= 4
     dev = h.device
     # alloc_rows >= U: the selections are written into the head of larger (zero-tailed) buffers -- the equal-sized
     # per-rank blocks of dp.NodeSharding.all_gather_rows
@@ -218,13 +236,16 @@ def hpd_stream_fwd(h, w, b, k, h_planes=None, w_planes=None, alloc_rows=None):
         return utopv, utopi, torch.empty(0, dtype=torch.float32, device=dev), torch.empty(0, dtype=torch.float32, device=dev)
     row_max = torch.empty(U, dtype=torch.float32, device=dev)
     row_sum = torch.empty(U, dtype=torch.float32, device=dev)
-    if STREAM_FWD_REFINED and k <= 4:
+    if refined:
         h, w = _f32c(h), _f32c(w)
+        hp = split_f16x2(h) if h_planes is None else h_planes
+        wp = split_f16x2(w) if w_planes is None else w_planes
         work = torch.empty(_lib.load().gngf_hpd_stream_refined_workspace_floats(U, T), dtype=torch.float32, device=dev)
-        call("gngf_hpd_stream_fwd_refined", hp.data_ptr(), wp.data_ptr(), h.data_ptr(), w.data_ptr(), b.data_ptr(), U, T,
-             Kd, k, utopv.data_ptr(), utopi.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), work.data_ptr(),
-             _stream())
+        call("gngf_hpd_stream_fwd_refined", hp.data.data_ptr(), hp.scale.data_ptr(), wp.data.data_ptr(),
+             wp.scale.data_ptr(), h.data_ptr(), w.data_ptr(), b.data_ptr(), U, T, Kd, k, utopv.data_ptr(),
+             utopi.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), work.data_ptr(), _stream())
         return utopv, utopi, row_max, row_sum
+    hp, wp = split_bf16x3(h), split_bf16x3(w)      # (K > 4: three bf16 planes, six products)
     work = torch.empty(_lib.load().gngf_hpd_stream_workspace_floats(U, T, k), dtype=torch.float32, device=dev)
     call("gngf_hpd_stream_fwd", hp.data_ptr(), wp.data_ptr(), b.data_ptr(), U, T, Kd, k, utopv.data_ptr(),
          utopi.data_ptr(), row_max.data_ptr(), row_sum.data_ptr(), work.data_ptr(), _stream())
@@ -240,13 +261,14 @@ def hpd_stream_bwd(lat: Lattice, h, w, b, h_planes, w_planes, utopv, utopi, dtv,
     dh = torch.zeros((U, kd), dtype=torch.float32, device=h.device)
     work = torch.empty(_lib.load().gngf_hpd_stream_bwd_workspace_floats(U, K), dtype=torch.float32, device=h.device)
     if node_ids is None:
-        call("gngf_hpd_stream_bwd", lat, h_planes.data_ptr(), w_planes.data_ptr(), h.data_ptr(), w.data_ptr(),
-             b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(), _ptr(cnt), _ptr(gcol_k),
+        call("gngf_hpd_stream_bwd", lat, h_planes.data.data_ptr(), h_planes.scale.data_ptr(), w_planes.data.data_ptr(),
+             w_planes.scale.data_ptr(), h.data_ptr(), w.data_ptr(), b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(), _ptr(cnt), _ptr(gcol_k),
              row_max.data_ptr(), row_sum.data_ptr(), act_prev, dh.data_ptr(), dw.data_ptr(), db.data_ptr(),
              work.data_ptr(), _stream())
     else:   # rows = active nodes; dtv and cnt stay indexed by the lattice node
-        call("gngf_hpd_stream_bwd_nodes", lat, node_ids.data_ptr(), h_planes.data_ptr(), w_planes.data_ptr(),
-             h.data_ptr(), w.data_ptr(), b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(),
+        call("gngf_hpd_stream_bwd_nodes", lat, node_ids.data_ptr(), h_planes.data.data_ptr(),
+             h_planes.scale.data_ptr(), w_planes.data.data_ptr(), w_planes.scale.data_ptr(), h.data_ptr(), w.data_ptr(),
+             b.data_ptr(), U, T, kd, K, utopv.data_ptr(), utopi.data_ptr(), dtv.data_ptr(),
              _ptr(cnt), _ptr(gcol_k), row_max.data_ptr(), row_sum.data_ptr(), act_prev, dh.data_ptr(), dw.data_ptr(),
              db.data_ptr(), work.data_ptr(), _stream())
     return dh
@@ -402,8 +424,8 @@ class ForwardState:
     uprobs: Optional[torch.Tensor] = None                        # (U,T); None on the streaming path
     row_max: Optional[torch.Tensor] = None                       # (U,) softmax statistics (streaming path)
     row_sum: Optional[torch.Tensor] = None
-    w_planes: Optional[torch.Tensor] = None                      # (3,T,Kd) bf16 planes of the output layer
-    h_planes: Optional[torch.Tensor] = None                      # (3,U,Kd) bf16 planes of its input (streaming path)
+    w_planes: Optional["Planes16"] = None                        # (2,T,Kd) fp16 planes + scale of the output layer
+    h_planes: Optional["Planes16"] = None                        # (2,U,Kd) fp16 planes + scale of its input (streaming path)
     hpd_small: bool = False                                      # fused small-lattice HPD kernels were used
     nfeat: Optional[torch.Tensor] = None                         # (S,F) written by the HPD kernel itself (small lattices)
     utopv: Optional[torch.Tensor] = None                         # (U,K)
@@ -543,8 +565,8 @@ def hpd_forward_nodes(lat: Lattice, hpd_w, hpd_b, k: int, device, cfg, state, ta
     acts.append(h)
     kd = h.shape[1]
     if _streaming_ok(cfg, U, T, k, kd):
-        state.w_planes = split_bf16x3(hpd_w[-1])
-        state.h_planes = split_bf16x3(h) if rows > 0 else None
+        state.w_planes = split_f16x2(hpd_w[-1])
+        state.h_planes = split_f16x2(h) if rows > 0 else None
         state.utopv, state.utopi, state.row_max, state.row_sum = hpd_stream_fwd(
             h, hpd_w[-1], hpd_b[-1], k, h_planes=state.h_planes, w_planes=state.w_planes,
             alloc_rows=None if state.shard is None else state.shard[4])
@@ -869,11 +891,12 @@ class GNGFPath(torch.autograd.Function):
             rows = int(max(128, min(U, BWD_CHUNK_BYTES // (T * 4)))) // 8 * 8
             dz = torch.zeros((U, kd), dtype=torch.float32, device=dev)
             wt_planes = split_bf16x3(hpd_w[nh - 1].t().contiguous())          # (3, kd, T): B operand of dX
+            wb_planes = split_bf16x3(hpd_w[nh - 1])                           # (3, T, kd): B operand of the logits
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             for r0 in range(0, U, rows):
                 n = min(rows, U - r0)
                 hc = h_last[r0:r0 + n]
-                buf = tc_linear_fwd(hc, hpd_w[nh - 1], params[2 * (nh - 1) + 1], ACT_NONE, w_planes=state.w_planes)
+                buf = tc_linear_fwd(hc, hpd_w[nh - 1], params[2 * (nh - 1) + 1], ACT_NONE, w_planes=wb_planes)
                 call("gngf_hpd_dlogits", lat, buf.data_ptr(), T, K, state.utopi.data_ptr(), dtv.data_ptr(),
                      state.cnt.data_ptr(), None, _ptr(gcol_k), None, state.row_max.data_ptr(),
                      state.row_sum.data_ptr(), r0, n, buf.data_ptr(), st)

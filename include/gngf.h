@@ -140,11 +140,19 @@ int gngf_scatter_node_rows(const int32_t* node_ids, int64_t n_nodes, const void*
  *   a_planes (3,M,K), b_planes (3,N,K) bf16, 16-byte aligned, K % 8 == 0.  This is the HPD output layer
  *   (models.py:80-88: Linear(128, T)) when T is large.                                                       */
 int gngf_split_bf16x3(const float* src, int64_t n, uint16_t* planes, void* stream);
+/* Two fp16 planes with a power-of-two scale (the operands of the STREAMING kernels): x 2^s = hi + mid, s chosen on the
+ * device so that max|x| 2^s lies in [2^13, 2^14) -- 22 mantissa bits per element against 16 for two bf16 planes, at the
+ * same tensor-core cost (measured at BASELINE.json configs[2]: dW3 error 1.8e-3 -> fp32 level).  planes (2, n) fp16;
+ * scale: 2 device floats, scale[0] receives 2^-s (what a consumer multiplies its accumulator with), scale[1] is
+ * scratch.  src 16-byte aligned.  No host synchronisation (CUDA-graph capturable).                               */
+int gngf_split_f16x2(const float* src, int64_t n, uint16_t* planes, float* scale, void* stream);
 /* transposing variant: planes (3, cols, ld) of src (rows, cols)^T, ld >= rows, columns >= rows zero-filled      */
 int gngf_split_bf16x3_t(const float* src, int64_t rows, int64_t cols, int64_t ld, uint16_t* planes, void* stream);
 /* accumulate != 0: C += product + bias (no activation) -- used for weight gradients summed over row chunks.
  * k_splits > 1: the K range is split over CTAs and summed with atomics into a ZERO-INITIALISED C (for products
  * whose M x N alone cannot fill the chip, e.g. dX = dlogits W3 with K = T).                                    */
+/* operand formats of the planes given to gngf_tc_gemm_bf16x3 (0 = fp16, 1 = bf16; default 1, 1); process-wide */
+int gngf_tc_gemm_set_formats(int32_t a_fmt, int32_t b_fmt);
 int gngf_tc_gemm_bf16x3(const uint16_t* a_planes, const uint16_t* b_planes, const float* bias, int64_t M, int64_t N,
                         int64_t K, int32_t act, int32_t accumulate, int32_t k_splits, float* C, void* stream);
 
@@ -164,31 +172,33 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
  *   those of an fp32 evaluation as long as the true top-k lie within the approximate top-8 (a violation needs five
  *   logits within 2e-5 of the k-th largest).  workspace: gngf_hpd_stream_refined_workspace_floats(U, T) floats.   */
 int64_t gngf_hpd_stream_refined_workspace_floats(int64_t U, int64_t T);
-int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const uint16_t* b_planes, const float* h, const float* w,
-                                const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk, float* utopv,
-                                int32_t* utopi, float* row_max, float* row_sum, float* workspace, void* stream);
+/*   a_planes (2,U,Kdim) / b_planes (2,T,Kdim) with their scales: gngf_split_f16x2 of h / w.                          */
+int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const float* a_scale, const uint16_t* b_planes,
+                                const float* b_scale, const float* h, const float* w, const float* bias, int64_t U,
+                                int64_t T, int64_t Kdim, int32_t topk, float* utopv, int32_t* utopi, float* row_max,
+                                float* row_sum, float* workspace, void* stream);
 
 /* K5c fused, streaming (top-k-only mode): backward of gngf_hpd_stream_fwd's layer + softmax + top-k
  *   (models.py:80-88, 105-123; DifferentiableTopk.backward, models.py:21-42; column-sum adjoint of utils.py:138)
  *   without materialising logits, probabilities or dlogits.  Per node u
  *     g_k = dtv[u,k] + sum_l cnt[s(l,u)] gcol_k[l,k],   dlogit[u,:] = -<g,p_top> p[u,:] + scatter_k(p_k g_k),
  *   and   dh (U,Kdim) = (dlogit W) .* act_prev'(h),   dw (T,Kdim) += dlogit^T h,   db (T) += colsum(dlogit).
- *   The dense products run on tcgen05 (two bf16 planes, hi.hi + hi.mid + mid.hi, relative error ~1e-5), recomputing
- *   the logits tile by tile from the planes and the forward's row_max / row_sum.
- *   h_planes (3,U,Kdim) / w_planes (3,T,Kdim): gngf_split_bf16x3 planes; h (U,Kdim), w (T,Kdim): the fp32 originals
+ *   The dense products run on tcgen05 (two fp16 planes of the power-of-two-scaled operands, hi.hi + hi.mid + mid.hi),
+ *   recomputing the logits tile by tile from the planes and the forward's row_max / row_sum.
+ *   h_planes (2,U,Kdim) / w_planes (2,T,Kdim) + h_scale / w_scale: gngf_split_f16x2; h (U,Kdim), w (T,Kdim): the fp32 originals
  *   (used by the K-sparse part); utopv / utopi (U,topk): the forward's outputs; dh must be ZERO-INITIALISED, dw / db
  *   are accumulated into; workspace: gngf_hpd_stream_bwd_workspace_floats(U, topk) floats, 16-byte aligned.      */
 int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk);
-int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const uint16_t* w_planes, const float* h,
-                        const float* w, const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk,
-                        const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
+int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const float* h_scale, const uint16_t* w_planes,
+                        const float* w_scale, const float* h, const float* w, const float* bias, int64_t U, int64_t T,
+                        int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,
                         const float* gcol_k, const float* row_max, const float* row_sum, int32_t act_prev, float* dh,
                         float* dw, float* db, float* workspace, void* stream);
 /* the same on the active nodes: rows of h_planes / h / utopv / utopi / row_max / row_sum / dh are the nodes
  * node_ids[0..U), while dtv (box, topk) and cnt stay indexed by the lattice node; node_ids == NULL: U = box     */
-int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes,
-                              const uint16_t* w_planes, const float* h, const float* w, const float* bias, int64_t U,
-                              int64_t T, int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi,
+int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes, const float* h_scale,
+                              const uint16_t* w_planes, const float* w_scale, const float* h, const float* w,
+                              const float* bias, int64_t U, int64_t T, int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi,
                               const float* dtv, const int32_t* cnt, const float* gcol_k, const float* row_max,
                               const float* row_sum, int32_t act_prev, float* dh, float* dw, float* db, float* workspace,
                               void* stream);

@@ -110,7 +110,7 @@ def test_active_node_and_split_loss_entry_points_validate_on_the_host():
     # the streaming backward on a node list accepts fewer rows than the box; the plain entry point only without a
     # column-sum adjoint (rows whose adjoints arrive row-indexed: the node-parallel owner's call)
     small = build_lattice(level_resolutions(8, 32, 4))
-    a = (16,) * 5
+    a = (16,) * 7          # h_planes, h_scale, w_planes, w_scale, h, w, bias
     common = (16, 16, 16, None, None, 16, 16, 1, 16, 16, 16, 16, None)
     with_colsum = (16, 16, 16, 16, 16, 16, 16, 1, 16, 16, 16, 16, None)
     assert lib.gngf_hpd_stream_bwd(small, *a, 100, 256, 128, 4, *with_colsum) == -2               # U != box
@@ -123,5 +123,8 @@ def test_active_node_and_split_loss_entry_points_validate_on_the_host():
     assert lib.gngf_gather_node_adjoints(small, None, 5, 4, None, None, None, 16, None) == -1     # no adjoints
     assert lib.gngf_gather_node_adjoints(small, None, 5, 4, 16, None, 16, 16, None) == -1         # gcol_k without cnt
     assert lib.gngf_gather_node_adjoints(small, None, 5, 0, 16, None, None, 16, None) == -1
+    assert lib.gngf_split_f16x2(16, -1, 16, 16, None) == -1 and lib.gngf_split_f16x2(16, 8, 16, None, None) == -1
+    assert lib.gngf_split_f16x2(20, 8, 16, 16, None) == -1                      # source must be 16-byte aligned
+    assert lib.gngf_tc_gemm_set_formats(2, 0) == -1 and lib.gngf_tc_gemm_set_formats(1, 1) == 0
     assert lib.gngf_peer_allreduce_set_timeout_ms(0) == -1 and lib.gngf_peer_allreduce_set_timeout_ms(30000) == 0
     assert lib.gngf_hpd_stream_bwd_nodes(small, 16, *a, small.num_nodes + 1, 256, 128, 4, *common) == -2
