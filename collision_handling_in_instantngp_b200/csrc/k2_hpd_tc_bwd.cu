@@ -3,9 +3,15 @@
 // (U, T) logits, probabilities or dlogits.
 //
 // In top-k-only mode the adjoint of the probabilities is non-zero at the K selected slots only, so per lattice node r
-//     dlogit[r, t] = -<G,p>_r * p[r, t]  +  sum_k [t == t_k] p_k g_k ,      p[r, t] = exp(z[r, t] - max_r) / sum_r .
-// The K-sparse part is a gather / scatter of K rows per node (hpd_stream_bwd_sparse_kernel).  The dense part is an
-// attention-shaped pair of products with E[r, t] = a_r exp(z[r, t] - max_r), a_r = -<G,p>_r / sum_r:
+//     dlogit[r, t] = p[r, t] (G[r, t] - <G,p>_r) = -<G,p>_r p[r, t]           for t not selected,
+//                                                 p_k (g_k - <G,p>_r)          for t = t_k,     p = exp(z - max_r) / sum_r .
+// The selected slots are a gather / scatter of K rows per node in fp32 (hpd_stream_bwd_sparse_kernel) and are MASKED OUT
+// of the dense part.  (The first version let the dense part cover every t and added p_k g_k on top: with a peaked softmax
+// -- p_k -> 1, the regime of a random-init HPD fed integer lattice coordinates -- the two terms cancel to a result
+// 1/(1 - p_k) times smaller, and the dense term's independent rounding, ~3e-6 from the exp2 argument alone, was measured
+// as 1.6e-3 in dW3 at the size of BASELINE.json configs[2]; computing p_k (g_k - <G,p>) as ONE product is what a plain
+// fp32 evaluation does.)  The dense part is an attention-shaped pair of products with E[r, t] = a_r exp(z[r, t] - max_r)
+// for the unselected t, a_r = -<G,p>_r / sum_r:
 //     dh  (U, Kd) = E   W3           dW3 (T, Kd) += E^T h           db3 (T) += E^T 1
 // Both are instances of ONE kernel (hpd_stream_bwd_kernel<DW>):
 //     X (128 x Kd) resident, Y tiles (128 x Kd) streamed by TMA through a 3-slot ring (X travels through it once per item)
@@ -69,6 +75,7 @@ constexpr int C_OUT_DW = 2;    // 2^-sa / scale_h
 constexpr int C_SA = 3;        // sa (as a float): exponent offset of the DW = true pass
 constexpr int C_MAXLA = 4;     // scratch: max over rows of log2|a_r| as ordered-int bits
 constexpr float E_SHIFT = 12.0f;
+constexpr int SB_MAX_K = 8;    // selected slots per node on the streaming path (the forward's KTOP)
 
 // x_rows / y_rows: number of valid rows of X / Y (U or T); Kdim <= 128.
 // DW = false: X = h tile, rows carry (a, -max log2e), columns the bias;  DW = true: X = W3 tile, the other way round.
@@ -83,7 +90,9 @@ __global__ void __launch_bounds__(THREADS, 1)
     hpd_stream_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                           int x_rows, int y_rows, int Kdim, int n_split, const float* __restrict__ bias,
                           const float* __restrict__ m2neg, const float* __restrict__ ascale,
-                          const float* __restrict__ consts, float* __restrict__ out, float* __restrict__ dbias) {
+                          const float* __restrict__ consts, const int* __restrict__ utopi, int topk,
+                          float* __restrict__ out, float* __restrict__ dbias) {
+  // utopi (nodes, topk): the selected slots, masked out of E (DW = false: nodes are the X rows; DW = true: the Y rows)
   // m2neg / ascale: DW = false: per ROW  -max_r log2e          / a_r (applied at the flush);
   //                 DW = true : per COLUMN -max_r log2e + log2|a_r| / sgn(a_r)
   extern __shared__ uint8_t smem_raw[];
@@ -261,6 +270,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         r_scale = row_ok ? 1.0f : 0.0f;
       }
       const float flush_scale = DW ? out_scale : (row_ok ? out_scale * __ldg(ascale + row) : 0.0f);
+      int tk[SB_MAX_K];   // DW = false: this row's selected slots
+#pragma unroll
+      for (int k = 0; k < SB_MAX_K; ++k)
+        tk[k] = (!DW && row_ok && k < topk) ? __ldg(utopi + static_cast<int64_t>(row) * topk + k) : -1;
       {  // X tile: ring slot (TMA, 128-byte swizzle) -> tensor memory; warp (q, half) copies plane `half` of rows 32q..
         const uint32_t slot = nent % RING;
         mbar_wait(r_full + slot, (nent / RING) & 1);
@@ -290,6 +303,30 @@ __global__ void __launch_bounds__(THREADS, 1)
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         const uint32_t se = tmem_base + lane_off + SE_COL + buf * SBN + half * 64;
+        // DW = true: which of this thread's 64 columns (nodes) selected this thread's slot?  The warp reads the 64 x topk
+        // selections of its nodes once per tile (coalesced), finds those that fall into its 32 slots, and hands each to
+        // the lane that owns the slot: bit c of `kill` = column c of this thread is a selected slot of that node.
+        uint64_t kill = 0;
+        if (DW) {
+          const int node0 = t * SBN + half * 64;
+          const int first_slot = m0 + q * 32;
+          const int total = 64 * topk;
+          for (int i0 = 0; i0 < total; i0 += 32) {
+            const int e_i = i0 + lane;
+            const int node_off = e_i / topk;
+            int d = -1;
+            if (e_i < total && node0 + node_off < y_rows)
+              d = __ldg(utopi + static_cast<int64_t>(node0) * topk + e_i) - first_slot;
+            unsigned hits = __ballot_sync(0xffffffffu, d >= 0 && d < 32);
+            while (hits) {
+              const int src = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const int dd = __shfl_sync(0xffffffffu, d, src);
+              const int nn = __shfl_sync(0xffffffffu, node_off, src);
+              if (lane == dd) kill |= 1ull << nn;
+            }
+          }
+        }
         mbar_wait(s_full + buf, ph);
         tc_fence_after();
         uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
@@ -334,13 +371,30 @@ __global__ void __launch_bounds__(THREADS, 1)
               e[j] = c < y_rows ? ev : 0.0f;   // (zero-filled Y rows give S = 0, not a logit: exp2 may overflow there)
             }
           }
+          {  // the selected slots belong to the sparse part
+            uint32_t k32 = static_cast<uint32_t>(kill >> (cb * 32));
+            if (!DW) {
+#pragma unroll
+              for (int k = 0; k < SB_MAX_K; ++k) {
+                const unsigned d = static_cast<unsigned>(tk[k] - c0);
+                if (tk[k] >= 0 && d < 32u) k32 |= 1u << d;
+              }
+            }
+            if (k32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if ((k32 >> j) & 1u) e[j] = 0.0f;
+            }
+          }
           if (!row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) e[j] = 0.0f;
           }
-          if (DW) {
+          if (DW) {   // two-level sum: a chunk's 32 terms first (pairwise), then into the running total
+            float cs[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rsum += e[j];
+            for (int j = 0; j < 8; ++j) cs[j] = (e[j] + e[j + 8]) + (e[j + 16] + e[j + 24]);
+            rsum += ((cs[0] + cs[1]) + (cs[2] + cs[3])) + ((cs[4] + cs[5]) + (cs[6] + cs[7]));
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -400,7 +454,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 }
 
-// per node u: g_k = dtv[u,k] + sum_l cnt[s(l,u)] gcol_k[l,k];  spk[u,k] = p_k g_k;  a_u = -sum_k spk / row_sum;
+// per node u: g_k = dtv[u,k] + sum_l cnt[s(l,u)] gcol_k[l,k];  spk[u,k] = p_k (g_k - <g,p>) (the dlogits of the selected
+// slots);  a_u = -<g,p> / row_sum;
 // m2neg_u = -row_max log2e;  coff_u = m2neg_u + log2|a_u| (-inf when a_u = 0), sgn_u = sign(a_u): the column offset / sign
 // of the DW = true pass, whose E carries a_u inside the exp2 argument; the largest log2|a_u| goes to consts[C_MAXLA].
 // (The dense-adjoint inputs of gngf_hpd_dlogits do not exist in top-k-only mode.)
@@ -428,7 +483,10 @@ __global__ void __launch_bounds__(256)
     const int64_t un = node_ids ? node_ids[u] : u;
     const int cx = lat.ox + static_cast<int>(un / lat.wy), cy = lat.oy + static_cast<int>(un % lat.wy);
     float dot = 0.0f;
-    for (int k = 0; k < K; ++k) {
+    float gk[SB_MAX_K];
+#pragma unroll
+    for (int k = 0; k < SB_MAX_K; ++k) {
+      if (k >= K) break;
       float g = dtv[un * K + k];
       if (gcol_k) {
         for (int l = 0; l < L; ++l) {
@@ -439,9 +497,16 @@ __global__ void __launch_bounds__(256)
           }
         }
       }
-      const float pg = utopv[u * K + k] * g;
-      spk[u * K + k] = pg;
-      dot += pg;
+      gk[k] = g;
+      dot = fmaf(utopv[u * K + k], g, dot);
+    }
+    // dlogit at the selected slots, as ONE product (see the header): p_k (g_k - <g,p>)
+#pragma unroll
+    for (int k = 0; k < SB_MAX_K; ++k) {
+      if (k >= K) break;
+      float v = utopv[u * K + k] * (gk[k] - dot);
+      if (!(fabsf(v) <= 3.0e38f)) v = 0.0f;
+      spk[u * K + k] = v;
     }
     float a = -dot / row_sum[u];
     float m = -row_max[u] * LOG2E;
@@ -596,7 +661,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
   using namespace gngf::tc;
   using namespace gngf::tc::sb;
   const int64_t box = static_cast<int64_t>(lat.wx) * lat.wy;
-  if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > 2 * BK || topk <= 0 || topk > GNGF_MAX_TOPK ||
+  if (U <= 0 || T <= 0 || Kdim <= 0 || (Kdim % 8) != 0 || Kdim > 2 * BK || topk <= 0 || topk > SB_MAX_K ||
       U >= (1ll << 31) || T >= (1ll << 31) || (node_ids ? U > box : (gcol_k != nullptr && U != box)))
     return GNGF_ERR_UNSUPPORTED;   // (no node list and no column-sum adjoint: plain rows, dtv indexed by the row)
   if (gcol_k && !cnt) return GNGF_ERR_INVALID_ARGUMENT;
@@ -640,7 +705,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(map_h, map_w, static_cast<int>(U),
                                                                    static_cast<int>(T), static_cast<int>(Kdim), ns, bias,
-                                                                   m2neg, ascale, consts, dh, nullptr);
+                                                                   m2neg, ascale, consts, utopi, topk, dh, nullptr);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
@@ -650,7 +715,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(map_w, map_h, static_cast<int>(T),
                                                                   static_cast<int>(U), static_cast<int>(Kdim), ns, bias,
-                                                                  coff, sgn, consts, dw, db);
+                                                                  coff, sgn, consts, utopi, topk, dw, db);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
