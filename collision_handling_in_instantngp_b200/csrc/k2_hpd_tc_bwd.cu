@@ -57,7 +57,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SE_COL = 0;                            // two S / E buffers of 128 columns
 constexpr uint32_t O_COL = 256;                           // O accumulator, 128 columns
 constexpr uint32_t X_COL = 384;                           // resident X tile: plane p at [X_COL + 64 p, +64) (bf16 pairs)
-constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * 8 /*kill bits*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* o_empty = o_full + 1;
   uint64_t* xt_full = o_empty + 1;         // X tile copied into tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
+  unsigned long long* kill_s = reinterpret_cast<unsigned long long*>(ring + RING * TILE_BYTES + 256);   // [EPI_WARPS][32]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2) kill_s[(warp - 2) * 32 + lane] = 0ull;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -300,31 +302,68 @@ __global__ void __launch_bounds__(THREADS, 1)
         nent += 1 + (t1 - t0);
       }
       float rsum = 0.0f;   // DW: db3[row] = sum of E over all streamed nodes
+      const int k_shift = (topk & (topk - 1)) == 0 ? __ffs(topk) - 1 : -1;   // log2(topk) when it is a power of two
+      unsigned long long* kill_w = kill_s + (warp - 2) * 32;
+      int nxt[2 * SB_MAX_K];   // DW: (selected slot - first slot of this warp) of the next Y tile's 64 nodes x topk
+      auto load_sel = [&](int tile) {
+        const int node0 = tile * SBN + half * 64;
+        const int first_slot = m0 + q * 32;
+        const int total = 64 * topk;
+#pragma unroll
+        for (int i = 0; i < 2 * SB_MAX_K; ++i) {
+          const int e_i = i * 32 + lane;
+          nxt[i] = -1;
+          if (e_i < total && static_cast<int64_t>(node0) * topk + e_i < static_cast<int64_t>(y_rows) * topk)
+            nxt[i] = __ldg(utopi + static_cast<int64_t>(node0) * topk + e_i) - first_slot;
+        }
+      };
+      if (DW) load_sel(t0);
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         const uint32_t se = tmem_base + lane_off + SE_COL + buf * SBN + half * 64;
         // DW = true: which of this thread's 64 columns (nodes) selected this thread's slot?  The warp reads the 64 x topk
-        // selections of its nodes once per tile (coalesced), finds those that fall into its 32 slots, and hands each to
-        // the lane that owns the slot: bit c of `kill` = column c of this thread is a selected slot of that node.
+        // selections of its nodes once per tile (coalesced; requested ONE TILE AHEAD so that their latency hides behind
+        // this tile's work).  An entry that falls into the warp's 32 slots must reach the lane that owns the slot: lanes
+        // holding the SAME slot (neighbouring nodes select the same slots: a popular slot is hit by all 64 nodes of every
+        // tile) first OR their node bits together (match.any + redux.or), and one of them ORs the result into the
+        // owner's word in shared memory -- a handful of shared-memory atomics per tile whatever the hit count.
         uint64_t kill = 0;
         if (DW) {
-          const int node0 = t * SBN + half * 64;
-          const int first_slot = m0 + q * 32;
           const int total = 64 * topk;
-          for (int i0 = 0; i0 < total; i0 += 32) {
-            const int e_i = i0 + lane;
-            const int node_off = e_i / topk;
-            int d = -1;
-            if (e_i < total && node0 + node_off < y_rows)
-              d = __ldg(utopi + static_cast<int64_t>(node0) * topk + e_i) - first_slot;
-            unsigned hits = __ballot_sync(0xffffffffu, d >= 0 && d < 32);
-            while (hits) {
-              const int src = __ffs(hits) - 1;
-              hits &= hits - 1;
-              const int dd = __shfl_sync(0xffffffffu, d, src);
-              const int nn = __shfl_sync(0xffffffffu, node_off, src);
-              if (lane == dd) kill |= 1ull << nn;
+          int cur[2 * SB_MAX_K];
+#pragma unroll
+          for (int i = 0; i < 2 * SB_MAX_K; ++i) cur[i] = nxt[i];
+          if (t + 1 < t1) load_sel(t + 1);
+          bool any = false;
+#pragma unroll
+          for (int i = 0; i < 2 * SB_MAX_K; ++i) {
+            if (i * 32 < total) {   // warp-uniform
+              const int d = cur[i];
+              const bool hit = d >= 0 && d < 32;
+              const unsigned hits = __ballot_sync(0xffffffffu, hit);
+              if (hits) {           // warp-uniform
+                any = true;
+                if (hit) {
+                  const int e_i = i * 32 + lane;
+                  const int node = k_shift >= 0 ? (e_i >> k_shift) : (e_i / topk);
+                  const int base = k_shift >= 0 ? ((i * 32) >> k_shift) : ((i * 32) / topk);   // nodes of this round: base .. base + 32
+                  const unsigned same = __match_any_sync(hits, d);
+                  const unsigned bits = __reduce_or_sync(same, 1u << (node - base));
+                  if (lane == __ffs(same) - 1) {   // 32-bit shared-memory atomics (a 64-bit OR would be a CAS loop)
+                    const unsigned long long m64 = static_cast<unsigned long long>(bits) << base;
+                    unsigned* w32 = reinterpret_cast<unsigned*>(kill_w + d);
+                    if (static_cast<unsigned>(m64)) atomicOr(w32, static_cast<unsigned>(m64));
+                    if (static_cast<unsigned>(m64 >> 32)) atomicOr(w32 + 1, static_cast<unsigned>(m64 >> 32));
+                  }
+                }
+              }
             }
+          }
+          if (any) {                // warp-uniform
+            __syncwarp();
+            kill = kill_w[lane];
+            kill_w[lane] = 0ull;
+            __syncwarp();
           }
         }
         mbar_wait(s_full + buf, ph);
@@ -398,8 +437,8 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            // (values above fp16's largest finite number -- an exp2 argument gone wrong -- must not become inf)
-            const float a = fminf(fmaxf(e[2 * i], -65504.0f), 65504.0f), b = fminf(fmaxf(e[2 * i + 1], -65504.0f), 65504.0f);
+            // (|E| <= 2^13 (1 + 1e-4) by construction of the exponent offsets: fp16 cannot overflow here)
+            const float a = e[2 * i], b = e[2 * i + 1];
             const uint32_t h2 = pack_f16x2(a, b);
             const float2 hf = unpack_f16x2(h2);
             hi[cb * 16 + i] = h2;
