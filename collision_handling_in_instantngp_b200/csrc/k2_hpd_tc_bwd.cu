@@ -57,7 +57,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SE_COL = 0;                            // two S / E buffers of 128 columns
 constexpr uint32_t O_COL = 256;                           // O accumulator, 128 columns
 constexpr uint32_t X_COL = 384;                           // resident X tile: plane p at [X_COL + 64 p, +64) (bf16 pairs)
-constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * 8 /*kill bits*/;
+constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 128 * 16 /*selected-slot masks*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* o_empty = o_full + 1;
   uint64_t* xt_full = o_empty + 1;         // X tile copied into tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
-  unsigned long long* kill_s = reinterpret_cast<unsigned long long*>(ring + RING * TILE_BYTES + 256);   // [EPI_WARPS][32]
+  unsigned* kill_s = reinterpret_cast<unsigned*>(ring + RING * TILE_BYTES + 256);   // [2 buffers][128 slots][4 words]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) kill_s[(warp - 2) * 32 + lane] = 0ull;
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < 2 * 128 * 4; i += 32 * EPI_WARPS) kill_s[i] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -302,68 +303,58 @@ __global__ void __launch_bounds__(THREADS, 1)
         nent += 1 + (t1 - t0);
       }
       float rsum = 0.0f;   // DW: db3[row] = sum of E over all streamed nodes
-      const int k_shift = (topk & (topk - 1)) == 0 ? __ffs(topk) - 1 : -1;   // log2(topk) when it is a power of two
-      unsigned long long* kill_w = kill_s + (warp - 2) * 32;
-      int nxt[2 * SB_MAX_K];   // DW: (selected slot - first slot of this warp) of the next Y tile's 64 nodes x topk
+      const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
+      int nxt[SB_MAX_K / 2];   // DW: selected slots of entries etid, etid + 256, .. of the next Y tile (-1: none)
       auto load_sel = [&](int tile) {
-        const int node0 = tile * SBN + half * 64;
-        const int first_slot = m0 + q * 32;
-        const int total = 64 * topk;
 #pragma unroll
-        for (int i = 0; i < 2 * SB_MAX_K; ++i) {
-          const int e_i = i * 32 + lane;
+        for (int i = 0; i < SB_MAX_K / 2; ++i) {
+          const int e_i = i * 256 + etid;          // k-major: entry = k * 128 + node
+          const int k = e_i >> 7, node = tile * SBN + (e_i & 127);
+          // (the RAW loaded value: any arithmetic on it here would wait for the load and undo the prefetch)
           nxt[i] = -1;
-          if (e_i < total && static_cast<int64_t>(node0) * topk + e_i < static_cast<int64_t>(y_rows) * topk)
-            nxt[i] = __ldg(utopi + static_cast<int64_t>(node0) * topk + e_i) - first_slot;
+          if (k < topk && node < y_rows) nxt[i] = __ldg(utopi + static_cast<int64_t>(node) * topk + k);
         }
       };
       if (DW) load_sel(t0);
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         const uint32_t se = tmem_base + lane_off + SE_COL + buf * SBN + half * 64;
-        // DW = true: which of this thread's 64 columns (nodes) selected this thread's slot?  The warp reads the 64 x topk
-        // selections of its nodes once per tile (coalesced; requested ONE TILE AHEAD so that their latency hides behind
-        // this tile's work).  An entry that falls into the warp's 32 slots must reach the lane that owns the slot: lanes
-        // holding the SAME slot (neighbouring nodes select the same slots: a popular slot is hit by all 64 nodes of every
-        // tile) first OR their node bits together (match.any + redux.or), and one of them ORs the result into the
-        // owner's word in shared memory -- a handful of shared-memory atomics per tile whatever the hit count.
+        // DW = true: which of this thread's 64 columns (nodes) selected this thread's slot?  The 256 epilogue threads share
+        // the tile's 128 x topk selections (one coalesced pass, requested ONE TILE AHEAD; thread e takes entries e, e + 256,
+        // ... in k-major order, so the 32 lanes of a warp hold the k-th choice of 32 neighbouring nodes -- mostly the SAME
+        // slot): an entry that falls into the CTA's 128 slots sets the node's bit in that slot's 128-bit mask in shared
+        // memory -- one atomic per warp when the lanes agree, one per lane otherwise -- and after a barrier among the
+        // epilogue warps every thread reads (and clears) the 64 bits of its own slot and half.  Two mask buffers
+        // alternate, so the clears of tile j are ordered before the atomics of tile j + 2 by the barrier of tile j + 1.
         uint64_t kill = 0;
         if (DW) {
-          const int total = 64 * topk;
-          int cur[2 * SB_MAX_K];
+          unsigned* kb = kill_s + (it & 1) * (128 * 4);
+          int cur[SB_MAX_K / 2];
 #pragma unroll
-          for (int i = 0; i < 2 * SB_MAX_K; ++i) cur[i] = nxt[i];
+          for (int i = 0; i < SB_MAX_K / 2; ++i) cur[i] = nxt[i];
           if (t + 1 < t1) load_sel(t + 1);
-          bool any = false;
 #pragma unroll
-          for (int i = 0; i < 2 * SB_MAX_K; ++i) {
-            if (i * 32 < total) {   // warp-uniform
-              const int d = cur[i];
-              const bool hit = d >= 0 && d < 32;
+          for (int i = 0; i < SB_MAX_K / 2; ++i) {
+            if (i * 256 < 128 * topk) {   // uniform
+              const int d = cur[i] - m0;      // slot - first slot of the X tile (cur = -1: no entry)
+              const bool hit = cur[i] >= 0 && d >= 0 && d < 128;
               const unsigned hits = __ballot_sync(0xffffffffu, hit);
-              if (hits) {           // warp-uniform
-                any = true;
-                if (hit) {
-                  const int e_i = i * 32 + lane;
-                  const int node = k_shift >= 0 ? (e_i >> k_shift) : (e_i / topk);
-                  const int base = k_shift >= 0 ? ((i * 32) >> k_shift) : ((i * 32) / topk);   // nodes of this round: base .. base + 32
-                  const unsigned same = __match_any_sync(hits, d);
-                  const unsigned bits = __reduce_or_sync(same, 1u << (node - base));
-                  if (lane == __ffs(same) - 1) {   // 32-bit shared-memory atomics (a 64-bit OR would be a CAS loop)
-                    const unsigned long long m64 = static_cast<unsigned long long>(bits) << base;
-                    unsigned* w32 = reinterpret_cast<unsigned*>(kill_w + d);
-                    if (static_cast<unsigned>(m64)) atomicOr(w32, static_cast<unsigned>(m64));
-                    if (static_cast<unsigned>(m64 >> 32)) atomicOr(w32 + 1, static_cast<unsigned>(m64 >> 32));
-                  }
+              if (hits) {                 // warp-uniform
+                const int d0 = __shfl_sync(0xffffffffu, d, __ffs(hits) - 1);
+                const int word = (etid & 127) >> 5;   // the warp's 32 nodes share one 32-bit word of every mask
+                if (__all_sync(0xffffffffu, !hit || d == d0)) {
+                  if (lane == 0) atomicOr(kb + d0 * 4 + word, hits);
+                } else if (hit) {
+                  atomicOr(kb + d * 4 + word, 1u << lane);
                 }
               }
             }
           }
-          if (any) {                // warp-uniform
-            __syncwarp();
-            kill = kill_w[lane];
-            kill_w[lane] = 0ull;
-            __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+          const uint2 mine = *reinterpret_cast<const uint2*>(kb + row_l * 4 + half * 2);
+          if (mine.x | mine.y) {
+            kill = (static_cast<uint64_t>(mine.y) << 32) | mine.x;
+            *reinterpret_cast<uint2*>(kb + row_l * 4 + half * 2) = make_uint2(0u, 0u);
           }
         }
         mbar_wait(s_full + buf, ph);
