@@ -600,23 +600,10 @@ __global__ void __launch_bounds__(256)
                              int T, int Kdim, int topk, const float* __restrict__ cand_v, const int* __restrict__ cand_i,
                              float* __restrict__ row_max, float* __restrict__ row_sum, float* __restrict__ utopv,
                              int* __restrict__ utopi) {
-  // A warp walks a run of RF_RUN consecutive nodes.  Neighbouring lattice nodes mostly share their candidates, so the last
-  // 8 distinct W rows (and bias values) stay in registers: the first form, a warp per node, read 8 x 512 B of W per node
-  // from the L2 -- 123 GB and 41 ms at BASELINE.json configs[3] with T = 2^14.
-  constexpr int RF_RUN = 32, RF_CACHE = 8;
-  const int64_t run = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
+  const int64_t u = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
   const int lane = threadIdx.x % 32;
-  const int64_t u0 = run * RF_RUN;
-  if (u0 >= U) return;
-  const int64_t u1 = min(static_cast<int64_t>(U), u0 + RF_RUN);
+  if (u >= U) return;
   const int c0 = lane * 4;   // Kdim <= 128, Kdim % 4 == 0
-  int cs[RF_CACHE];
-  float4 cw[RF_CACHE];
-  float cbias[RF_CACHE];
-#pragma unroll
-  for (int e = 0; e < RF_CACHE; ++e) cs[e] = -1;
-  int victim = 0;
-  for (int64_t u = u0; u < u1; ++u) {
   float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c0 < Kdim) hv = *reinterpret_cast<const float4*>(h + u * Kdim + c0);
   float z[KTOP], za[KTOP];
@@ -625,34 +612,13 @@ __global__ void __launch_bounds__(256)
   for (int k = 0; k < KTOP; ++k) {
     idx[k] = cand_i[u * KTOP + k];
     za[k] = cand_v[u * KTOP + k];
-    const bool valid = idx[k] >= 0 && idx[k] < T;
-    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float bv = 0.0f;
-    bool found = false;
-#pragma unroll
-    for (int e = 0; e < RF_CACHE; ++e) {
-      if (cs[e] == idx[k]) {   // (warp-uniform)
-        found = true;
-        wv = cw[e];
-        bv = cbias[e];
-      }
+    float acc = 0.0f;
+    if (idx[k] >= 0 && idx[k] < T && c0 < Kdim) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<int64_t>(idx[k]) * Kdim + c0));
+      acc = fmaf(hv.w, wv.w, fmaf(hv.z, wv.z, fmaf(hv.y, wv.y, hv.x * wv.x)));
     }
-    if (valid && !found) {
-      if (c0 < Kdim) wv = __ldg(reinterpret_cast<const float4*>(w + static_cast<int64_t>(idx[k]) * Kdim + c0));
-      bv = __ldg(bias + idx[k]);
-#pragma unroll
-      for (int e = 0; e < RF_CACHE; ++e) {
-        if (e == victim) {
-          cs[e] = idx[k];
-          cw[e] = wv;
-          cbias[e] = bv;
-        }
-      }
-      victim = (victim + 1) % RF_CACHE;
-    }
-    float acc = fmaf(hv.w, wv.w, fmaf(hv.z, wv.z, fmaf(hv.y, wv.y, hv.x * wv.x)));
     acc = warp_sum(acc);
-    z[k] = valid ? acc + bv : -INFINITY;   // (fewer than KTOP slots: T < 8)
+    z[k] = (idx[k] >= 0 && idx[k] < T) ? acc + __ldg(bias + idx[k]) : -INFINITY;   // (fewer than KTOP slots: T < 8)
   }
   // re-rank (insertion sort of 8, every lane redundantly)
   float zs[KTOP];
@@ -700,7 +666,6 @@ __global__ void __launch_bounds__(256)
     utopv[u * topk + lane] = p;
     utopi[u * topk + lane] = ik;
   }
-  }   // nodes of the run
 }
 
 // ---- two fp16 planes with a power-of-two scale ---------------------------------------------------------------------
@@ -964,7 +929,7 @@ int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const float* a_scale, 
       nullptr, nullptr, cand_v, cand_i);
   gngf::note_launch();
   if ((rc = gngf::check_launch())) return rc;
-  hpd_stream_refine_kernel<<<static_cast<unsigned>(gngf::ceil_div(gngf::ceil_div(U, 32) * 32, 256)), 256, 0, st>>>(
+  hpd_stream_refine_kernel<<<static_cast<unsigned>(gngf::ceil_div(U * 32, 256)), 256, 0, st>>>(
       h, w, bias, static_cast<int>(U), static_cast<int>(T), static_cast<int>(Kdim), topk, cand_v, cand_i, row_max, row_sum,
       utopv, utopi);
   gngf::note_launch();
