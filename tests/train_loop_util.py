@@ -53,7 +53,7 @@ def train_epochs(net, x, y, img_u8, shuffled, reordered, epochs, c=ID_4061):
     for _ in range(epochs):
         net.train()
         outputs = torch.empty((shape, 3), device=dev)
-        indices = torch.zeros((shape, c["L"], 4, int(K * 1 / pct)), device=dev)   # reference: torch.empty
+        indices = torch.empty((shape, c["L"], 4, int(K * 1 / pct)), device=dev)   # functions.py:179: torch.empty, as is
         losses, mses = [], []
         for b in range(num_batches):
             start, stop = b * int(pct * shape), (b + 1) * int(pct * shape)
