@@ -200,6 +200,30 @@ def test_linear_forward_backward(M, N, K, act):
     assert rel_err(dx.cpu().numpy(), (dz.astype(np.float64) @ w) * (xin > 0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(20001, 64, 32), (33000, 128, 64), (16384, 32, 64), (40007, 128, 128), (17000, 64, 64)])
+def test_skinny_linear_layers(M, N, K):
+    """The persistent skinny-layer kernels (k2_linear.cu: weights resident in shared memory, 128-row tiles; one-pass dW / db)
+    that serve the hidden HPD layers on large lattices: forward, dX with the ReLU mask, dW, db against float64."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn((M, K), device=DEV, generator=g)
+    w = torch.randn((N, K), device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    y = ops.linear_fwd(x, w, b, 1)
+    ref = torch.relu(x.double() @ w.double().T + b.double())
+    assert float((y.double() - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    dz = torch.randn((M, N), device=DEV, generator=g)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    xin = torch.relu(x)
+    dx = ops.linear_bwd(dz, xin, w, 1, True, dw, db)
+    assert float((dw.double() - dz.double().T @ xin.double()).abs().max()) < 1e-5 * float(dw.abs().max())
+    assert float((db.double() - dz.double().sum(0)).abs().max()) < 1e-5 * float(db.abs().max())
+    assert float((dx.double() - (dz.double() @ w.double()) * (xin > 0)).abs().max()) < 1e-5 * float(dx.abs().max())
+    # dW only / dX only (the call shapes of the small-lattice path)
+    dw2 = torch.zeros_like(w)
+    assert ops.linear_bwd(dz, xin, w, 0, False, dw2, None) is None
+    assert float((dw2 - dw).abs().max()) < 1e-5 * float(dw.abs().max())
+
+
 def test_linear_layers_with_more_than_65535_row_tiles():
     """67 M lattice nodes (the 8192^2 configuration) are > 65 535 row tiles of 64: the row tiles sit on grid.x."""
     M, N, K = 64 * 70000 + 7, 8, 4
