@@ -25,15 +25,20 @@ sys.path.insert(0, HERE)
 from run_main import install_matplotlib_stub  # noqa: E402
 
 
-def load_reference(ref_dir, device):
+def load_reference(ref_dir, device, impl="reference"):
+    """impl = "reference": everything is the reference's.  impl = "dropin": `models` resolves to this repository's drop-in
+    module (repository root ahead of the reference on sys.path, as in run_main.py); functions / utils / params stay the
+    reference's, so Loss and get_optimizer are its own."""
     import torch
     os.environ["WANDB_MODE"] = "disabled"
     install_matplotlib_stub()
     for name in ("functions", "models", "utils", "params"):
         sys.modules.pop(name, None)
     root = os.path.dirname(HERE)
-    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != root]       # never this repository's models.py
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != root]       # never this repository's models.py ...
     sys.path.insert(0, ref_dir)
+    if impl == "dropin":
+        sys.path.insert(0, root)                                                    # ... unless it is what is asked for
     real = torch.set_default_device
     try:
         if device == "cpu":
@@ -46,7 +51,11 @@ def load_reference(ref_dir, device):
     dev = torch.device(device)
     for m in (functions, models, utils):
         m.device = dev
-    assert os.path.realpath(models.__file__).startswith(os.path.realpath(ref_dir)), models.__file__
+    if impl == "dropin":
+        assert not os.path.realpath(models.__file__).startswith(os.path.realpath(ref_dir)), models.__file__
+    else:
+        assert os.path.realpath(models.__file__).startswith(os.path.realpath(ref_dir)), models.__file__
+    assert os.path.realpath(utils.__file__).startswith(os.path.realpath(ref_dir)), utils.__file__
     return functions, models, utils
 
 
@@ -89,38 +98,46 @@ def main():
     ap.add_argument("--workload", required=True, help="JSON of a bench.py WORKLOADS entry")
     ap.add_argument("--ref-dir", default=os.path.join(HERE, "_ref"))
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--impl", default="reference", choices=["reference", "dropin"])
+    ap.add_argument("--record", default="", help="npz: the loss of every step, the initial and the final parameters")
     a = ap.parse_args()
     import torch
     w = json.loads(a.workload)
     if a.device == "cpu":
         torch.set_num_threads(a.threads or os.cpu_count() or 1)
-    functions, models, utils = load_reference(os.path.abspath(a.ref_dir), a.device)
+    functions, models, utils = load_reference(os.path.abspath(a.ref_dir), a.device, a.impl)
     sys.path.insert(0, os.path.dirname(HERE))
     from bench import make_inputs                                               # the same synthetic batch as the GPU arm
     x_np, y_np = make_inputs(dict(w, P=a.points), 65535)
     x = torch.from_numpy(x_np).to(a.device)
     y = torch.from_numpy(y_np).to(a.device)
-    step, _ = make_step(functions, models, utils, w, x, y, a.device)
+    step, net = make_step(functions, models, utils, w, x, y, a.device)
+    init = {"init." + k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
+    losses = []
 
     def sync():
         if a.device == "cuda":
             torch.cuda.synchronize()
 
     for _ in range(a.warmup):
-        step()
+        losses.append(float(step().detach()))
     sync()
     times = []
     for _ in range(a.steps):
         sync()
         t0 = time.perf_counter()
         loss = step()
-        float(loss.detach())
+        losses.append(float(loss.detach()))
         sync()
         times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
     out = {"device": a.device, "points": a.points, "steps": a.steps, "warmup": a.warmup, "sec_per_step": sec,
            "samples_per_s": a.points / sec, "threads": int(torch.get_num_threads()) if a.device == "cpu" else None,
-           "loss": float(loss.detach()), "reference_models_file": os.path.realpath(models.__file__)}
+           "loss": float(loss.detach()), "models_file": os.path.realpath(models.__file__)}
+    out["impl"] = a.impl
+    if a.record:
+        final = {"final." + k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+        np.savez_compressed(a.record, losses=np.asarray(losses), **init, **final)
     if a.device == "cuda":
         out["peak_mem_gb"] = torch.cuda.max_memory_allocated() / 2 ** 30
         out["gpu"] = torch.cuda.get_device_name(0)
