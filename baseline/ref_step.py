@@ -100,6 +100,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--impl", default="reference", choices=["reference", "dropin"])
     ap.add_argument("--record", default="", help="npz: the loss of every step, the initial and the final parameters")
+    ap.add_argument("--perturb", type=float, default=0.0, help="multiply every parameter by 1 + PERTURB * N(0,1) before the "
+                    "first step (how fast does rounding-level noise grow in this configuration?)")
     a = ap.parse_args()
     import torch
     w = json.loads(a.workload)
@@ -112,6 +114,11 @@ def main():
     x = torch.from_numpy(x_np).to(a.device)
     y = torch.from_numpy(y_np).to(a.device)
     step, net = make_step(functions, models, utils, w, x, y, a.device)
+    if a.perturb:
+        g = torch.Generator(device=a.device).manual_seed(12345)
+        with torch.no_grad():
+            for prm in net.parameters():
+                prm.mul_(1.0 + a.perturb * torch.randn(prm.shape, generator=g, device=prm.device))
     init = {"init." + k: v.detach().cpu().numpy().copy() for k, v in net.state_dict().items()}
     losses = []
 
