@@ -241,6 +241,7 @@ constexpr int STREAM_EPI_WARPS = 16;                     // four per TMEM lane q
 constexpr int STREAM_COL_PARTS = STREAM_EPI_WARPS / 4;   // column parts per tile
 constexpr int STREAM_THREADS = 64 + 32 * STREAM_EPI_WARPS;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float DEAD_CHUNK_LOG2 = -130.0f;               // 2^x flushes to zero (ex2.approx.ftz) with 4 binades to spare
 
 struct RowTop {
   float v[KTOP];
@@ -472,10 +473,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
             comp *= sc;
             m2 = cmax2;
           }
-          float csum = 0.0f;
+          // A chunk whose largest logit sits more than 130 binades under the running maximum adds exactly nothing:
+          // ex2.approx.ftz returns 0 below 2^-126.  That is the common case once the HPD is fed integer lattice
+          // coordinates (models.py:416-418: logits O(1e2)..O(1e4), a one-hot softmax), and it takes the 16 MUFU.EX2 and
+          // the summation chain out of an epilogue that otherwise bounds this kernel (tensor pipe 58 % active).
+          // (!(x < y) rather than x >= y: a NaN logit keeps the full path and reaches the row sum as before.)
+          if (!(cmax2 - m2 < DEAD_CHUNK_LOG2)) {
+            float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // four chains instead of one 16-deep FADD chain
 #pragma unroll
-          for (int j = 0; j < 16; ++j) csum += fast_exp2(fmaf(z[j], LOG2E, -m2));   // one FFMA + MUFU.EX2 per element
-          {  // compensated accumulation of the chunk sums (rows are up to 2^22 columns long)
+            for (int j = 0; j < 16; ++j) cs[j & 3] += fast_exp2(fmaf(z[j], LOG2E, -m2));   // one FFMA + MUFU.EX2 per element
+            const float csum = (cs[0] + cs[1]) + (cs[2] + cs[3]);
+            // compensated accumulation of the chunk sums (rows are up to 2^22 columns long)
             const float y = csum - comp;
             const float tsum = ssum + y;
             comp = (tsum - ssum) - y;

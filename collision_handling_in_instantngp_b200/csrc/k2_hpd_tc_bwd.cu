@@ -77,6 +77,7 @@ constexpr int C_SA = 3;        // sa (as a float): exponent offset of the DW = t
 constexpr int C_MAXLA = 4;     // scratch: max over rows of log2|a_r| as ordered-int bits
 constexpr float E_SHIFT = 12.0f;
 constexpr int SB_MAX_K = 8;    // selected slots per node on the streaming path (the forward's KTOP)
+constexpr float DEAD_CHUNK_LOG2 = -130.0f;   // exp2 arguments below this give exactly 0 (ex2.approx.ftz flushes under 2^-126)
 
 // x_rows / y_rows: number of valid rows of X / Y (U or T); Kdim <= 128.
 // DW = false: X = h tile, rows carry (a, -max log2e), columns the bias;  DW = true: X = W3 tile, the other way round.
@@ -109,6 +110,11 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* o_empty = o_full + 1;
   uint64_t* xt_full = o_empty + 1;         // X tile copied into tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
+  // live_s[buf] = 1 + (running number of the last tile whose E in S / E buffer `buf` has a non-zero entry): written by
+  // the epilogue warps before they arrive on e_full, read by the MMA issuer after it (never cleared: a stale stamp
+  // cannot equal the current tile's)
+  volatile uint32_t* live_s = reinterpret_cast<volatile uint32_t*>(bars) + 48;   // byte 192 of the 256-byte barrier block
+  float* cmax_s = reinterpret_cast<float*>(bars) + 52;   // [2 buffers][4 chunks of 32 columns]: largest column offset
   unsigned* kill_s = reinterpret_cast<unsigned*>(ring + RING * TILE_BYTES + 256);   // [2 buffers][128 slots][4 words]
   float* col_s = reinterpret_cast<float*>(kill_s + 2 * 128 * 4);                    // [2 buffers][offset 128 | scale 128]
 
@@ -128,6 +134,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     mbar_init(o_full, 1);
     mbar_init(o_empty, EPI_WARPS);
     mbar_init(xt_full, EPI_WARPS);
+    live_s[0] = 0u;
+    live_s[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -230,21 +238,34 @@ __global__ void __launch_bounds__(THREADS, 1)
             const uint32_t eb = tmem_u + SE_COL + buf * SBN;
             const uint32_t yb = y_lo_mn + slot * (TILE_BYTES >> 4);
             const uint32_t d = tmem_u + O_COL;
+            // An E tile without a single non-zero fp16 entry adds nothing to O: its three products are not issued (the
+            // item's first tile always is -- it initialises the accumulator).  With the HPD fed integer lattice
+            // coordinates the softmax is one-hot and most tiles are like that (83 % at BASELINE.json configs[3]).
+            const bool live = (j == 1) || (live_s[buf] == it2 + 1u);   // warp-uniform: one shared-memory word
+            if (live) {
 #pragma unroll
-            for (int pr = 0; pr < 3; ++pr) {
-              const int pa = pr >> 1, pb = pr & 1;
+              for (int pr = 0; pr < 3; ++pr) {
+                const int pa = pr >> 1, pb = pr & 1;
 #pragma unroll
-              for (int k = 0; k < SBN / UMMA_K; ++k) {
-                // A: E plane pa in tensor memory: S columns 16k.. live at packed columns 64 (k / 4) + 32 pa + 8 (k % 4)
-                const uint32_t at = eb + 64 * (k >> 2) + 32 * pa + 8 * (k & 3);
-                // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*TP_BYTES apart),
-                //    K = streamed index (rows of 128 bytes, 16 rows = 2048 bytes per step)
-                const uint64_t bd = umma_desc_pack(yb + ((pb * TP_BYTES + k * UMMA_K * 128) >> 4));
-                umma_bf16_ts_lead(d, at, bd, idesc2, (j != 1) || (pr | k) != 0);
+                for (int k = 0; k < SBN / UMMA_K; ++k) {
+                  // A: E plane pa in tensor memory: S columns 16k.. live at packed columns 64 (k / 4) + 32 pa + 8 (k % 4)
+                  const uint32_t at = eb + 64 * (k >> 2) + 32 * pa + 8 * (k & 3);
+                  // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*TP_BYTES apart),
+                  //    K = streamed index (rows of 128 bytes, 16 rows = 2048 bytes per step)
+                  const uint64_t bd = umma_desc_pack(yb + ((pb * TP_BYTES + k * UMMA_K * 128) >> 4));
+                  umma_bf16_ts_lead(d, at, bd, idesc2, (j != 1) || (pr | k) != 0);
+                }
               }
             }
-            umma_commit_lead(e_empty + buf);
-            umma_commit_lead(r_empty + slot);
+            if (live) {
+              umma_commit_lead(e_empty + buf);
+              umma_commit_lead(r_empty + slot);
+            } else if (elect_one()) {
+              // nothing reads E(j-1) or Y_{j-1} any more (S(j-1) completed before the epilogue could write E): both are
+              // released at once instead of behind the S(j) products a commit would wait for
+              mbar_arrive(e_empty + buf);
+              mbar_arrive(r_empty + slot);
+            }
             ++it2;
           }
         }
@@ -341,7 +362,16 @@ __global__ void __launch_bounds__(THREADS, 1)
         // epilogue warps every thread reads (and clears) the 64 bits of its own slot and half.  Two mask buffers
         // alternate, so the clears of tile j are ordered before the atomics of tile j + 2 by the barrier of tile j + 1.
         float* cbuf = col_s + (it & 1) * 256;
-        cbuf[etid] = (!DW && etid < 128) ? pf_col * LOG2E : pf_col;
+        {
+          const float cval = (!DW && etid < 128) ? pf_col * LOG2E : pf_col;
+          cbuf[etid] = cval;
+          if (etid < 128) {   // warp-uniform: the four warps that hold the offsets; warp w = columns 32w.. = chunk w
+            float m = cval;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) cmax_s[(it & 1) * 4 + (etid >> 5)] = m;
+          }
+        }
         if (t + 1 < t1) load_col(t + 1);
         uint64_t kill = 0;
         if (DW) {
@@ -380,22 +410,60 @@ __global__ void __launch_bounds__(THREADS, 1)
         mbar_wait(s_full + buf, ph);
         tc_fence_after();
         uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
+        uint32_t nz = 0u;           // OR of every fp16 pair this thread writes
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const int c0 = t * SBN + half * 64 + cb * 32;
           uint32_t v[32];
           tmem_ld32(se + cb * 32, v);
+          {  // cheap bound first: arg_j = v_j k1 + (r_off + off_j) <= max(v) k1 + (r_off + max(off)) (k1 > 0, and fp32
+             // fma / add are monotone, so the bound holds in floating point too): 16 FMNMX3 decide most chunks
+            float vm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) vm = fmaxf(vm, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            if (fmaf(vm, k1, r_off + cmax_s[(it & 1) * 4 + half * 2 + cb]) < DEAD_CHUNK_LOG2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                hi[cb * 16 + i] = 0u;
+                mid[cb * 16 + i] = 0u;
+              }
+              continue;
+            }
+          }
           float e[32];
+          float amax = -INFINITY;   // largest exp2 argument of the chunk
           {
             const float* offp = cbuf + half * 64 + cb * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 off = *reinterpret_cast<const float4*>(offp + j);
-              const float4 sc = *reinterpret_cast<const float4*>(offp + 128 + j);
-              e[j + 0] = fast_exp2(fmaf(__uint_as_float(v[j + 0]), k1, r_off + off.x)) * sc.x;
-              e[j + 1] = fast_exp2(fmaf(__uint_as_float(v[j + 1]), k1, r_off + off.y)) * sc.y;
-              e[j + 2] = fast_exp2(fmaf(__uint_as_float(v[j + 2]), k1, r_off + off.z)) * sc.z;
-              e[j + 3] = fast_exp2(fmaf(__uint_as_float(v[j + 3]), k1, r_off + off.w)) * sc.w;
+              e[j + 0] = fmaf(__uint_as_float(v[j + 0]), k1, r_off + off.x);
+              e[j + 1] = fmaf(__uint_as_float(v[j + 1]), k1, r_off + off.y);
+              e[j + 2] = fmaf(__uint_as_float(v[j + 2]), k1, r_off + off.z);
+              e[j + 3] = fmaf(__uint_as_float(v[j + 3]), k1, r_off + off.w);
+              amax = fmaxf(fmaxf(amax, fmaxf(e[j + 0], e[j + 1])), fmaxf(e[j + 2], e[j + 3]));
+            }
+          }
+          // Dead chunk: every argument more than 130 binades down -- ex2.approx.ftz returns exactly 0 for each of them
+          // (it flushes below 2^-126), so E, its two planes and the chunk's share of db3 are exactly zero and the 32
+          // MUFU.EX2, the masks and the plane split are skipped.
+          if (amax < DEAD_CHUNK_LOG2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              hi[cb * 16 + i] = 0u;
+              mid[cb * 16 + i] = 0u;
+            }
+            continue;
+          }
+          {
+            const float* offp = cbuf + half * 64 + cb * 32 + 128;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(offp + j);
+              e[j + 0] = fast_exp2(e[j + 0]) * sc.x;
+              e[j + 1] = fast_exp2(e[j + 1]) * sc.y;
+              e[j + 2] = fast_exp2(e[j + 2]) * sc.z;
+              e[j + 3] = fast_exp2(e[j + 3]) * sc.w;
             }
           }
           {  // the selected slots belong to the sparse part
@@ -431,14 +499,19 @@ __global__ void __launch_bounds__(THREADS, 1)
             const float2 hf = unpack_f16x2(h2);
             hi[cb * 16 + i] = h2;
             mid[cb * 16 + i] = pack_f16x2(a - hf.x, b - hf.y);
+            nz |= h2;             // (mid = 0 wherever hi = 0: |a| < 2^-25 rounds to zero in both)
           }
         }
         // E over S, in place: this thread's 64 fp32 columns become 32 columns of hi pairs + 32 columns of mid pairs
         tmem_st32(se, hi);
         tmem_st32(se + 32, mid);
         tc_fence_before();
+        const bool warp_live = __any_sync(0xffffffffu, (nz & 0x7fff7fffu) != 0u);   // (-0 is zero)
         __syncwarp();
-        if (lane == 0) mbar_arrive(e_full + buf);
+        if (lane == 0) {
+          if (warp_live) live_s[buf] = it + 1u;   // every live warp stores the same stamp; released by the arrive below
+          mbar_arrive(e_full + buf);
+        }
       }
 
       // ---- O tile: accumulated in TMEM over the item's Y tiles -> global (reductions: other splits / the sparse part
@@ -664,8 +737,20 @@ __global__ void __launch_bounds__(256)
     if (cs[e] >= 0) flush(cs[e], ca[e], cb[e]);
 }
 
+// Column splits per X tile.  Work items are (X tile, split) pairs handed out round-robin to one CTA per SM.  Plenty of X
+// tiles (the dh pass of a large lattice): no split.  Few (the dW3 pass: T / 128 tiles): split so that the number of
+// items is a MULTIPLE of the SM count -- 128 tiles x 2 splits on 148 SMs left 40 SMs with half the work of the others
+// (14 % of that pass) -- with at least 64 Y tiles per item to amortise the X-tile load and the accumulator flush.
 static int split_count(int64_t x_tiles, int64_t y_tiles) {
-  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(y_tiles, (2 * gngf::sm_count()) / x_tiles)));
+  const int64_t sms = gngf::sm_count();
+  if (x_tiles >= 8 * sms) return 1;
+  int64_t g = x_tiles, b = sms;
+  while (b) { const int64_t t = g % b; g = b; b = t; }      // gcd
+  const int64_t unit = sms / g;                             // smallest split count with x_tiles * ns % sms == 0
+  const int64_t most = std::max<int64_t>(1, y_tiles / 64);  // keep items at >= 64 Y tiles
+  int64_t ns = std::max<int64_t>(1, (2 * sms) / x_tiles);   // the old rule: at least two items per SM
+  if (unit <= most) ns = unit * std::max<int64_t>(1, std::min<int64_t>(most / unit, (ns + unit - 1) / unit));
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ns, y_tiles)));
 }
 
 }  // namespace sb
