@@ -1,4 +1,5 @@
 // Library-level entry points of libgngf_sm100.so: status strings, device info, launch accounting.
+#include <cstdlib>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -20,6 +21,12 @@ int sm_count() {
       cached = n;
     else
       return 148;
+    // measurement aid (profiles/sm_limit_probe.py): persistent kernels launch on fewer SMs -- does a kernel's time scale
+    // with the SMs it runs on (bound inside the SM) or stay put (bound by the L2 / fabric they share)?
+    if (const char* lim = getenv("GNGF_DEBUG_SM_LIMIT")) {
+      const int v = atoi(lim);
+      if (v > 0 && v < cached) cached = v;
+    }
   }
   return cached;
 }

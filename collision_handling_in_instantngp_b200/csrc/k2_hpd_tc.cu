@@ -291,9 +291,24 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   uint64_t* a_empty = a_full + 1;
   uint64_t* b_full = a_empty + 1;
   uint64_t* b_empty = b_full + STAGES;
+  // Accumulator ring.  With two buffers a tile's MMAs may only start when the epilogue of the tile before last has
+  // drained its buffer, so the pair runs at (MMA + epilogue + hand-offs) / 2 per tile whenever epilogue + hand-offs
+  // exceed the MMA time (measured: 2 407 cycles per tile against 1 578 of tensor work, both sides 27 % idle waiting for
+  // each other).  The two-plane pass keeps its row tile in tensor memory, which leaves exactly one more 128-column
+  // accumulator: 3 x 128 + 128 = 512 columns.
+  constexpr int NACC = NPROD == 3 ? 3 : 2;
   uint64_t* tfull = b_empty + STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + NACC;
+  uint64_t* at_full = tempty + NACC;             // A_IN_TMEM: the row tile has been copied into tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(at_full + 1);
+  // Two-plane pass: the resident row tile is the A operand from TENSOR MEMORY (columns 256..383: plane p at +64 p,
+  // 8 columns per K = 16 step), copied there once per item by eight epilogue warps -- with both operands in shared
+  // memory every 128x128x16 MMA reads 8 KB in 64 cycles, which is all the 128 B/clk an SM's shared memory delivers,
+  // before the 64 KB per tile that TMA writes into the ring: 256 KB per tile = 2 048 cycles against 1 536 of tensor
+  // work.  (Measured once before and rejected, 338 vs 343 ms, when the epilogue bounded the kernel; it no longer does.)
+  constexpr bool A_IN_TMEM = NPROD == 3;
+  constexpr uint32_t A_COL = NACC * BN;
+  constexpr uint32_t TMEM_ALLOC = A_IN_TMEM ? 512u : TMEM_COLS;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   if (warp == 0 && lane == 0) {
@@ -301,11 +316,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
+    mbar_init(at_full, 8);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(b_full + s, 1);
       mbar_init(b_empty + s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(tfull + s, 1);
       mbar_init(tempty + s, STREAM_EPI_WARPS);
     }
@@ -313,7 +329,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
+                 "r"(TMEM_ALLOC)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -369,9 +385,16 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int sp = w % n_split;
         const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
-        mbar_wait(a_full, a_phase);
-        a_phase ^= 1;
-        tc_fence_after();
+        if (A_IN_TMEM) {
+          mbar_wait(at_full, a_phase);
+          a_phase ^= 1;
+          tc_fence_after();
+          if (elect_one()) mbar_arrive(a_empty);   // the shared-memory copy is free for the next item's row tile
+        } else {
+          mbar_wait(a_full, a_phase);
+          a_phase ^= 1;
+          tc_fence_after();
+        }
         for (int nt = nt0; nt < nt1; ++nt) {
           mbar_wait(tempty + acc, acc_phase ^ 1);
           tc_fence_after();
@@ -385,9 +408,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
             for (int pr = 0; pr < NPROD; ++pr) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
-                const uint64_t ad = umma_desc_pack(a_lo + ((pa[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
                 const uint64_t bd = umma_desc_pack(b_lo + ((pb[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
-                umma_bf16_lead(d, ad, bd, idesc, (kb | pr | k) != 0);
+                if (A_IN_TMEM) {
+                  umma_bf16_ts_lead(d, tmem_u + A_COL + pa[pr] * 64 + kb * 32 + k * 8, bd, idesc, (kb | pr | k) != 0);
+                } else {
+                  const uint64_t ad = umma_desc_pack(a_lo + ((pa[pr] * PLANE_BYTES + k * UMMA_K * 2) >> 4));
+                  umma_bf16_lead(d, ad, bd, idesc, (kb | pr | k) != 0);
+                }
               }
             }
             umma_commit_lead(b_empty + stage);
@@ -397,12 +424,12 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
             }
           }
           umma_commit_lead(tfull + acc);
-          if (++acc == 2) {
+          if (++acc == NACC) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
-        umma_commit_lead(a_empty);  // every MMA that reads the resident A tile has completed
+        if (!A_IN_TMEM) umma_commit_lead(a_empty);  // every MMA that reads the resident A tile has completed
       }
     }
   } else {  // ---- epilogue warps 2..17: thread = (lattice node, 32-column part of every tile) ----
@@ -415,10 +442,38 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     // the accumulator holds (h 2^sa)(W 2^sb)^T: undo the operands' power-of-two scales in the bias FMA
     const float inv = (a_scale ? __ldg(a_scale) : 1.0f) * (b_scale ? __ldg(b_scale) : 1.0f);
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, at_phase = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int m0 = (w / n_split) * BM, sp = w % n_split;
       const int nt0 = sp * tiles_per_split, nt1 = min(col_tiles, nt0 + tiles_per_split);
+      if (A_IN_TMEM && part < 2) {
+        // (every MMA of the previous item has completed: this warp has seen the tfull of its last tile.)  Row tile:
+        // shared memory (TMA, 128-byte swizzle, [k-block][plane] x 16 KB) -> tensor memory; warp (q, part) copies
+        // plane `part` of rows 32 q .. 32 q + 31
+        mbar_wait(a_full, at_phase);
+        at_phase ^= 1;
+        const int row_l = q * 32 + lane;
+        const uint8_t* xrow = a_buf + (row_l >> 3) * 1024 + (row_l & 7) * 128;
+#pragma unroll 1
+        for (int kb = 0; kb < A_KBLOCKS; ++kb) {
+          uint32_t v[32];
+          if (kb < kblocks) {
+            const uint8_t* src = xrow + (kb * NPL + part) * PLANE_BYTES;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 c = *reinterpret_cast<const uint4*>(src + ((ch ^ (row_l & 7)) << 4));
+              v[ch * 4 + 0] = c.x; v[ch * 4 + 1] = c.y; v[ch * 4 + 2] = c.z; v[ch * 4 + 3] = c.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          tmem_st32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + A_COL + part * 64 + kb * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(at_full);
+      }
       // running statistics in the base-2 domain: m2 = max(z) * log2(e), ssum = sum 2^(z*log2e - m2)
       float m2 = -INFINITY, ssum = 0.0f, comp = 0.0f;
       RowTop top;
@@ -498,7 +553,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty + acc);
-        if (++acc == 2) {
+        if (++acc == NACC) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -523,7 +578,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC) : "memory");
   }
 }
 
