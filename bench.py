@@ -324,9 +324,10 @@ def algorithmic_cost(name, key, w, lat):
     if name == "gngf_tc_gemm_bf16x3":
         return "tensor", 6 * 2.0 * float(key[0]) * key[1] * key[2]
     if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
-        # two fused passes (dh, dW3), each: logits recomputed (3 split products) + second product (3 split products);
-        # useful work = the two gradient products, 2 * 2*U*T*kd
-        return "tensor", 12 * 2.0 * Ua * T * kd
+        # two fused passes (dh, dW3), each: logits recomputed (3 split products, every tile) + second product (3 split
+        # products, only on the tiles whose E is not all zero: fraction f counted on the device during the profiled
+        # steps, gngf_hpd_stream_bwd_stats); useful work = the two gradient products, 2 * 2*U*T*kd
+        return "tensor", (6 + 6 * w.get("_stream_live_frac", 1.0)) * 2.0 * Ua * T * kd
     table = {
         # per point: x (8) + per level 4 node-feature gathers (4*F*4) + enc row (F*4) + 4 multiplicity atomics (4*4)
         "gngf_encode_fwd": P * (8 + L * (4 * F * 4 + F * 4 + 16)),
@@ -367,7 +368,7 @@ def useful_tflops(name, achieved, w):
     if name == "gngf_hpd_stream_fwd_refined":
         return achieved / 3
     if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
-        return achieved / 6                       # 12 executed passes for the 2 gradient products
+        return achieved * 2 / (6 + 6 * w.get("_stream_live_frac", 1.0))   # executed passes for the 2 gradient products
     if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
         dims = [w["L"] * w["F"], *w["mlp"], 3]
         useful = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * (1 if name == "gngf_mlp3_tc_fwd" else 2)
@@ -494,6 +495,7 @@ def measure(torch, dist, R, steps, warmup, *, profile, eager_e2e, graph, flush):
 
     if profile:        # per-kernel device times (CUDA events around every C-ABI call, serial schedule) -> dominant kernel
         prof = CallProfiler(torch)
+        _ops.stream_bwd_stats(reset=True)
         _lib.PROFILER = prof
         _ops.CONCURRENT = False
         for _ in range(profile):
@@ -503,6 +505,9 @@ def measure(torch, dist, R, steps, warmup, *, profile, eager_e2e, graph, flush):
         _lib.PROFILER = None
         out["profile"] = prof.summary()
         out["profile_steps"] = profile
+        # tiles of the streaming backward's two dense passes and how many of them issued their second product (it is
+        # skipped for all-zero E tiles: the executed tensor work depends on the data)
+        out["stream_bwd_stats"] = _ops.stream_bwd_stats(reset=True)
     st = R.net.last_state
     out["lat"] = st.lat
     ids = st.node_ids_all if st.shard is not None else st.node_ids
@@ -628,7 +633,13 @@ def run_ours(args):
     m = measure(torch, dist, R, args.steps, args.warmup, profile=prof_steps, eager_e2e=graph, graph=graph, flush=flush)
     clocks = sampler.stop()
     wp = dict(w, P=R.local_points, _active_nodes=m["hpd_rows_this_rank"])
+    st = m.get("stream_bwd_stats")
+    if st and (st[0] + st[2]) > 0:
+        wp["_stream_live_frac"] = (st[1] + st[3]) / float(st[0] + st[2])
     roofline = roofline_of(m, wp, prof_steps, name)
+    if st and (st[0] + st[2]) > 0:
+        roofline["stream_bwd_tiles"] = {"dh_pass": st[0], "dh_second_product_issued": st[1], "dw3_pass": st[2],
+                                        "dw3_second_product_issued": st[3], "profiled_steps": prof_steps}
     dev_ms, e2e_ms, e2e_eager_ms = m["dev_ms"], m["e2e_ms"], m.get("e2e_eager_ms", m["e2e_ms"])
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms, e2e_eager_ms], device=dev, dtype=torch.float64)

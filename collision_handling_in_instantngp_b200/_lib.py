@@ -94,6 +94,7 @@ SIGNATURES = {
     "gngf_hpd_stream_fwd_refined": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P,
                                             _P, _P]),
     "gngf_hpd_stream_bwd_workspace_floats": (c_int64, [c_int64, c_int32]),
+    "gngf_hpd_stream_bwd_stats": (c_int, [c_void_p, c_int32]),
     "gngf_hpd_stream_bwd": (c_int, [Lattice, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, _P,
                                     _P, _P, _P, c_int32, _P, _P, _P, _P, _P]),
     "gngf_hpd_stream_bwd_nodes": (c_int, [Lattice, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int32, _P,

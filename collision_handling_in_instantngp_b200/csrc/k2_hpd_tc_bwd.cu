@@ -87,6 +87,11 @@ constexpr float DEAD_CHUNK_LOG2 = -130.0f;   // exp2 arguments below this give e
 //   -> O += E Y (A = E from tensor memory, B = the same Y tile read MN-major).
 // Neither product reads its A operand from shared memory, so the only shared-memory operand traffic is the Y tile
 // (4 KB per 128x128x16 MMA = 64 B/clk), and the ring holds 128-row tiles (X travels through it once per item).
+// [0] tiles, [1] tiles whose second product was issued -- DW = false; [2], [3] the same for DW = true.  Accumulated over
+// launches until gngf_hpd_stream_bwd_stats() reads and clears them: what bench.py needs to state the EXECUTED tensor work
+// of a pass whose second product is data dependent.
+__device__ unsigned long long g_stream_stats[4];
+
 template <bool DW>
 __global__ void __launch_bounds__(THREADS, 1)
     hpd_stream_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
@@ -156,6 +161,12 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int items = x_tiles * n_split;
   const int kblocks = (Kdim + BK - 1) / BK;   // 1 or 2
   const int n2 = kblocks * BK;                // N of the second product (columns of O)
+  // Item w -> (X tile, split of the Y stream).  DW = false: the Y stream is W3 (L2-resident), consecutive items walk the
+  // splits of one X tile.  DW = true: the Y stream is the h planes of every node (15 GB at BASELINE.json configs[3]) and
+  // is streamed once PER X TILE, so consecutive items -- the CTAs that run at the same time -- take the SAME split of
+  // different X tiles: one HBM read of an h tile serves ~128 CTAs out of the L2 instead of ~4.
+  auto item_x = [&](int w) { return DW ? w % x_tiles : w / n_split; };
+  auto item_split = [&](int w) { return DW ? w / x_tiles : w % n_split; };
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer: per item the X tile, then its Y tiles, all through one ring ----
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         ++n;
       };
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        const int m0 = (w / n_split) * BM, sp = w % n_split;
+        const int m0 = item_x(w) * BM, sp = item_split(w);
         const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
         if (t0 >= t1) continue;   // empty split (every role skips it)
         load_tile(&map_x, m0);
@@ -184,11 +195,19 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint32_t idesc2 = umma_idesc_fmt(BM, n2, 0, 0) | UMMA_B_MN_MAJOR;
       const uint32_t y_lo = umma_desc_lo(smem_u32(ring));                      // K-major view (first product)
       const uint32_t y_lo_mn = umma_desc_lo(smem_u32(ring), NP * TP_BYTES);    // MN-major view (second product)
-      uint32_t nent = 0;                       // ring entries consumed before this item
-      uint32_t it1 = 0, it2 = 0;               // running tile counters (S / E buffer = counter & 1)
+      // Ring position and S / E buffer of the next S product and of the next O product as wrap-around counters: they
+      // stay in the uniform datapath, and so do the 24 descriptors derived from them.  (`entry % RING` is an IMAD.HI in
+      // the vector datapath: every descriptor then took an R2UR.BROADCAST to reach the UTCHMMA -- 424 instructions per
+      // tile in this warp, ~1 400 cycles against 1 536 of tensor work, serial with the wait for the epilogue.)
+      uint32_t rs = 0, rph = 0;                // ring slot / phase of the next entry to consume
+      uint32_t os = 0;                         // ring slot of the next O product's Y tile
+      uint32_t sbuf = 0, sph = 0;              // S / E buffer and phase of the next S product
+      uint32_t obuf = 0, oph = 0;              // ... of the next O product
+      uint32_t it2 = 0;                        // running tile counter of the O side (the epilogue's liveness stamp)
+      uint32_t n_live = 0;                     // tiles whose second product was issued
       uint32_t x_phase = 0, o_phase = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        const int sp = w % n_split;
+        const int sp = item_split(w);
         const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
         const int nt = t1 - t0;
         if (nt <= 0) continue;
@@ -196,14 +215,18 @@ __global__ void __launch_bounds__(THREADS, 1)
         mbar_wait(xt_full, x_phase);
         x_phase ^= 1;
         tc_fence_after();
-        if (elect_one()) mbar_arrive(r_empty + nent % RING);
-        const uint32_t y0 = nent + 1;          // ring entry of this item's first Y tile
+        if (elect_one()) mbar_arrive(r_empty + rs);
+        if (++rs == RING) {
+          rs = 0;
+          rph ^= 1;
+        }
+        os = rs;                               // ring slot of this item's first Y tile
         for (int j = 0; j <= nt; ++j) {
           if (j < nt) {  // S(j) = X Y_j^T : products hi.hi, hi.mid, mid.hi
-            const uint32_t buf = it1 & 1, ph = (it1 >> 1) & 1;
-            const uint32_t ent = y0 + j, slot = ent % RING;
-            mbar_wait(r_full + slot, (ent / RING) & 1);
-            mbar_wait(e_empty + buf, ph ^ 1);    // the second product of tile it1 - 2 has finished reading this buffer
+            const uint32_t buf = sbuf, ph = sph;
+            const uint32_t slot = rs;
+            mbar_wait(r_full + slot, rph);
+            mbar_wait(e_empty + buf, ph ^ 1);    // the second product of the tile before last has finished with this buffer
             tc_fence_after();
             const uint32_t yb = y_lo + slot * (TILE_BYTES >> 4);
             const uint32_t d = tmem_u + SE_COL + buf * SBN;
@@ -224,11 +247,16 @@ __global__ void __launch_bounds__(THREADS, 1)
               }
             }
             umma_commit_lead(s_full + buf);
-            ++it1;
+            if (++rs == RING) {
+              rs = 0;
+              rph ^= 1;
+            }
+            sph ^= sbuf;                         // (the phase flips when the buffer index wraps 1 -> 0)
+            sbuf ^= 1;
           }
           if (j >= 1) {  // O += E(j-1) Y_{j-1}
-            const uint32_t buf = it2 & 1, ph = (it2 >> 1) & 1;
-            const uint32_t slot = (y0 + j - 1) % RING;
+            const uint32_t buf = obuf, ph = oph;
+            const uint32_t slot = os;
             mbar_wait(e_full + buf, ph);
             if (j == 1) {
               mbar_wait(o_empty, o_phase ^ 1);   // the previous item's O has been read out
@@ -241,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             // An E tile without a single non-zero fp16 entry adds nothing to O: its three products are not issued (the
             // item's first tile always is -- it initialises the accumulator).  With the HPD fed integer lattice
             // coordinates the softmax is one-hot and most tiles are like that (83 % at BASELINE.json configs[3]).
-            const bool live = (j == 1) || (live_s[buf] == it2 + 1u);   // warp-uniform: one shared-memory word
+            const bool live = (j == 1) || __any_sync(0xffffffffu, live_s[buf] == it2 + 1u);   // (a vote: provably warp-uniform)
             if (live) {
 #pragma unroll
               for (int pr = 0; pr < 3; ++pr) {
@@ -258,6 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1)
               }
             }
             if (live) {
+              ++n_live;
               umma_commit_lead(e_empty + buf);
               umma_commit_lead(r_empty + slot);
             } else if (elect_one()) {
@@ -267,10 +296,16 @@ __global__ void __launch_bounds__(THREADS, 1)
               mbar_arrive(r_empty + slot);
             }
             ++it2;
+            if (++os == RING) os = 0;
+            oph ^= obuf;
+            obuf ^= 1;
           }
         }
         umma_commit_lead(o_full);
-        nent += 1 + nt;
+      }
+      if (elect_one()) {
+        atomicAdd(g_stream_stats + (DW ? 2 : 0), static_cast<unsigned long long>(it2));
+        atomicAdd(g_stream_stats + (DW ? 3 : 1), static_cast<unsigned long long>(n_live));
       }
     }
   } else {  // ---- epilogue warps 2..9 ----
@@ -280,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t it = 0, o_phase = 0, nent = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
-      const int m0 = (w / n_split) * BM, sp = w % n_split;
+      const int m0 = item_x(w) * BM, sp = item_split(w);
       const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
       if (t0 >= t1) continue;
       const int row = m0 + row_l;
@@ -411,16 +446,25 @@ __global__ void __launch_bounds__(THREADS, 1)
         tc_fence_after();
         uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
         uint32_t nz = 0u;           // OR of every fp16 pair this thread writes
+        // both 32-column chunks are requested before the wait: what follows the accumulator is a latency chain (load ->
+        // maximum -> bound -> store -> arrive) that the MMA issuer waits for, not a throughput problem
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(se, va);
+        tmem_ld32_nowait(se + 32, vb);
+        tmem_wait_ld();
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const int c0 = t * SBN + half * 64 + cb * 32;
-          uint32_t v[32];
-          tmem_ld32(se + cb * 32, v);
+          uint32_t(&v)[32] = cb ? vb : va;
           {  // cheap bound first: arg_j = v_j k1 + (r_off + off_j) <= max(v) k1 + (r_off + max(off)) (k1 > 0, and fp32
-             // fma / add are monotone, so the bound holds in floating point too): 16 FMNMX3 decide most chunks
-            float vm = -INFINITY;
+             // fma / add are monotone, so the bound holds in floating point too): a tree of 16 FMNMX3 decides most chunks
+            float m8[8];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) vm = fmaxf(vm, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+            for (int j = 0; j < 8; ++j)
+              m8[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                            fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            const float vm = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                   fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
             if (fmaf(vm, k1, r_off + cmax_s[(it & 1) * 4 + half * 2 + cb]) < DEAD_CHUNK_LOG2) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -503,8 +547,9 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
         // E over S, in place: this thread's 64 fp32 columns become 32 columns of hi pairs + 32 columns of mid pairs
-        tmem_st32(se, hi);
-        tmem_st32(se + 32, mid);
+        tmem_st32_nowait(se, hi);
+        tmem_st32_nowait(se + 32, mid);
+        tmem_wait_st();
         tc_fence_before();
         const bool warp_live = __any_sync(0xffffffffu, (nz & 0x7fff7fffu) != 0u);   // (-0 is zero)
         __syncwarp();
@@ -846,6 +891,20 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const float*
   return gngf_hpd_stream_bwd_nodes(lat, nullptr, h_planes, h_scale, w_planes, w_scale, h, w, bias, U, T, Kdim, topk, utopv,
                                    utopi, dtv, cnt,
                                    gcol_k, row_max, row_sum, act_prev, dh, dw, db, workspace, stream);
+}
+
+int gngf_hpd_stream_bwd_stats(uint64_t* out4, int32_t reset) {
+  if (!out4) return GNGF_ERR_INVALID_ARGUMENT;
+  unsigned long long h[4] = {0, 0, 0, 0};
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpyFromSymbol(h, gngf::tc::sb::g_stream_stats, sizeof(h)) != cudaSuccess)
+    return gngf::check_launch();
+  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(gngf::tc::sb::g_stream_stats, z, sizeof(z)) != cudaSuccess) return gngf::check_launch();
+  }
+  return GNGF_OK;
 }
 
 }  // extern "C"

@@ -363,6 +363,15 @@ def gather_rows(x, lat: Lattice, uvals: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
+def stream_bwd_stats(reset=False):
+    """[dh-pass tiles, of which issued their second product, dW3-pass tiles, of which issued] since the last reset
+    (gngf.h: gngf_hpd_stream_bwd_stats); synchronises the device.  bench.py's executed-FLOP accounting."""
+    import ctypes
+    out = (ctypes.c_uint64 * 4)()
+    call("gngf_hpd_stream_bwd_stats", ctypes.cast(out, ctypes.c_void_p), 1 if reset else 0)
+    return [int(v) for v in out]
+
+
 def active_nodes(x: torch.Tensor, lat: Lattice, shard=None) -> torch.Tensor:
     """Ascending int32 ids of the lattice nodes that the corners of x touch (k11_active_nodes.cu).  One
     device->host read of the count (the list sizes every launch of the HPD chain).  With `shard` (dp.NodeSharding) the
