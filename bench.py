@@ -245,10 +245,10 @@ class CallProfiler:
 # `ncu --set full` captures (profiles/r01_*_ncu_full.txt); None where no capture exists yet
 NCU_TRAFFIC = {("cfg2", "gngf_mlp3_bwd"): 2606080, ("cfg2", "gngf_mlp3_fwd"): 1892096,
                ("cfg2", "gngf_mlp3_tc_bwd"): 4250112, ("cfg2", "gngf_mlp3_tc_fwd"): 1924608,
-               # configs[3] / T = 2^14 (profiles/r02_cfg4_t14_stream_ncu_full.txt, r02_cfg4_t14_stream_fwd_ncu_full.txt): the dh
-               # pass of the streaming backward (31.02 GB read + 15.32 GB written; the dW3 pass of the same C call moves
-               # the same planes again and was not captured), the streaming forward pass (15.43 + 8.62 GB)
-               ("cfg4_t14", "gngf_hpd_stream_bwd_nodes"): 46342624000,
+               # configs[3] / T = 2^14 (profiles/r02_cfg4_t14_stream_skip_ncu.txt): the dh pass of the streaming backward
+               # (31.48 GB read + 15.32 GB written; the dW3 pass of the same C call moves the same planes again: ncu
+               # returned no counters for it), the streaming forward pass (15.43 + 8.62 GB)
+               ("cfg4_t14", "gngf_hpd_stream_bwd_nodes"): 46799761000,
                ("cfg4_t14", "gngf_hpd_stream_fwd_refined"): 24050862000,
                ("cfg3_t14", "gngf_hpd_stream_bwd"): 441328128,
                ("cfg3_t14", "gngf_hpd_stream_fwd"): 154538000, ("cfg3_t14", "gngf_tc_gemm_bf16x3"): 2802181000}
