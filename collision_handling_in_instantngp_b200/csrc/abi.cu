@@ -31,6 +31,11 @@ int sm_count() {
   return cached;
 }
 
+int debug_no_skip() {
+  const char* v = getenv("GNGF_DEBUG_NO_SKIP");
+  return (v && v[0] == '1') ? 1 : 0;
+}
+
 int check_launch() {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return GNGF_OK;

@@ -12,6 +12,7 @@ void note_launch(int n = 1);
 int check_launch();  // cudaGetLastError -> gngf_status, remembers the message for gngf_strerror
 
 int sm_count();       // multiprocessors of the current device (cached)
+int debug_no_skip();  // GNGF_DEBUG_NO_SKIP=1 (read on every call; tests only): the streaming kernels skip nothing
 
 // number of leading level nodes (the coarsest levels are stored first) that fit a shared-memory budget
 inline int private_node_count(const gngf_lattice& lat, int64_t max_nodes) {

@@ -276,7 +276,7 @@ template <int NPROD>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
     hpd_stream_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const float* __restrict__ bias, const float* __restrict__ a_scale,
-                          const float* __restrict__ b_scale, int U, int T, int Kdim, int topk, int n_split,
+                          const float* __restrict__ b_scale, int U, int T, int Kdim, int topk, int n_split, int no_skip,
                           float* __restrict__ part_max, float* __restrict__ part_sum, float* __restrict__ part_topv,
                           int* __restrict__ part_topi) {
   extern __shared__ uint8_t smem_raw[];
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
           // coordinates (models.py:416-418: logits O(1e2)..O(1e4), a one-hot softmax), and it takes the 16 MUFU.EX2 and
           // the summation chain out of an epilogue that otherwise bounds this kernel (tensor pipe 58 % active).
           // (!(x < y) rather than x >= y: a NaN logit keeps the full path and reaches the row sum as before.)
-          if (!(cmax2 - m2 < DEAD_CHUNK_LOG2)) {
+          if (no_skip || !(cmax2 - m2 < DEAD_CHUNK_LOG2)) {
             float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // four chains instead of one 16-deep FADD chain
 #pragma unroll
             for (int j = 0; j < 16; ++j) cs[j & 3] += fast_exp2(fmaf(z[j], LOG2E, -m2));   // one FFMA + MUFU.EX2 per element
@@ -935,7 +935,8 @@ int gngf_hpd_stream_fwd(const uint16_t* a_planes, const uint16_t* b_planes, cons
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
   hpd_stream_fwd_kernel<6><<<grid, STREAM_THREADS, StreamPlan<6>::SMEM, st>>>(map_a, map_b, bias, nullptr, nullptr, static_cast<int>(U),
                                                                      static_cast<int>(T), static_cast<int>(Kdim), topk,
-                                                                     n_split, part_max, part_sum, part_topv, part_topi);
+                                                                     n_split, gngf::debug_no_skip(), part_max, part_sum, part_topv,
+                                                                     part_topi);
   gngf::note_launch();
   rc = gngf::check_launch();
   if (rc) return rc;
@@ -984,7 +985,8 @@ int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const float* a_scale, 
   const int grid = static_cast<int>(std::min<int64_t>(row_tiles * n_split, gngf::sm_count()));
   hpd_stream_fwd_kernel<3><<<grid, STREAM_THREADS, StreamPlan<3>::SMEM, st>>>(map_a, map_b, bias, a_scale, b_scale, static_cast<int>(U),
                                                                      static_cast<int>(T), static_cast<int>(Kdim), KTOP,
-                                                                     n_split, part_max, part_sum, part_topv, part_topi);
+                                                                     n_split, gngf::debug_no_skip(), part_max, part_sum, part_topv,
+                                                                     part_topi);
   gngf::note_launch();
   if ((rc = gngf::check_launch())) return rc;
   hpd_stream_merge_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 128)), 128, 0, st>>>(

@@ -97,8 +97,10 @@ __global__ void __launch_bounds__(THREADS, 1)
     hpd_stream_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                           int x_rows, int y_rows, int Kdim, int n_split, const float* __restrict__ bias,
                           const float* __restrict__ m2neg, const float* __restrict__ ascale,
-                          const float* __restrict__ consts, const int* __restrict__ utopi, int topk,
+                          const float* __restrict__ consts, const int* __restrict__ utopi, int topk, int no_skip,
                           float* __restrict__ out, float* __restrict__ dbias) {
+  // no_skip (GNGF_DEBUG_NO_SKIP=1, tests only): every chunk takes the full path and every tile issues its second product
+  // -- the reference point for "skipping changes nothing"
   // utopi (nodes, topk): the selected slots, masked out of E (DW = false: nodes are the X rows; DW = true: the Y rows)
   // m2neg / ascale: DW = false: per ROW  -max_r log2e          / a_r (applied at the flush);
   //                 DW = true : per COLUMN -max_r log2e + log2|a_r| / sgn(a_r)
@@ -269,7 +271,8 @@ __global__ void __launch_bounds__(THREADS, 1)
             // An E tile without a single non-zero fp16 entry adds nothing to O: its three products are not issued (the
             // item's first tile always is -- it initialises the accumulator).  With the HPD fed integer lattice
             // coordinates the softmax is one-hot and most tiles are like that (83 % at BASELINE.json configs[3]).
-            const bool live = (j == 1) || __any_sync(0xffffffffu, live_s[buf] == it2 + 1u);   // (a vote: provably warp-uniform)
+            const bool live = (j == 1) || no_skip != 0 ||
+                              __any_sync(0xffffffffu, live_s[buf] == it2 + 1u);   // (a vote: provably warp-uniform)
             if (live) {
 #pragma unroll
               for (int pr = 0; pr < 3; ++pr) {
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                             fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
             const float vm = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
                                    fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-            if (fmaf(vm, k1, r_off + cmax_s[(it & 1) * 4 + half * 2 + cb]) < DEAD_CHUNK_LOG2) {
+            if (!no_skip && fmaf(vm, k1, r_off + cmax_s[(it & 1) * 4 + half * 2 + cb]) < DEAD_CHUNK_LOG2) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 hi[cb * 16 + i] = 0u;
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           // Dead chunk: every argument more than 130 binades down -- ex2.approx.ftz returns exactly 0 for each of them
           // (it flushes below 2^-126), so E, its two planes and the chunk's share of db3 are exactly zero and the 32
           // MUFU.EX2, the masks and the plane split are skipped.
-          if (amax < DEAD_CHUNK_LOG2) {
+          if (!no_skip && amax < DEAD_CHUNK_LOG2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               hi[cb * 16 + i] = 0u;
@@ -856,13 +859,14 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
                            static_cast<int>(SMEM_BYTES)) != cudaSuccess)
     return gngf::check_launch();
   const int sms = gngf::sm_count();
+  const int no_skip = gngf::debug_no_skip();
   {  // dh (U, Kdim) += E W3 : X = h tiles, Y = W3 tiles
     const int64_t xt = gngf::ceil_div(U, BM), yt = gngf::ceil_div(T, SBN);
     const int ns = split_count(xt, yt);
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(map_h, map_w, static_cast<int>(U),
                                                                    static_cast<int>(T), static_cast<int>(Kdim), ns, bias,
-                                                                   m2neg, ascale, consts, utopi, topk, dh, nullptr);
+                                                                   m2neg, ascale, consts, utopi, topk, no_skip, dh, nullptr);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
@@ -872,7 +876,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(map_w, map_h, static_cast<int>(T),
                                                                   static_cast<int>(U), static_cast<int>(Kdim), ns, bias,
-                                                                  coff, sgn, consts, utopi, topk, dw, db);
+                                                                  coff, sgn, consts, utopi, topk, no_skip, dw, db);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }

@@ -559,6 +559,69 @@ def test_streaming_hpd_at_the_size_of_configs2(regime):
         assert worst[k] < bar and alone[k] < bar, (k, worst[k], alone[k], bar)
 
 
+def test_zero_skipping_changes_nothing(monkeypatch):
+    """The streaming kernels skip what a one-hot softmax makes exactly zero (dead 32-column chunks, all-zero E tiles:
+    k2_hpd_tc_bwd.cu, k2_hpd_tc.cu).  With GNGF_DEBUG_NO_SKIP=1 they take the full path on every chunk and tile.  On a
+    random-init HPD fed integer coordinates up to 8 191 (BASELINE.json configs[3]: logits O(1e4), > 95 % of the tiles
+    dead) the two must agree: selections and row maxima bit for bit, row sums / probabilities to 1e-6 (a skipped chunk
+    also skips a no-op step of the compensated sum), and -- fed the same forward outputs -- dh BIT FOR BIT (one CTA owns
+    a row tile and walks its column tiles in order) and dW3 / db3 to the reordering noise of their atomics (1e-6 of the
+    largest entry); the fast run must indeed have skipped most second products (gngf_hpd_stream_bwd_stats)."""
+    from collision_handling_in_instantngp_b200.models import GeneralNeuralGaugeFields
+    torch.manual_seed(65535)
+    T, K, Kd = 2 ** 14, 4, 128
+    net = GeneralNeuralGaugeFields(input_dim=2, hash_table_size=T, num_levels=16, n_min=16, n_max=8192,
+                                   MLP_hidden_layers_widths=[64, 64], HPD_hidden_layers_widths=[32, 64, 128],
+                                   HPD_out_features=T, topk_k=K, should_keep_topk_only=True)
+    ws, bs = net.HPD.weights()
+    U = 40000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    with torch.no_grad():
+        # lattice coordinates: runs of neighbouring nodes at scattered places of the 8193 x 8193 lattice, plus the origin
+        base = torch.randint(0, 8192, (U // 100, 2), generator=g, device=DEV)
+        xy = (base[:, None, :] + torch.stack([torch.arange(100, device=DEV), torch.zeros(100, dtype=torch.long, device=DEV)], -1)[None])
+        xy = xy.reshape(-1, 2).clamp_(0, 8192).float()
+        xy[:200] = torch.stack([torch.arange(200, device=DEV).float() % 20, torch.arange(200, device=DEV).float() // 20], -1)
+        h = torch.relu(xy @ ws[0].t() + bs[0])
+        for i in (1, 2):
+            h = ops.linear_fwd(h, ws[i], bs[i], ops.ACT_RELU)
+        w, b = ws[3].detach().contiguous(), bs[3].detach().contiguous()
+    dtv = torch.randn((U, K), generator=g, device=DEV)
+
+    hp, wp = ops.split_f16x2(h), ops.split_f16x2(w)
+
+    def forward():
+        out = ops.hpd_stream_fwd(h, w, b, K, h_planes=hp, w_planes=wp)
+        torch.cuda.synchronize()
+        return out
+
+    def backward(utopv, utopi, rmax, rsum):
+        dw = torch.zeros((T, Kd), device=DEV)
+        db = torch.zeros(T, device=DEV)
+        dh = ops.hpd_stream_bwd(_flat_lattice(U), h, w, b, hp, wp, utopv, utopi, dtv, None, None, rmax, rsum, dw, db)
+        torch.cuda.synchronize()
+        return dh, dw, db
+
+    ops.stream_bwd_stats(reset=True)
+    fwd_fast = forward()
+    bwd_fast = backward(*fwd_fast)
+    st = ops.stream_bwd_stats(reset=True)
+    monkeypatch.setenv("GNGF_DEBUG_NO_SKIP", "1")
+    fwd_full = forward()
+    bwd_full = backward(*fwd_fast)          # the SAME forward outputs: the backward passes are compared on their own
+    st_full = ops.stream_bwd_stats(reset=True)
+    monkeypatch.delenv("GNGF_DEBUG_NO_SKIP")
+    print(f"\nsecond products issued: dh pass {st[1]} of {st[0]} tiles, dW3 pass {st[3]} of {st[2]}; without skipping {st_full[1]} / {st_full[3]}")
+    assert st_full[1] == st_full[0] and st_full[3] == st_full[2]
+    assert st[1] < 0.2 * st[0] and st[3] < 0.2 * st[2]
+    assert torch.equal(fwd_fast[1], fwd_full[1]) and torch.equal(fwd_fast[2], fwd_full[2])      # selections, row maxima
+    assert float(((fwd_fast[3] - fwd_full[3]).abs() / fwd_full[3]).max()) < 1e-6                 # row sums
+    assert float((fwd_fast[0] - fwd_full[0]).abs().max()) < 1e-6                                 # probabilities (<= 1)
+    assert torch.equal(bwd_fast[0], bwd_full[0]), ("dh", float((bwd_fast[0] - bwd_full[0]).abs().max()))
+    for name, a, c in zip(("dw", "db"), bwd_fast[1:], bwd_full[1:]):
+        assert float((a - c).abs().max()) <= 1e-6 * float(c.abs().max()), name
+
+
 def _flat_lattice(U):
     """A one-level lattice whose node box is U x 1 (the kernel-level tests need node ids only)."""
     from collision_handling_in_instantngp_b200._lib import Lattice
