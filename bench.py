@@ -324,10 +324,11 @@ def algorithmic_cost(name, key, w, lat):
     if name == "gngf_tc_gemm_bf16x3":
         return "tensor", 6 * 2.0 * float(key[0]) * key[1] * key[2]
     if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
-        # two fused passes (dh, dW3), each: logits recomputed (3 split products, every tile) + second product (3 split
-        # products, only on the tiles whose E is not all zero: fraction f counted on the device during the profiled
-        # steps, gngf_hpd_stream_bwd_stats); useful work = the two gradient products, 2 * 2*U*T*kd
-        return "tensor", (6 + 6 * w.get("_stream_live_frac", 1.0)) * 2.0 * Ua * T * kd
+        # two fused passes (dh, dW3), each: one screening product of the logits on every tile, the other two on the
+        # tiles it cannot rule out, the second product (3 split products) on the tiles whose E is not all zero --
+        # products per tile counted on the device during the profiled steps (gngf_hpd_stream_bwd_stats; 6 if nothing
+        # is skipped); useful work = the two gradient products, 2 * 2*U*T*kd
+        return "tensor", 2 * w.get("_stream_products_per_tile", 6.0) * 2.0 * Ua * T * kd
     table = {
         # per point: x (8) + per level 4 node-feature gathers (4*F*4) + enc row (F*4) + 4 multiplicity atomics (4*4)
         "gngf_encode_fwd": P * (8 + L * (4 * F * 4 + F * 4 + 16)),
@@ -368,7 +369,7 @@ def useful_tflops(name, achieved, w):
     if name == "gngf_hpd_stream_fwd_refined":
         return achieved / 3
     if name in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes"):
-        return achieved * 2 / (6 + 6 * w.get("_stream_live_frac", 1.0))   # executed passes for the 2 gradient products
+        return achieved / w.get("_stream_products_per_tile", 6.0)   # executed products per pass for 1 gradient product
     if name in ("gngf_mlp3_tc_fwd", "gngf_mlp3_tc_bwd"):
         dims = [w["L"] * w["F"], *w["mlp"], 3]
         useful = 2.0 * sum(a * b for a, b in zip(dims[:-1], dims[1:])) * (1 if name == "gngf_mlp3_tc_fwd" else 2)
@@ -634,12 +635,18 @@ def run_ours(args):
     clocks = sampler.stop()
     wp = dict(w, P=R.local_points, _active_nodes=m["hpd_rows_this_rank"])
     st = m.get("stream_bwd_stats")
-    if st and (st[0] + st[2]) > 0:
-        wp["_stream_live_frac"] = (st[1] + st[3]) / float(st[0] + st[2])
+    if st and (st[0] + st[3]) > 0:
+        # products per tile, averaged over both passes: 1 (screening) + 2 (rest of the logits) + 3 (second product)
+        wp["_stream_products_per_tile"] = (st[0] + st[3] + 2.0 * (st[1] + st[4]) + 3.0 * (st[2] + st[5])) / (st[0] + st[3])
     roofline = roofline_of(m, wp, prof_steps, name)
-    if st and (st[0] + st[2]) > 0:
-        roofline["stream_bwd_tiles"] = {"dh_pass": st[0], "dh_second_product_issued": st[1], "dw3_pass": st[2],
-                                        "dw3_second_product_issued": st[3], "profiled_steps": prof_steps}
+    if st and (st[0] + st[3]) > 0:
+        if roofline["kernel"] in ("gngf_hpd_stream_bwd", "gngf_hpd_stream_bwd_nodes") and roofline["unit"] == "TFLOP/s":
+            # what a pass that skips nothing (6 split products per tile and pass) would have to sustain to take the same time
+            roofline["dense_equivalent_tflops"] = roofline["achieved"] * 6.0 / wp["_stream_products_per_tile"]
+        roofline["stream_bwd_tiles"] = {"dh_pass": st[0], "dh_all_logit_products": st[1], "dh_second_product_issued": st[2],
+                                        "dw3_pass": st[3], "dw3_all_logit_products": st[4],
+                                        "dw3_second_product_issued": st[5], "profiled_steps": prof_steps,
+                                        "products_per_tile": wp["_stream_products_per_tile"]}
     dev_ms, e2e_ms, e2e_eager_ms = m["dev_ms"], m["e2e_ms"], m.get("e2e_eager_ms", m["e2e_ms"])
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms, e2e_eager_ms], device=dev, dtype=torch.float64)

@@ -66,7 +66,8 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SE_COL = 0;                            // two S / E buffers of 128 columns
 constexpr uint32_t O_COL = 256;                           // O accumulator, 128 columns
 constexpr uint32_t X_COL = 384;                           // resident X tile: plane p at [X_COL + 64 p, +64) (bf16 pairs)
-constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 128 * 16 /*selected-slot masks*/ +
+constexpr uint32_t CTRL_BYTES = 512;                      // barriers, flags, per-chunk maxima
+constexpr size_t SMEM_BYTES = RING * TILE_BYTES + 1024 /*align*/ + CTRL_BYTES + 2 * 128 * 16 /*selected-slot masks*/ +
                               2 * 256 * 4 /*per-column offset / scale of two Y tiles*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -84,6 +85,8 @@ constexpr int C_OUT_DH = 1;    // 2^-12 / scale_w
 constexpr int C_OUT_DW = 2;    // 2^-sa / scale_h
 constexpr int C_SA = 3;        // sa (as a float): exponent offset of the DW = true pass
 constexpr int C_MAXLA = 4;     // scratch: max over rows of log2|a_r| as ordered-int bits
+constexpr int C_MAXW = 5;      // largest row norm of W3 (bits of a non-negative float: integer atomicMax)
+constexpr float SCREEN_ERR = 1.0f / 512.0f;   // |S - S_hihi| <= 2^-10 (1 + 2^-11) |x||y| for fp16-rounded planes; x2 margin
 constexpr float E_SHIFT = 12.0f;
 constexpr int SB_MAX_K = 8;    // selected slots per node on the streaming path (the forward's KTOP)
 constexpr float DEAD_CHUNK_LOG2 = -130.0f;   // exp2 arguments below this give exactly 0 (ex2.approx.ftz flushes under 2^-126)
@@ -96,20 +99,23 @@ constexpr float DEAD_CHUNK_LOG2 = -130.0f;   // exp2 arguments below this give e
 //   -> O += E Y (A = E from tensor memory, B = the same Y tile read MN-major).
 // Neither product reads its A operand from shared memory, so the only shared-memory operand traffic is the Y tile
 // (4 KB per 128x128x16 MMA = 64 B/clk), and the ring holds 128-row tiles (X travels through it once per item).
-// [0] tiles, [1] tiles whose second product was issued -- DW = false; [2], [3] the same for DW = true.  Accumulated over
-// launches until gngf_hpd_stream_bwd_stats() reads and clears them: what bench.py needs to state the EXECUTED tensor work
-// of a pass whose second product is data dependent.
-__device__ unsigned long long g_stream_stats[4];
+// [0] tiles, [1] tiles that needed the two remaining logit products after the screening product, [2] tiles whose second
+// product O += E Y was issued -- DW = false; [3..5] the same for DW = true.  Accumulated over launches until
+// gngf_hpd_stream_bwd_stats() reads and clears them: what bench.py needs to state the EXECUTED tensor work of passes
+// whose products are data dependent.
+__device__ unsigned long long g_stream_stats[6];
 
 template <bool DW>
 __global__ void __launch_bounds__(THREADS, 1)
     hpd_stream_bwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                           int x_rows, int y_rows, int Kdim, int n_split, const float* __restrict__ bias,
                           const float* __restrict__ m2neg, const float* __restrict__ ascale,
-                          const float* __restrict__ consts, const int* __restrict__ utopi, int topk, int no_skip,
+                          const float* __restrict__ errv, const float* __restrict__ consts,
+                          const int* __restrict__ utopi, int topk, int no_skip,
                           float* __restrict__ out, float* __restrict__ dbias) {
   // no_skip (GNGF_DEBUG_NO_SKIP=1, tests only): every chunk takes the full path and every tile issues its second product
   // -- the reference point for "skipping changes nothing"
+  // errv (nodes): bound on |S - S_hihi| of a node against ANY slot, in accumulator units (hpd_stream_bwd_errv_kernel)
   // utopi (nodes, topk): the selected slots, masked out of E (DW = false: nodes are the X rows; DW = true: the Y rows)
   // m2neg / ascale: DW = false: per ROW  -max_r log2e          / a_r (applied at the flush);
   //                 DW = true : per COLUMN -max_r log2e + log2|a_r| / sgn(a_r)
@@ -125,13 +131,18 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* o_full = e_empty + 2;
   uint64_t* o_empty = o_full + 1;
   uint64_t* xt_full = o_empty + 1;         // X tile copied into tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
+  uint64_t* v_full = xt_full + 1;          // [2] the epilogue warps have voted on the screening product
+  uint64_t* s2_full = v_full + 2;          // [2] the two remaining logit products have been added (live tiles only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s2_full + 2);
+  volatile uint32_t* o_valid_s = tmem_slot + 1;   // the item's O accumulator holds something (else: nothing to flush)
   // live_s[buf] = 1 + (running number of the last tile whose E in S / E buffer `buf` has a non-zero entry): written by
   // the epilogue warps before they arrive on e_full, read by the MMA issuer after it (never cleared: a stale stamp
   // cannot equal the current tile's)
   volatile uint32_t* live_s = reinterpret_cast<volatile uint32_t*>(bars) + 48;   // byte 192 of the 256-byte barrier block
+  volatile uint32_t* live1_s = live_s + 2;   // the same stamp for "the screening product could not rule this tile out"
   float* cmax_s = reinterpret_cast<float*>(bars) + 52;   // [2 buffers][4 chunks of 32 columns]: largest column offset
-  unsigned* kill_s = reinterpret_cast<unsigned*>(ring + RING * TILE_BYTES + 256);   // [2 buffers][128 slots][4 words]
+  float* emax_s = reinterpret_cast<float*>(bars) + 64;   // [2 buffers][4 chunks]: largest errv of the chunk's columns (DW)
+  unsigned* kill_s = reinterpret_cast<unsigned*>(ring + RING * TILE_BYTES + CTRL_BYTES);   // [2 buffers][128 slots][4 words]
   float* col_s = reinterpret_cast<float*>(kill_s + 2 * 128 * 4);                    // [2 buffers][offset 128 | scale 128]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -150,8 +161,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     mbar_init(o_full, 1);
     mbar_init(o_empty, EPI_WARPS);
     mbar_init(xt_full, EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(v_full + s, EPI_WARPS);
+      mbar_init(s2_full + s, 1);
+    }
     live_s[0] = 0u;
     live_s[1] = 0u;
+    live1_s[0] = 0u;
+    live1_s[1] = 0u;
+    *o_valid_s = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -214,9 +232,25 @@ __global__ void __launch_bounds__(THREADS, 1)
       uint32_t os = 0;                         // ring slot of the next O product's Y tile
       uint32_t sbuf = 0, sph = 0;              // S / E buffer and phase of the next S product
       uint32_t obuf = 0, oph = 0;              // ... of the next O product
-      uint32_t it2 = 0;                        // running tile counter of the O side (the epilogue's liveness stamp)
-      uint32_t n_live = 0;                     // tiles whose second product was issued
+      uint32_t it2 = 0;                        // running tile counter of the O side (the epilogue's liveness stamps)
+      uint32_t p2a = 0, p2b = 0;               // phases of s2_full / e_full of buffer 0 / 1 (used by live tiles only)
+      uint32_t n_s2 = 0, n_live = 0;           // tiles that needed all three logit products / issued their second product
       uint32_t x_phase = 0, o_phase = 0;
+      // one logit product (planes pa x pb of X and Y) into S / E buffer d: 8 MMAs at Kdim = 128
+      auto logit_product = [&](uint32_t d, uint32_t yb, int pa, int pb, bool first) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          if (kb < kblocks) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // A: resident X tile in tensor memory, 8 columns per K = 16 step, 32 per k-block, 64 per plane
+              const uint32_t at = tmem_u + X_COL + pa * 64 + kb * 32 + k * 8;
+              const uint64_t bd = umma_desc_pack(yb + (((kb * NP + pb) * TP_BYTES + k * UMMA_K * 2) >> 4));
+              umma_bf16_ts_lead(d, at, bd, idesc1, !first || (kb | k) != 0);
+            }
+          }
+        }
+      };
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int sp = item_split(w);
         const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
@@ -232,31 +266,19 @@ __global__ void __launch_bounds__(THREADS, 1)
           rph ^= 1;
         }
         os = rs;                               // ring slot of this item's first Y tile
+        bool o_init = false;                   // the item's O accumulator has been written
         for (int j = 0; j <= nt; ++j) {
-          if (j < nt) {  // S(j) = X Y_j^T : products hi.hi, hi.mid, mid.hi
+          if (j < nt) {
+            // SCREENING product S1(j) = X_hi Y_hi^T -- one of the three split products.  It differs from the full S by at
+            // most errv (hpd_stream_bwd_errv_kernel), and at a one-hot softmax that is enough to rule out almost every
+            // tile: S1 + errv so far below the row maximum that exp2 underflows.  The other two products are issued
+            // only for the tiles the epilogue could not rule out.
             const uint32_t buf = sbuf, ph = sph;
             const uint32_t slot = rs;
             mbar_wait(r_full + slot, rph);
-            mbar_wait(e_empty + buf, ph ^ 1);    // the second product of the tile before last has finished with this buffer
+            mbar_wait(e_empty + buf, ph ^ 1);    // the tile before last has finished with this buffer
             tc_fence_after();
-            const uint32_t yb = y_lo + slot * (TILE_BYTES >> 4);
-            const uint32_t d = tmem_u + SE_COL + buf * SBN;
-#pragma unroll
-            for (int pr = 0; pr < 3; ++pr) {
-              const int pa = pr >> 1, pb = pr & 1;   // (0,0) (0,1) (1,0)
-#pragma unroll
-              for (int kb = 0; kb < 2; ++kb) {
-                if (kb < kblocks) {
-#pragma unroll
-                  for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // A: resident X tile in tensor memory, 8 columns per K = 16 step, 32 per k-block, 64 per plane
-                    const uint32_t at = tmem_u + X_COL + pa * 64 + kb * 32 + k * 8;
-                    const uint64_t bd = umma_desc_pack(yb + (((kb * NP + pb) * TP_BYTES + k * UMMA_K * 2) >> 4));
-                    umma_bf16_ts_lead(d, at, bd, idesc1, (pr | kb | k) != 0);
-                  }
-                }
-              }
-            }
+            logit_product(tmem_u + SE_COL + buf * SBN, y_lo + slot * (TILE_BYTES >> 4), 0, 0, true);
             umma_commit_lead(s_full + buf);
             if (++rs == RING) {
               rs = 0;
@@ -265,59 +287,83 @@ __global__ void __launch_bounds__(THREADS, 1)
             sph ^= sbuf;                         // (the phase flips when the buffer index wraps 1 -> 0)
             sbuf ^= 1;
           }
-          if (j >= 1) {  // O += E(j-1) Y_{j-1}
+          if (j >= 1) {  // resolve tile j - 1
             const uint32_t buf = obuf, ph = oph;
             const uint32_t slot = os;
-            mbar_wait(e_full + buf, ph);
+            mbar_wait(v_full + buf, ph);         // the eight epilogue warps have looked at S1
             if (j == 1) {
               mbar_wait(o_empty, o_phase ^ 1);   // the previous item's O has been read out
               o_phase ^= 1;
             }
-            tc_fence_after();
-            const uint32_t eb = tmem_u + SE_COL + buf * SBN;
-            const uint32_t yb = y_lo_mn + slot * (TILE_BYTES >> 4);
-            const uint32_t d = tmem_u + O_COL;
-            // An E tile without a single non-zero fp16 entry adds nothing to O: its three products are not issued (the
-            // item's first tile always is -- it initialises the accumulator).  With the HPD fed integer lattice
-            // coordinates the softmax is one-hot and most tiles are like that (83 % at BASELINE.json configs[3]).
-            const bool live = (j == 1) || no_skip != 0 ||
-                              __any_sync(0xffffffffu, live_s[buf] == it2 + 1u);   // (a vote: provably warp-uniform)
-            if (live) {
+            // (votes: provably warp-uniform, which keeps every descriptor below in the uniform datapath)
+            const bool live1 = no_skip != 0 || __any_sync(0xffffffffu, live1_s[buf] == it2 + 1u);
+            bool issued_o = false;
+            if (live1) {
+              ++n_s2;
+              tc_fence_after();
+              const uint32_t d1 = tmem_u + SE_COL + buf * SBN;
+              const uint32_t yk = y_lo + slot * (TILE_BYTES >> 4);
+              logit_product(d1, yk, 0, 1, false);   // + X_hi Y_mid^T
+              logit_product(d1, yk, 1, 0, false);   // + X_mid Y_hi^T
+              umma_commit_lead(s2_full + buf);
+              const uint32_t p2 = buf ? p2b : p2a;
+              mbar_wait(e_full + buf, p2);          // E written over S by the epilogue
+              if (buf) p2b ^= 1; else p2a ^= 1;
+              tc_fence_after();
+              // An E tile without a single non-zero fp16 entry adds nothing to O: its three products are not issued.
+              const bool live2 = no_skip != 0 || __any_sync(0xffffffffu, live_s[buf] == it2 + 1u);
+              if (live2) {
+                const uint32_t eb = tmem_u + SE_COL + buf * SBN;
+                const uint32_t yb = y_lo_mn + slot * (TILE_BYTES >> 4);
+                const uint32_t d = tmem_u + O_COL;
 #pragma unroll
-              for (int pr = 0; pr < 3; ++pr) {
-                const int pa = pr >> 1, pb = pr & 1;
+                for (int pr = 0; pr < 3; ++pr) {
+                  const int pa = pr >> 1, pb = pr & 1;
 #pragma unroll
-                for (int k = 0; k < SBN / UMMA_K; ++k) {
-                  // A: E plane pa in tensor memory: S columns 16k.. live at packed columns 64 (k / 4) + 32 pa + 8 (k % 4)
-                  const uint32_t at = eb + 64 * (k >> 2) + 32 * pa + 8 * (k & 3);
-                  // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*TP_BYTES apart),
-                  //    K = streamed index (rows of 128 bytes, 16 rows = 2048 bytes per step)
-                  const uint64_t bd = umma_desc_pack(yb + ((pb * TP_BYTES + k * UMMA_K * 128) >> 4));
-                  umma_bf16_ts_lead(d, at, bd, idesc2, (j != 1) || (pr | k) != 0);
+                  for (int k = 0; k < SBN / UMMA_K; ++k) {
+                    // A: E plane pa in tensor memory: S columns 16k.. live at packed columns 64 (k / 4) + 32 pa + 8 (k % 4)
+                    const uint32_t at = eb + 64 * (k >> 2) + 32 * pa + 8 * (k & 3);
+                    // B: Y plane read MN-major: N = feature index (64 contiguous per k-block, k-blocks NP*TP_BYTES apart),
+                    //    K = streamed index (rows of 128 bytes, 16 rows = 2048 bytes per step)
+                    const uint64_t bd = umma_desc_pack(yb + ((pb * TP_BYTES + k * UMMA_K * 128) >> 4));
+                    umma_bf16_ts_lead(d, at, bd, idesc2, o_init || (pr | k) != 0);
+                  }
                 }
+                o_init = true;
+                issued_o = true;
+                ++n_live;
               }
             }
-            if (live) {
-              ++n_live;
+            if (live1) {
+              // (commits: behind the products that read this S / E buffer and this Y tile)
               umma_commit_lead(e_empty + buf);
               umma_commit_lead(r_empty + slot);
             } else if (elect_one()) {
-              // nothing reads E(j-1) or Y_{j-1} any more (S(j-1) completed before the epilogue could write E): both are
-              // released at once instead of behind the S(j) products a commit would wait for
+              // nothing reads S1(j-1) or Y_{j-1} any more (the epilogue has read S1; its product completed before that):
+              // both are released at once instead of behind the S1(j) product a commit would wait for
               mbar_arrive(e_empty + buf);
               mbar_arrive(r_empty + slot);
             }
+            (void)issued_o;
             ++it2;
             if (++os == RING) os = 0;
             oph ^= obuf;
             obuf ^= 1;
           }
         }
-        umma_commit_lead(o_full);
+        // o_full: behind the item's last O product if there was one; else there is nothing to flush and the epilogue is
+        // told so (the flag is written, fenced, and only then the barrier is signalled)
+        if (elect_one()) {
+          *o_valid_s = o_init ? 1u : 0u;
+          __threadfence_block();
+          if (o_init) umma_commit(o_full);
+          else mbar_arrive(o_full);
+        }
       }
       if (elect_one()) {
-        atomicAdd(g_stream_stats + (DW ? 2 : 0), static_cast<unsigned long long>(it2));
-        atomicAdd(g_stream_stats + (DW ? 3 : 1), static_cast<unsigned long long>(n_live));
+        atomicAdd(g_stream_stats + (DW ? 3 : 0), static_cast<unsigned long long>(it2));
+        atomicAdd(g_stream_stats + (DW ? 4 : 1), static_cast<unsigned long long>(n_s2));
+        atomicAdd(g_stream_stats + (DW ? 5 : 2), static_cast<unsigned long long>(n_live));
       }
     }
   } else {  // ---- epilogue warps 2..9 ----
@@ -326,6 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int row_l = q * 32 + lane;        // row of the X tile / of E / of O
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t it = 0, o_phase = 0, nent = 0;
+    uint32_t p2a = 0, p2b = 0;   // phases of s2_full of buffer 0 / 1 (live tiles only; the issuer keeps the same count)
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int m0 = item_x(w) * BM, sp = item_split(w);
       const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
@@ -343,6 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         r_scale = row_ok ? 1.0f : 0.0f;
       }
       const float flush_scale = DW ? out_scale : (row_ok ? out_scale * __ldg(ascale + row) : 0.0f);
+      const float err_row = (!DW && row_ok) ? __ldg(errv + row) : 0.0f;   // DW: per column, staged as chunk maxima
       int tk[SB_MAX_K];   // DW = false: this row's selected slots
 #pragma unroll
       for (int k = 0; k < SB_MAX_K; ++k)
@@ -389,12 +437,16 @@ __global__ void __launch_bounds__(THREADS, 1)
       // every epilogue thread fetches ONE value one tile ahead and parks it in shared memory before the tile's barrier,
       // so the inner loop reads its 64 columns with broadcast LDS instead of waiting on 16 global loads per 32 columns
       // (22 % of this kernel's stall samples in the first version).  Columns past the last row get offset -inf: E = 0.
-      float pf_col = 0.0f;
+      float pf_col = 0.0f, pf_err = 0.0f;
       auto load_col = [&](int tile) {
         const int c = tile * SBN + (etid & 127);
         const bool second = etid >= 128;
         pf_col = second ? 0.0f : -INFINITY;
-        if (c < y_rows) pf_col = second ? (DW ? __ldg(ascale + c) : 1.0f) : (DW ? __ldg(m2neg + c) : __ldg(bias + c));
+        pf_err = 0.0f;
+        if (c < y_rows) {
+          pf_col = second ? (DW ? __ldg(ascale + c) : 1.0f) : (DW ? __ldg(m2neg + c) : __ldg(bias + c));
+          if (DW && !second) pf_err = __ldg(errv + c);
+        }
       };
       load_col(t0);
       if (DW) load_sel(t0);
@@ -413,10 +465,16 @@ __global__ void __launch_bounds__(THREADS, 1)
           const float cval = (!DW && etid < 128) ? pf_col * LOG2E : pf_col;
           cbuf[etid] = cval;
           if (etid < 128) {   // warp-uniform: the four warps that hold the offsets; warp w = columns 32w.. = chunk w
-            float m = cval;
+            float m = cval, me = pf_err;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0) cmax_s[(it & 1) * 4 + (etid >> 5)] = m;
+            for (int o = 16; o > 0; o >>= 1) {
+              m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+              if (DW) me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, o));
+            }
+            if (lane == 0) {
+              cmax_s[(it & 1) * 4 + (etid >> 5)] = m;
+              emax_s[(it & 1) * 4 + (etid >> 5)] = me;
+            }
           }
         }
         if (t + 1 < t1) load_col(t + 1);
@@ -456,14 +514,61 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         mbar_wait(s_full + buf, ph);
         tc_fence_after();
-        uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
-        uint32_t nz = 0u;           // OR of every fp16 pair this thread writes
         // both 32-column chunks are requested before the wait: what follows the accumulator is a latency chain (load ->
-        // maximum -> bound -> store -> arrive) that the MMA issuer waits for, not a throughput problem
+        // maximum -> bound -> vote -> arrive) that the MMA issuer waits for, not a throughput problem
         uint32_t va[32], vb[32];
         tmem_ld32_nowait(se, va);
         tmem_ld32_nowait(se + 32, vb);
         tmem_wait_ld();
+        {  // ---- verdict on the SCREENING product (X_hi Y_hi^T): can any of this thread's 64 entries be non-zero?
+           // arg_j <= (max(v1) + err) k1 + (r_off + max(off)) with err >= |S - S1| (k1 > 0; fp32 fma / add are monotone)
+          auto tree_max = [](const uint32_t(&v)[32]) {
+            float m8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              m8[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                            fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            return fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+          };
+          const int ci = (it & 1) * 4 + half * 2;
+          const float e0 = DW ? emax_s[ci] : err_row, e1 = DW ? emax_s[ci + 1] : err_row;
+          // per chunk: the cheap bound (largest accumulator + largest offset), and where that is not enough the bound
+          // element by element (the DW pass's column offsets -- minus the row maximum of 32 different nodes -- vary by
+          // hundreds within a chunk: largest accumulator and largest offset rarely belong to the same column)
+          auto chunk_dead = [&](const uint32_t(&v)[32], float err, int cb) {
+            if (fmaf(tree_max(v) + err, k1, r_off + cmax_s[ci + cb]) < DEAD_CHUNK_LOG2) return true;
+            const float* offp = cbuf + half * 64 + cb * 32;
+            float am[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 off = *reinterpret_cast<const float4*>(offp + j);
+              am[0] = fmaxf(am[0], fmaf(__uint_as_float(v[j + 0]) + err, k1, r_off + off.x));
+              am[1] = fmaxf(am[1], fmaf(__uint_as_float(v[j + 1]) + err, k1, r_off + off.y));
+              am[2] = fmaxf(am[2], fmaf(__uint_as_float(v[j + 2]) + err, k1, r_off + off.z));
+              am[3] = fmaxf(am[3], fmaf(__uint_as_float(v[j + 3]) + err, k1, r_off + off.w));
+            }
+            return fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3])) < DEAD_CHUNK_LOG2;
+          };
+          const bool dead = !row_ok || (chunk_dead(va, e0, 0) && chunk_dead(vb, e1, 1));
+          const bool warp_dead = __all_sync(0xffffffffu, dead);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (!warp_dead) live1_s[buf] = it + 1u;   // every warp that objects stores the same stamp
+            mbar_arrive(v_full + buf);                // (release: the issuer reads the stamp after its wait)
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // ... and so do the other epilogue warps
+          if (!no_skip && live1_s[buf] != it + 1u) continue;   // ruled out: E = 0, nothing is written, nothing is issued
+        }
+        // ---- the tile stays: the issuer adds the two remaining logit products to the same buffer
+        mbar_wait(s2_full + buf, buf ? p2b : p2a);
+        if (buf) p2b ^= 1; else p2a ^= 1;
+        tc_fence_after();
+        tmem_ld32_nowait(se, va);
+        tmem_ld32_nowait(se + 32, vb);
+        tmem_wait_ld();
+        uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
+        uint32_t nz = 0u;           // OR of every fp16 pair this thread writes
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const int c0 = t * SBN + half * 64 + cb * 32;
@@ -576,10 +681,11 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_wait(o_full, o_phase);
       o_phase ^= 1;
       tc_fence_after();
+      const bool o_valid = *o_valid_s != 0u;   // (no tile of the item issued its second product: O was never written)
 #pragma unroll 1
       for (int cc = 0; cc < 64; cc += 32) {
         const int col0 = half * 64 + cc;
-        if (col0 >= n2) continue;   // warp-uniform
+        if (col0 >= n2 || !o_valid) continue;   // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + O_COL + col0, v);
         if (row_ok) {
@@ -798,6 +904,45 @@ __global__ void __launch_bounds__(256)
 // tiles (the dh pass of a large lattice): no split.  Few (the dW3 pass: T / 128 tiles): split so that the number of
 // items is a MULTIPLE of the SM count -- 128 tiles x 2 splits on 148 SMs left 40 SMs with half the work of the others
 // (14 % of that pass) -- with at least 64 Y tiles per item to amortise the X-tile load and the accumulator flush.
+// largest row norm of W3 -> consts[C_MAXW] (bits of a non-negative float order like integers)
+__global__ void __launch_bounds__(256)
+    hpd_stream_bwd_wnorm_kernel(const float* __restrict__ w, int64_t T, int Kdim, float* __restrict__ consts) {
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  float ss = 0.0f;
+  if (row < T)
+    for (int c = lane; c < Kdim; c += 32) {
+      const float v = __ldg(w + row * Kdim + c);
+      ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0 && row < T) atomicMax(reinterpret_cast<int*>(consts) + C_MAXW, __float_as_int(sqrtf(ss) * 1.0001f));
+}
+
+// errv[u] >= |S[u, t] - S_hihi[u, t]| for every slot t, in accumulator units (both operands carry their plane scale):
+// with fp16-rounded planes x = x_hi + x_mid + r, |x - x_hi| <= 2^-11 |x|, so the products the screening pass leaves out
+// are bounded by 2^-10 (1 + 2^-11) sum |x||y| <= 2^-10 (1 + 2^-11) |x||y| (Cauchy-Schwarz); SCREEN_ERR doubles that, which
+// also covers the fp32 accumulation order and the sub-normal tail of the planes.
+__global__ void __launch_bounds__(256)
+    hpd_stream_bwd_errv_kernel(const float* __restrict__ h, int64_t U, int Kdim, const float* __restrict__ h_scale,
+                               const float* __restrict__ w_scale, const float* __restrict__ consts,
+                               float* __restrict__ errv) {
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= U) return;
+  float ss = 0.0f;
+  for (int c = lane; c < Kdim; c += 32) {
+    const float v = __ldg(h + row * Kdim + c);
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0)
+    // (h_scale / w_scale hold the INVERSE plane scales, see hpd_stream_bwd_consts_kernel)
+    errv[row] = SCREEN_ERR * (sqrtf(ss) * 1.0001f) * __ldg(consts + C_MAXW) / (__ldg(h_scale) * __ldg(w_scale)) + 1.0f;
+}
+
 static int split_count(int64_t x_tiles, int64_t y_tiles) {
   const int64_t sms = gngf::sm_count();
   if (x_tiles >= 8 * sms) return 1;
@@ -817,7 +962,7 @@ static int split_count(int64_t x_tiles, int64_t y_tiles) {
 extern "C" {
 
 int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk) {
-  return 4 * ((U + 3) & ~int64_t(3)) + U * static_cast<int64_t>(topk) + 16;
+  return 5 * ((U + 3) & ~int64_t(3)) + U * static_cast<int64_t>(topk) + 16;
 }
 
 int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const uint16_t* h_planes, const float* h_scale,
@@ -841,13 +986,14 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
        reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(w)) & 15)
     return GNGF_ERR_INVALID_ARGUMENT;
   cudaStream_t st = gngf::as_stream(stream);
-  // workspace: ascale | m2neg | coff | sgn (U each, rounded up to 4) | spk (U, topk) | consts (8, 16-byte aligned)
+  // workspace: ascale | m2neg | coff | sgn | errv (U each, rounded up to 4) | spk (U, topk) | consts (8, 16-byte aligned)
   const int64_t U4 = (U + 3) & ~int64_t(3);
   float* ascale = workspace;
   float* m2neg = workspace + U4;
   float* coff = workspace + 2 * U4;
   float* sgn = workspace + 3 * U4;
-  float* spk = workspace + 4 * U4;
+  float* errv = workspace + 4 * U4;
+  float* spk = workspace + 5 * U4;
   float* consts = spk + ((U * topk + 3) & ~int64_t(3));
   if (cudaMemsetAsync(consts, 0x80, 8 * sizeof(float), st) != cudaSuccess) return gngf::check_launch();
   hpd_stream_bwd_prep_kernel<<<static_cast<unsigned>(gngf::ceil_div(U, 256)), 256, 0, st>>>(
@@ -856,6 +1002,14 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
   int rc = gngf::check_launch();
   if (rc) return rc;
   hpd_stream_bwd_consts_kernel<<<1, 1, 0, st>>>(h_scale, w_scale, consts);
+  gngf::note_launch();
+  if ((rc = gngf::check_launch())) return rc;
+  // the screening pass's error bound per node: |W3 row|_max, then SCREEN_ERR |h_u| |W3 row|_max in accumulator units
+  hpd_stream_bwd_wnorm_kernel<<<static_cast<unsigned>(gngf::ceil_div(T * 32, 256)), 256, 0, st>>>(w, T, static_cast<int>(Kdim),
+                                                                                                   consts);
+  gngf::note_launch();
+  hpd_stream_bwd_errv_kernel<<<static_cast<unsigned>(gngf::ceil_div(U * 32, 256)), 256, 0, st>>>(
+      h, U, static_cast<int>(Kdim), h_scale, w_scale, consts, errv);
   gngf::note_launch();
   if ((rc = gngf::check_launch())) return rc;
 
@@ -875,7 +1029,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(map_h, map_w, static_cast<int>(U),
                                                                    static_cast<int>(T), static_cast<int>(Kdim), ns, bias,
-                                                                   m2neg, ascale, consts, utopi, topk, no_skip, dh, nullptr);
+                                                                   m2neg, ascale, errv, consts, utopi, topk, no_skip, dh, nullptr);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
@@ -885,7 +1039,7 @@ int gngf_hpd_stream_bwd_nodes(gngf_lattice lat, const int32_t* node_ids, const u
     const int grid = static_cast<int>(std::min<int64_t>(xt * ns, sms));
     hpd_stream_bwd_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(map_w, map_h, static_cast<int>(T),
                                                                   static_cast<int>(U), static_cast<int>(Kdim), ns, bias,
-                                                                  coff, sgn, consts, utopi, topk, no_skip, dw, db);
+                                                                  coff, sgn, errv, consts, utopi, topk, no_skip, dw, db);
     gngf::note_launch();
     if ((rc = gngf::check_launch())) return rc;
   }
@@ -906,15 +1060,15 @@ int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const float*
                                    gcol_k, row_max, row_sum, act_prev, dh, dw, db, workspace, stream);
 }
 
-int gngf_hpd_stream_bwd_stats(uint64_t* out4, int32_t reset) {
-  if (!out4) return GNGF_ERR_INVALID_ARGUMENT;
-  unsigned long long h[4] = {0, 0, 0, 0};
+int gngf_hpd_stream_bwd_stats(uint64_t* out6, int32_t reset) {
+  if (!out6) return GNGF_ERR_INVALID_ARGUMENT;
+  unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
   if (cudaDeviceSynchronize() != cudaSuccess ||
       cudaMemcpyFromSymbol(h, gngf::tc::sb::g_stream_stats, sizeof(h)) != cudaSuccess)
     return gngf::check_launch();
-  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  for (int i = 0; i < 6; ++i) out6[i] = h[i];
   if (reset) {
-    const unsigned long long z[4] = {0, 0, 0, 0};
+    const unsigned long long z[6] = {0, 0, 0, 0, 0, 0};
     if (cudaMemcpyToSymbol(gngf::tc::sb::g_stream_stats, z, sizeof(z)) != cudaSuccess) return gngf::check_launch();
   }
   return GNGF_OK;

@@ -364,10 +364,11 @@ def gather_rows(x, lat: Lattice, uvals: torch.Tensor, out: Optional[torch.Tensor
 
 
 def stream_bwd_stats(reset=False):
-    """[dh-pass tiles, of which issued their second product, dW3-pass tiles, of which issued] since the last reset
-    (gngf.h: gngf_hpd_stream_bwd_stats); synchronises the device.  bench.py's executed-FLOP accounting."""
+    """[dh-pass tiles, of which needed all three logit products, of which issued the second product, dW3-pass tiles, ...,
+    ...] since the last reset (gngf.h: gngf_hpd_stream_bwd_stats); synchronises the device.  bench.py's executed-FLOP
+    accounting."""
     import ctypes
-    out = (ctypes.c_uint64 * 4)()
+    out = (ctypes.c_uint64 * 6)()
     call("gngf_hpd_stream_bwd_stats", ctypes.cast(out, ctypes.c_void_p), 1 if reset else 0)
     return [int(v) for v in out]
 

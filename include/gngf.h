@@ -189,11 +189,13 @@ int gngf_hpd_stream_fwd_refined(const uint16_t* a_planes, const float* a_scale, 
  *   (used by the K-sparse part); utopv / utopi (U,topk): the forward's outputs; dh must be ZERO-INITIALISED, dw / db
  *   are accumulated into; workspace: gngf_hpd_stream_bwd_workspace_floats(U, topk) floats, 16-byte aligned.      */
 int64_t gngf_hpd_stream_bwd_workspace_floats(int64_t U, int32_t topk);
-/* Measurement aid.  The dense passes skip the second product (E W3 / E^T h) of every 128 x 128 tile whose E has no
- * non-zero fp16 entry -- with a one-hot softmax that is most of them -- so the tensor work they execute depends on the
- * data.  out4 = {dh-pass tiles, of which second product issued, dW3-pass tiles, of which issued}, accumulated over the
- * calls on the current device since the last reset; synchronises the device.                                          */
-int gngf_hpd_stream_bwd_stats(uint64_t* out4, int32_t reset);
+/* Measurement aid.  The dense passes screen every 128 x 128 tile with ONE of the three split products of the logits and
+ * add the other two -- and the second product (E W3 / E^T h) after them -- only where the tile cannot be ruled out (with
+ * a one-hot softmax: almost nowhere), so the tensor work they execute depends on the data.
+ * out6 = {dh-pass tiles, of which needed all three logit products, of which issued the second product,
+ *         dW3-pass tiles, ..., ...}, accumulated over the calls on the current device since the last reset;
+ * synchronises the device.                                                                                            */
+int gngf_hpd_stream_bwd_stats(uint64_t* out6, int32_t reset);
 int gngf_hpd_stream_bwd(gngf_lattice lat, const uint16_t* h_planes, const float* h_scale, const uint16_t* w_planes,
                         const float* w_scale, const float* h, const float* w, const float* bias, int64_t U, int64_t T,
                         int64_t Kdim, int32_t topk, const float* utopv, const int32_t* utopi, const float* dtv, const int32_t* cnt,

@@ -611,9 +611,10 @@ def test_zero_skipping_changes_nothing(monkeypatch):
     bwd_full = backward(*fwd_fast)          # the SAME forward outputs: the backward passes are compared on their own
     st_full = ops.stream_bwd_stats(reset=True)
     monkeypatch.delenv("GNGF_DEBUG_NO_SKIP")
-    print(f"\nsecond products issued: dh pass {st[1]} of {st[0]} tiles, dW3 pass {st[3]} of {st[2]}; without skipping {st_full[1]} / {st_full[3]}")
-    assert st_full[1] == st_full[0] and st_full[3] == st_full[2]
-    assert st[1] < 0.2 * st[0] and st[3] < 0.2 * st[2]
+    print(f"\ntiles / with all three logit products / with the second product: dh pass {st[0]} / {st[1]} / {st[2]}, dW3 pass "
+          f"{st[3]} / {st[4]} / {st[5]}; without skipping {st_full}")
+    assert st_full[1] == st_full[0] and st_full[2] == st_full[0] and st_full[4] == st_full[3] and st_full[5] == st_full[3]
+    assert st[2] <= st[1] < 0.5 * st[0] and st[5] <= st[4] < 0.5 * st[3] and st[2] < 0.2 * st[0] and st[5] < 0.2 * st[3]
     assert torch.equal(fwd_fast[1], fwd_full[1]) and torch.equal(fwd_fast[2], fwd_full[2])      # selections, row maxima
     assert float(((fwd_fast[3] - fwd_full[3]).abs() / fwd_full[3]).max()) < 1e-6                 # row sums
     assert float((fwd_fast[0] - fwd_full[0]).abs().max()) < 1e-6                                 # probabilities (<= 1)
