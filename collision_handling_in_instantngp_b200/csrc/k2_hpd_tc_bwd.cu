@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint64_t* s2_full = v_full + 2;          // [2] the two remaining logit products have been added (live tiles only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s2_full + 2);
   volatile uint32_t* o_valid_s = tmem_slot + 1;   // the item's O accumulator holds something (else: nothing to flush)
+  volatile uint32_t* mode_s = tmem_slot + 2;      // this item screens its tiles with one product (1) or issues all three (0)
   // live_s[buf] = 1 + (running number of the last tile whose E in S / E buffer `buf` has a non-zero entry): written by
   // the epilogue warps before they arrive on e_full, read by the MMA issuer after it (never cleared: a stale stamp
   // cannot equal the current tile's)
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     live1_s[0] = 0u;
     live1_s[1] = 0u;
     *o_valid_s = 0u;
+    *mode_s = 1u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -233,8 +235,18 @@ __global__ void __launch_bounds__(THREADS, 1)
       uint32_t sbuf = 0, sph = 0;              // S / E buffer and phase of the next S product
       uint32_t obuf = 0, oph = 0;              // ... of the next O product
       uint32_t it2 = 0;                        // running tile counter of the O side (the epilogue's liveness stamps)
-      uint32_t p2a = 0, p2b = 0;               // phases of s2_full / e_full of buffer 0 / 1 (used by live tiles only)
+      uint32_t p2a = 0, p2b = 0;               // phases of e_full of buffer 0 / 1 (not every tile gets that far)
+      uint32_t pva = 0, pvb = 0;               // phases of v_full of buffer 0 / 1 (screening items only)
       uint32_t n_s2 = 0, n_live = 0;           // tiles that needed all three logit products / issued their second product
+      // Screening pays where it rules tiles out (a one-hot softmax: BASELINE.json configs[3]) and costs a round trip
+      // through the epilogue per tile where it does not (logits within +-73 at configs[2]: nothing is 130 binades down).
+      // Each item decides from the items before: screening goes on while it rules out more than half of an item's tiles;
+      // after TWO failures in a row (one alone means little: at configs[3] a CTA's consecutive items are row tiles 148
+      // apart, and only those near the lattice origin have small logits) `backoff` plain items follow (8, doubling up
+      // to 64 with every failed probe) before screening is tried again.
+      bool screen = no_skip == 0;
+      uint32_t c_tiles = 0, c_s2 = 0, c_live = 0;   // the previous item's tiles / not ruled out / second product issued
+      uint32_t backoff = 8, plain_left = 0, fails = 0;
       uint32_t x_phase = 0, o_phase = 0;
       // one logit product (planes pa x pb of X and Y) into S / E buffer d: 8 MMAs at Kdim = 128
       auto logit_product = [&](uint32_t d, uint32_t yb, int pa, int pb, bool first) {
@@ -267,6 +279,25 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         os = rs;                               // ring slot of this item's first Y tile
         bool o_init = false;                   // the item's O accumulator has been written
+        if (c_tiles > 0 && no_skip == 0) {
+          if (screen) {
+            if (2 * c_s2 < c_tiles) {
+              backoff = 8;
+              fails = 0;
+            } else if (++fails >= 2) {
+              screen = false;
+              plain_left = backoff;
+              backoff = min(64u, backoff * 2);
+            }
+          } else if (--plain_left == 0) {
+            screen = true;   // (fails stays >= 2: one more failure sends the next items back to plain at once)
+          }
+        }
+        c_tiles = c_s2 = c_live = 0;
+        if (elect_one()) {                     // (read by the epilogue warps after the item's first s_full)
+          *mode_s = screen ? 1u : 0u;
+          __threadfence_block();
+        }
         for (int j = 0; j <= nt; ++j) {
           if (j < nt) {
             // SCREENING product S1(j) = X_hi Y_hi^T -- one of the three split products.  It differs from the full S by at
@@ -279,6 +310,10 @@ __global__ void __launch_bounds__(THREADS, 1)
             mbar_wait(e_empty + buf, ph ^ 1);    // the tile before last has finished with this buffer
             tc_fence_after();
             logit_product(tmem_u + SE_COL + buf * SBN, y_lo + slot * (TILE_BYTES >> 4), 0, 0, true);
+            if (!screen) {                       // a plain item: all three products at once
+              logit_product(tmem_u + SE_COL + buf * SBN, y_lo + slot * (TILE_BYTES >> 4), 0, 1, false);
+              logit_product(tmem_u + SE_COL + buf * SBN, y_lo + slot * (TILE_BYTES >> 4), 1, 0, false);
+            }
             umma_commit_lead(s_full + buf);
             if (++rs == RING) {
               rs = 0;
@@ -290,22 +325,31 @@ __global__ void __launch_bounds__(THREADS, 1)
           if (j >= 1) {  // resolve tile j - 1
             const uint32_t buf = obuf, ph = oph;
             const uint32_t slot = os;
-            mbar_wait(v_full + buf, ph);         // the eight epilogue warps have looked at S1
+            (void)ph;
+            bool live1 = true;                   // a plain item: every tile has all three products already
+            if (screen) {
+              mbar_wait(v_full + buf, buf ? pvb : pva);   // the eight epilogue warps have looked at S1
+              if (buf) pvb ^= 1; else pva ^= 1;
+              // (votes: provably warp-uniform, which keeps every descriptor below in the uniform datapath)
+              live1 = __any_sync(0xffffffffu, live1_s[buf] == it2 + 1u);
+            }
             if (j == 1) {
               mbar_wait(o_empty, o_phase ^ 1);   // the previous item's O has been read out
               o_phase ^= 1;
             }
-            // (votes: provably warp-uniform, which keeps every descriptor below in the uniform datapath)
-            const bool live1 = no_skip != 0 || __any_sync(0xffffffffu, live1_s[buf] == it2 + 1u);
             bool issued_o = false;
+            ++c_tiles;
             if (live1) {
               ++n_s2;
-              tc_fence_after();
-              const uint32_t d1 = tmem_u + SE_COL + buf * SBN;
-              const uint32_t yk = y_lo + slot * (TILE_BYTES >> 4);
-              logit_product(d1, yk, 0, 1, false);   // + X_hi Y_mid^T
-              logit_product(d1, yk, 1, 0, false);   // + X_mid Y_hi^T
-              umma_commit_lead(s2_full + buf);
+              ++c_s2;
+              if (screen) {
+                tc_fence_after();
+                const uint32_t d1 = tmem_u + SE_COL + buf * SBN;
+                const uint32_t yk = y_lo + slot * (TILE_BYTES >> 4);
+                logit_product(d1, yk, 0, 1, false);   // + X_hi Y_mid^T
+                logit_product(d1, yk, 1, 0, false);   // + X_mid Y_hi^T
+                umma_commit_lead(s2_full + buf);
+              }
               const uint32_t p2 = buf ? p2b : p2a;
               mbar_wait(e_full + buf, p2);          // E written over S by the epilogue
               if (buf) p2b ^= 1; else p2a ^= 1;
@@ -332,6 +376,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 o_init = true;
                 issued_o = true;
                 ++n_live;
+                ++c_live;
               }
             }
             if (live1) {
@@ -372,7 +417,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int row_l = q * 32 + lane;        // row of the X tile / of E / of O
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t it = 0, o_phase = 0, nent = 0;
-    uint32_t p2a = 0, p2b = 0;   // phases of s2_full of buffer 0 / 1 (live tiles only; the issuer keeps the same count)
+    uint32_t p2a = 0, p2b = 0;   // phases of s2_full of buffer 0 / 1 (tiles of screening items that were not ruled out)
+    bool screen = true;          // this item's mode (mode_s, read after the item's first s_full)
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int m0 = item_x(w) * BM, sp = item_split(w);
       const int t0 = sp * tiles_per_split, t1 = min(y_tiles, t0 + tiles_per_split);
@@ -520,7 +566,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         tmem_ld32_nowait(se, va);
         tmem_ld32_nowait(se + 32, vb);
         tmem_wait_ld();
-        {  // ---- verdict on the SCREENING product (X_hi Y_hi^T): can any of this thread's 64 entries be non-zero?
+        if (t == t0) screen = *mode_s != 0u;
+        if (screen) {  // ---- verdict on the SCREENING product (X_hi Y_hi^T): can any of this thread's 64 entries be non-zero?
            // arg_j <= (max(v1) + err) k1 + (r_off + max(off)) with err >= |S - S1| (k1 > 0; fp32 fma / add are monotone)
           auto tree_max = [](const uint32_t(&v)[32]) {
             float m8[8];
@@ -558,15 +605,15 @@ __global__ void __launch_bounds__(THREADS, 1)
             mbar_arrive(v_full + buf);                // (release: the issuer reads the stamp after its wait)
           }
           asm volatile("bar.sync 2, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // ... and so do the other epilogue warps
-          if (!no_skip && live1_s[buf] != it + 1u) continue;   // ruled out: E = 0, nothing is written, nothing is issued
+          if (live1_s[buf] != it + 1u) continue;   // ruled out: E = 0, nothing is written, nothing is issued
+          // ---- the tile stays: the issuer adds the two remaining logit products to the same buffer
+          mbar_wait(s2_full + buf, buf ? p2b : p2a);
+          if (buf) p2b ^= 1; else p2a ^= 1;
+          tc_fence_after();
+          tmem_ld32_nowait(se, va);
+          tmem_ld32_nowait(se + 32, vb);
+          tmem_wait_ld();
         }
-        // ---- the tile stays: the issuer adds the two remaining logit products to the same buffer
-        mbar_wait(s2_full + buf, buf ? p2b : p2a);
-        if (buf) p2b ^= 1; else p2a ^= 1;
-        tc_fence_after();
-        tmem_ld32_nowait(se, va);
-        tmem_ld32_nowait(se + 32, vb);
-        tmem_wait_ld();
         uint32_t hi[32], mid[32];   // this thread's 64 columns of E as fp16 pairs: hi plane, mid plane
         uint32_t nz = 0u;           // OR of every fp16 pair this thread writes
 #pragma unroll
