@@ -43,8 +43,13 @@
 //     zero planes when that is under -130; the exact per-element maximum decides the chunks the bound leaves open;
 //   * a tile whose E has no non-zero fp16 entry (warp votes -> a stamp in shared memory, released by the e_full arrive) does
 //     not issue O += E Y; its buffers are released by plain arrives.  98-99 % of the tiles at BASELINE.json configs[3].
-// GNGF_DEBUG_NO_SKIP=1 turns both off (tests: the results do not change -- dh bit for bit); gngf_hpd_stream_bwd_stats counts
-// the tiles that issued their second product (bench.py: executed FLOPs).
+//   * SCREENING: the first of the three split products of S, X_hi Y_hi^T, is within errv[u] = 2^-9 |h_u| max|W3 row| of
+//     their sum (hpd_stream_bwd_errv_kernel).  A work item in screening mode issues only that product per tile; the epilogue
+//     threads bound their arguments from it (+ errv), vote (v_full, a named barrier among themselves), and a tile nobody
+//     objects to is dropped there and then -- nothing written, nothing more issued.  The other tiles get the two remaining
+//     products into the same accumulator (s2_full) and the exact epilogue.  The mode is adaptive per item: see the issuer.
+// GNGF_DEBUG_NO_SKIP=1 turns all of it off (tests: the results do not change -- dh bit for bit); gngf_hpd_stream_bwd_stats
+// counts tiles / tiles with all three logit products / tiles that issued their second product (bench.py: executed FLOPs).
 #include <algorithm>
 
 #include <cuda_fp16.h>
