@@ -77,6 +77,17 @@ def test_host_side_argument_validation_needs_no_gpu():
         FusedAdam([p], lr=-1.0)
 
 
+def test_streaming_backward_workspace_and_stats_entry_points():
+    """The workspace of the streaming backward holds five per-node vectors (a, -max log2e, column offset, sign, and the
+    screening product's error bound), the dlogits of the K selected slots and the device scalars; the statistics entry
+    point rejects a null buffer before it touches the device."""
+    lib = pkg.load()
+    for U, K in ((1, 1), (130, 4), (173400, 4), (29972809, 8)):
+        U4 = (U + 3) // 4 * 4
+        assert lib.gngf_hpd_stream_bwd_workspace_floats(U, K) == 5 * U4 + U * K + 16
+    assert lib.gngf_hpd_stream_bwd_stats(None, 0) == -1
+
+
 def test_active_node_and_split_loss_entry_points_validate_on_the_host():
     """k11_active_nodes.cu / gngf_loss_parts / the *_enc and *_nodes variants: sizes and bad arguments are answered on
     the host, before any launch."""
